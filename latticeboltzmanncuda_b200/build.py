@@ -1,0 +1,46 @@
+"""Builds liblbm_b200.so (hand-written sm_100a kernels + the C ABI) in-tree with nvcc."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "liblbm_b200.so")
+SOURCES = ["lbm_kernels.cu", "lbm_capi.cu", "lbm_tma.cu", "lbm_geometry.cu"]
+HEADERS = ["d3q.h", "lbm_device.h", os.path.join("..", "..", "include", "lbm_b200.h")]
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def sources():
+    return [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def is_stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in sources() + HEADERS]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build_native(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a -> latticeboltzmanncuda_b200/liblbm_b200.so"""
+    if not force and not is_stale():
+        return LIB
+    cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+           "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-o", LIB] + sources()
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,732 @@
+// lbm_capi.cu -- the C ABI of include/lbm_b200.h: handle, device memory, host<->device
+// transfers, and the step driver that replaces Lattice::simulate* (the reference allocates a
+// second lattice, copies the whole lattice and frees the old one twice per step,
+// simulation/source/Lattice.cpp:115-210; here the two population buffers are allocated once
+// and only their roles swap).
+#include "../../include/lbm_b200.h"
+#include "lbm_device.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace lbm;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? LBM_ERR_NOMEM : LBM_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                               \
+    } while (0)
+
+constexpr size_t STAGING_BYTES = size_t(256) << 20;
+constexpr int AOS_BYTES = 144;     // sizeof(LatticePoint), simulation/include/LatticePoint.h:9-17
+constexpr int TABLE_BYTES = 380;   // sizeof(ReflectionValues), LatticePoint.h:3-7
+
+}  // namespace
+
+struct lbm_lattice_s {
+    lbm_config cfg;
+    Geom g;
+    int device = 0;
+    cudaStream_t stream = nullptr, side = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_side = nullptr, ev_main = nullptr;
+    float* buf[2] = {nullptr, nullptr};
+    int cur = 0;
+    bool pending_commit = false;
+    uint32_t* solid = nullptr;       // padded bit mask
+    bool any_solid = false;          // some bit set (geometry or wall ghosts)
+    uint8_t* solid_bytes = nullptr;  // nx*ny*nz (+2 planes) scratch
+    uint32_t *tmask = nullptr, *tprefix = nullptr, *toff = nullptr, *reflected = nullptr;
+    Link* links = nullptr;
+    size_t nlinks = 0;
+    double* force = nullptr;         // 3 doubles
+    bool force_on = false;
+    int src_on = 0;
+    int src_lo[3] = {0, 0, 0}, src_hi[3] = {0, 0, 0};
+    float src_f[27] = {0};
+    double* diag = nullptr;          // 4 doubles
+    unsigned* flag = nullptr;
+    void* staging = nullptr;
+    long long launches = 0;
+
+    size_t pop_bytes() const { return (size_t)g.np * sizeof(float); }
+    size_t state_bytes() const { return pop_bytes() * (size_t)cfg.q; }
+    size_t mask_words() const { return (size_t)g.xp * g.yp * g.wz; }
+};
+
+namespace {
+
+int use(lbm_handle h)
+{
+    if (!h) return fail(LBM_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->device));
+    return LBM_OK;
+}
+
+int ensure_staging(lbm_handle h)
+{
+    if (!h->staging) CK(cudaMalloc(&h->staging, STAGING_BYTES));
+    return LBM_OK;
+}
+
+__global__ void any_nonzero_kernel(const uint32_t* w, size_t n, unsigned* flag)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool nz = (i < n) && w[i] != 0u;
+    if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+
+int rebuild_mask(lbm_handle h, const uint8_t* dev_bytes, int has_x_ghost)
+{
+    if (!h->solid) CK(cudaMalloc(&h->solid, h->mask_words() * sizeof(uint32_t)));
+    CK(launch_build_mask(dev_bytes, has_x_ghost, h->solid, h->g, h->cfg.bc, h->stream));
+    if (!h->flag) CK(cudaMalloc(&h->flag, sizeof(unsigned)));
+    CK(cudaMemsetAsync(h->flag, 0, sizeof(unsigned), h->stream));
+    const size_t n = h->mask_words();
+    any_nonzero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->solid, n, h->flag);
+    CK(cudaGetLastError());
+    unsigned f = 0;
+    CK(cudaMemcpyAsync(&f, h->flag, sizeof f, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->any_solid = f != 0;
+    return LBM_OK;
+}
+
+bool has_wall(const lbm_config& c) { return c.bc[0] == LBM_BC_WALL || c.bc[1] == LBM_BC_WALL || c.bc[2] == LBM_BC_WALL; }
+
+void fill_params(lbm_handle h, StepParams& p, unsigned phases, int x0, int x1)
+{
+    std::memset(&p, 0, sizeof p);
+    p.fin = h->buf[h->cur];
+    p.fout = h->buf[h->cur ^ 1];
+    p.g = h->g;
+    p.x0 = x0; p.x1 = x1;
+    p.tau = h->cfg.tau;
+    p.inv_tau = 1.0f / h->cfg.tau;
+    p.phases = phases;
+    p.boundary_mode = h->cfg.boundary_mode;
+    p.solid = h->any_solid ? h->solid : nullptr;
+    if (h->nlinks) {
+        p.tmask = h->tmask; p.tprefix = h->tprefix; p.toff = h->toff; p.links = h->links;
+    }
+    p.force = (h->force_on && (h->nlinks || h->cfg.boundary_mode == LBM_BOUNDARY_BOUNCE_BACK)) ? h->force : nullptr;
+    p.force_mode = h->cfg.force_mode;
+    p.src_on = h->src_on;
+    for (int a = 0; a < 3; ++a) { p.src_lo[a] = h->src_lo[a]; p.src_hi[a] = h->src_hi[a]; p.bc[a] = h->cfg.bc[a]; }
+    std::memcpy(p.src_f, h->src_f, sizeof p.src_f);
+    std::memcpy(p.wall_u, h->cfg.wall_u, sizeof p.wall_u);
+    p.wall_moving = 0;
+    for (int i = 0; i < 6; ++i)
+        for (int a = 0; a < 3; ++a)
+            if (h->cfg.wall_u[i][a] != 0.0f) p.wall_moving = 1;
+}
+
+// is the cheap kernel (pull + collide on an all-fluid lattice) enough for these phases?
+bool fast_path_ok(lbm_handle h, unsigned phases)
+{
+    if (!(phases & PH_STREAM) || !(phases & PH_COLLIDE)) return false;
+    if (h->any_solid) return false;
+    if ((phases & PH_REFLECT) && h->nlinks) return false;
+    if ((phases & PH_SOURCE) && h->src_on) return false;
+    return true;
+}
+
+int launch_range(lbm_handle h, unsigned phases, int x0, int x1, cudaStream_t s)
+{
+    StepParams p;
+    fill_params(h, p, phases, x0, x1);
+    LaunchCfg c;
+    c.q = h->cfg.q;
+    c.moment_mode = h->cfg.moment_mode;
+    c.eq64 = h->cfg.eq_precision == LBM_EQ_FP64;
+    c.general = fast_path_ok(h, phases) ? 0 : 1;
+    CK(launch_step(c, p, s));
+    h->launches += 1;
+    return LBM_OK;
+}
+
+int fill_ghosts(lbm_handle h, bool include_x)
+{
+    const int* bc = h->cfg.bc;
+    int n = 0;
+    if (include_x && bc[0] == LBM_BC_PERIODIC) ++n;
+    if (bc[1] == LBM_BC_PERIODIC) ++n;
+    if (bc[2] == LBM_BC_PERIODIC) ++n;
+    if (!n) return LBM_OK;
+    CK(launch_fill_ghosts(h->buf[h->cur], h->g, h->cfg.q, bc, include_x, h->stream));
+    h->launches += n;
+    return LBM_OK;
+}
+
+int one_step(lbm_handle h, unsigned phases)
+{
+    if (h->pending_commit) return fail(LBM_ERR_STATE, "lbm_step_range in flight: call lbm_step_commit first");
+    if (phases & PH_STREAM) {
+        int rc = fill_ghosts(h, true);
+        if (rc) return rc;
+    }
+    int rc = launch_range(h, phases, 0, h->g.nx, h->stream);
+    if (rc) return rc;
+    h->cur ^= 1;
+    return LBM_OK;
+}
+
+}  // namespace
+
+// ---- C ABI -------------------------------------------------------------------------------------
+
+extern "C" {
+
+LBM_API const char* lbm_last_error(void) { return g_last_error.c_str(); }
+LBM_API const char* lbm_version(void) { return "lbm_b200 0.1 (sm_100a)"; }
+
+LBM_API int lbm_config_default(lbm_config* cfg)
+{
+    if (!cfg) return fail(LBM_ERR_INVALID, "null config");
+    std::memset(cfg, 0, sizeof *cfg);
+    cfg->nx = cfg->ny = cfg->nz = 1;
+    cfg->q = 27;
+    cfg->tau = 1.0f;
+    cfg->moment_mode = LBM_MOMENT_REFERENCE;
+    cfg->eq_precision = LBM_EQ_FP64;
+    cfg->boundary_mode = LBM_BOUNDARY_REFLECT;
+    cfg->force_mode = LBM_FORCE_REFERENCE_SLOT_INDEX;
+    cfg->engine = LBM_ENGINE_AUTO;
+    cfg->device = -1;
+    return LBM_OK;
+}
+
+LBM_API int lbm_create(const lbm_config* cfg, lbm_handle* out)
+{
+    if (!cfg || !out) return fail(LBM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->nx < 1 || cfg->ny < 1 || cfg->nz < 1) return fail(LBM_ERR_INVALID, "lattice extents must be >= 1");
+    if (cfg->nx > 65535 || cfg->ny > 65535 * 8) return fail(LBM_ERR_INVALID, "lattice extent too large for one launch");
+    if (cfg->q != 19 && cfg->q != 27) return fail(LBM_ERR_INVALID, "q must be 19 or 27");
+    if (!(cfg->tau > 0.0f)) return fail(LBM_ERR_INVALID, "tau must be positive");
+    for (int a = 0; a < 3; ++a) {
+        if (cfg->bc[a] < 0 || cfg->bc[a] > 3) return fail(LBM_ERR_INVALID, "bad bc");
+        if (cfg->bc[a] == LBM_BC_HALO && a != 0) return fail(LBM_ERR_INVALID, "LBM_BC_HALO is for the x axis only");
+    }
+    if (cfg->engine != LBM_ENGINE_AUTO && cfg->engine != LBM_ENGINE_PULL2)
+        return fail(LBM_ERR_UNSUPPORTED, "engine %d is not built in this version", cfg->engine);
+    const Geom g = make_geom(cfg->nx, cfg->ny, cfg->nz);
+    if (g.np >= (1ll << 32)) return fail(LBM_ERR_INVALID, "more than 2^32 padded cells per slab");
+
+    int dev = cfg->device;
+    if (dev < 0) CK(cudaGetDevice(&dev));
+    CK(cudaSetDevice(dev));
+
+    lbm_lattice_s* h = new (std::nothrow) lbm_lattice_s();
+    if (!h) return fail(LBM_ERR_NOMEM, "host allocation failed");
+    h->cfg = *cfg;
+    h->cfg.device = dev;
+    h->g = g;
+    h->device = dev;
+    auto bail = [&](int rc) { lbm_destroy(h); return rc; };
+#define CKB(call)                                                                          \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return bail(fail(e_ == cudaErrorMemoryAllocation ? LBM_ERR_NOMEM : LBM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_))); \
+    } while (0)
+    CKB(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKB(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CKB(cudaEventCreate(&h->ev0));
+    CKB(cudaEventCreate(&h->ev1));
+    CKB(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
+    CKB(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) {
+        CKB(cudaMalloc(&h->buf[b], h->state_bytes()));
+        CKB(cudaMemsetAsync(h->buf[b], 0, h->state_bytes(), h->stream));
+    }
+    CKB(cudaMalloc(&h->force, 3 * sizeof(double)));
+    CKB(cudaMemsetAsync(h->force, 0, 3 * sizeof(double), h->stream));
+    CKB(cudaMalloc(&h->diag, 4 * sizeof(double)));
+#undef CKB
+    if (has_wall(h->cfg)) {
+        int rc = rebuild_mask(h, nullptr, 0);   // wall ghosts are solid bits even without geometry
+        if (rc) return bail(rc);
+    }
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return bail(fail(LBM_ERR_CUDA, "create: %s", cudaGetErrorString(e)));
+    *out = h;
+    return LBM_OK;
+}
+
+LBM_API int lbm_destroy(lbm_handle h)
+{
+    if (!h) return LBM_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->side) cudaStreamSynchronize(h->side);
+    for (int b = 0; b < 2; ++b) cudaFree(h->buf[b]);
+    cudaFree(h->solid); cudaFree(h->solid_bytes); cudaFree(h->tmask); cudaFree(h->tprefix); cudaFree(h->toff);
+    cudaFree(h->reflected); cudaFree(h->links); cudaFree(h->force); cudaFree(h->diag); cudaFree(h->flag);
+    cudaFree(h->staging);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_side) cudaEventDestroy(h->ev_side);
+    if (h->ev_main) cudaEventDestroy(h->ev_main);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->side) cudaStreamDestroy(h->side);
+    delete h;
+    return LBM_OK;
+}
+
+LBM_API int lbm_sync(lbm_handle h)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->side));
+    CK(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+LBM_API int lbm_get_layout(lbm_handle h, lbm_layout* o)
+{
+    if (!h || !o) return fail(LBM_ERR_INVALID, "null argument");
+    o->nx = h->g.nx; o->ny = h->g.ny; o->nz = h->g.nz; o->q = h->cfg.q;
+    o->xp = h->g.xp; o->yp = h->g.yp; o->zp = h->g.zp; o->pad_z = PAD_Z;
+    o->plane = h->g.plane; o->pop_stride = h->g.np;
+    o->state_bytes = (int64_t)h->state_bytes();
+    o->n_buffers = 2;
+    return LBM_OK;
+}
+
+// ---- transfers --------------------------------------------------------------------------------------
+
+LBM_API int lbm_upload_aos(lbm_handle h, const void* cells, size_t count)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    const Geom& g = h->g;
+    const size_t n = (size_t)g.nx * g.ny * g.nz;
+    if (!cells || count != n) return fail(LBM_ERR_INVALID, "upload_aos: expected %zu records, got %zu", n, count);
+    if ((rc = ensure_staging(h))) return rc;
+    if (!h->solid_bytes) CK(cudaMalloc(&h->solid_bytes, n + 2 * (size_t)g.ny * g.nz));
+    const size_t per_plane = (size_t)g.ny * g.nz * AOS_BYTES;
+    if (per_plane > STAGING_BYTES) return fail(LBM_ERR_UNSUPPORTED, "one x-plane of AoS records exceeds the staging buffer");
+    const int chunk = (int)std::max<size_t>(1, STAGING_BYTES / per_plane);
+    for (int x0 = 0; x0 < g.nx; x0 += chunk) {
+        const int nxc = std::min(chunk, g.nx - x0);
+        CK(cudaMemcpyAsync(h->staging, (const char*)cells + (size_t)x0 * per_plane, (size_t)nxc * per_plane,
+                           cudaMemcpyHostToDevice, h->stream));
+        CK(launch_unpack_aos(h->staging, h->buf[h->cur], h->solid_bytes, g, h->cfg.q, x0, nxc, h->stream));
+        CK(cudaStreamSynchronize(h->stream));   // staging is reused by the next chunk
+    }
+    return rebuild_mask(h, h->solid_bytes, 0);
+}
+
+LBM_API int lbm_download_aos(lbm_handle h, void* cells, size_t count)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    const Geom& g = h->g;
+    const size_t n = (size_t)g.nx * g.ny * g.nz;
+    if (!cells || count != n) return fail(LBM_ERR_INVALID, "download_aos: expected %zu records, got %zu", n, count);
+    if ((rc = ensure_staging(h))) return rc;
+    const size_t per_plane = (size_t)g.ny * g.nz * AOS_BYTES;
+    if (per_plane > STAGING_BYTES) return fail(LBM_ERR_UNSUPPORTED, "one x-plane of AoS records exceeds the staging buffer");
+    const int chunk = (int)std::max<size_t>(1, STAGING_BYTES / per_plane);
+    for (int x0 = 0; x0 < g.nx; x0 += chunk) {
+        const int nxc = std::min(chunk, g.nx - x0);
+        CK(cudaMemsetAsync(h->staging, 0, (size_t)nxc * per_plane, h->stream));   // pointer fields come back null
+        CK(launch_pack_aos(h->staging, h->buf[h->cur], h->solid, h->reflected, g, h->cfg.q, x0, nxc, h->stream));
+        CK(cudaMemcpyAsync((char*)cells + (size_t)x0 * per_plane, h->staging, (size_t)nxc * per_plane,
+                           cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return LBM_OK;
+}
+
+LBM_API int lbm_upload_f_soa(lbm_handle h, const float* f)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    if (!f) return fail(LBM_ERR_INVALID, "null buffer");
+    if ((rc = ensure_staging(h))) return rc;
+    const Geom& g = h->g;
+    const size_t per_plane = (size_t)g.ny * g.nz * sizeof(float);
+    if (per_plane > STAGING_BYTES) return fail(LBM_ERR_UNSUPPORTED, "one x-plane exceeds the staging buffer");
+    const int chunk = (int)std::max<size_t>(1, STAGING_BYTES / 2 / per_plane);
+    // two half-buffers alternate so that the H2D copy of a chunk overlaps the scatter of the previous one
+    int slot = 0;
+    for (int q = 0; q < h->cfg.q; ++q) {
+        const float* src = f + (size_t)q * g.nx * g.ny * g.nz;
+        for (int x0 = 0; x0 < g.nx; x0 += chunk) {
+            const int nxc = std::min(chunk, g.nx - x0);
+            float* st = (float*)((char*)h->staging + (size_t)slot * (STAGING_BYTES / 2));
+            cudaStream_t s = slot ? h->side : h->stream;
+            CK(cudaMemcpyAsync(st, src + (size_t)x0 * g.ny * g.nz, (size_t)nxc * per_plane, cudaMemcpyHostToDevice, s));
+            CK(launch_scatter_dense(st, h->buf[h->cur] + (size_t)q * g.np, g, x0, nxc, s));
+            slot ^= 1;
+            if (slot == 0) { CK(cudaStreamSynchronize(h->stream)); CK(cudaStreamSynchronize(h->side)); }
+        }
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->side));
+    return LBM_OK;
+}
+
+LBM_API int lbm_download_f_soa(lbm_handle h, float* f)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    if (!f) return fail(LBM_ERR_INVALID, "null buffer");
+    if ((rc = ensure_staging(h))) return rc;
+    const Geom& g = h->g;
+    const size_t per_plane = (size_t)g.ny * g.nz * sizeof(float);
+    if (per_plane > STAGING_BYTES) return fail(LBM_ERR_UNSUPPORTED, "one x-plane exceeds the staging buffer");
+    const int chunk = (int)std::max<size_t>(1, STAGING_BYTES / per_plane);
+    CK(cudaStreamSynchronize(h->side));
+    for (int q = 0; q < h->cfg.q; ++q) {
+        float* dst = f + (size_t)q * g.nx * g.ny * g.nz;
+        for (int x0 = 0; x0 < g.nx; x0 += chunk) {
+            const int nxc = std::min(chunk, g.nx - x0);
+            CK(launch_gather_dense((float*)h->staging, h->buf[h->cur] + (size_t)q * g.np, g, x0, nxc, h->stream));
+            CK(cudaMemcpyAsync(dst + (size_t)x0 * g.ny * g.nz, h->staging, (size_t)nxc * per_plane, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        }
+    }
+    return LBM_OK;
+}
+
+LBM_API int lbm_set_solid_mask(lbm_handle h, const uint8_t* solid, int x_ghost_planes)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    const Geom& g = h->g;
+    const size_t per = (size_t)g.ny * g.nz;
+    const size_t n = per * (size_t)g.nx;
+    if (!h->solid_bytes) CK(cudaMalloc(&h->solid_bytes, n + 2 * per));
+    if (!solid) {
+        CK(cudaMemsetAsync(h->solid_bytes, 0, n + 2 * per, h->stream));
+        return rebuild_mask(h, h->solid_bytes, 1);
+    }
+    const size_t bytes = x_ghost_planes ? n + 2 * per : n;
+    CK(cudaMemcpyAsync(h->solid_bytes, solid, bytes, cudaMemcpyHostToDevice, h->stream));
+    return rebuild_mask(h, h->solid_bytes, x_ghost_planes ? 1 : 0);
+}
+
+LBM_API int lbm_get_solid_mask(lbm_handle h, uint8_t* solid)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    if (!solid) return fail(LBM_ERR_INVALID, "null buffer");
+    const Geom& g = h->g;
+    const size_t n = (size_t)g.nx * g.ny * g.nz;
+    if (!h->solid) { std::memset(solid, 0, n); return LBM_OK; }
+    if (!h->solid_bytes) CK(cudaMalloc(&h->solid_bytes, n + 2 * (size_t)g.ny * g.nz));
+    CK(launch_mask_to_bytes(h->solid, h->solid_bytes, g, h->stream));
+    CK(cudaMemcpyAsync(solid, h->solid_bytes, n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+// Turns the reference's per-solid-cell scatter tables into per-fluid-cell gather lists.
+LBM_API int lbm_set_reflection_table(lbm_handle h, const void* tables, const int64_t* cell_index, int n)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!tables || !cell_index))) return fail(LBM_ERR_INVALID, "bad reflection table arguments");
+    if (h->cfg.bc[0] == LBM_BC_HALO && n > 0)
+        return fail(LBM_ERR_UNSUPPORTED, "table reflection is not available on halo (slab) handles yet");
+    const Geom& g = h->g;
+    const long long ncell = (long long)g.nx * g.ny * g.nz;
+    struct HostLink { uint32_t tgt; Link l; long long order; };
+    std::vector<HostLink> hl;
+    const size_t words = h->mask_words();
+    std::vector<uint32_t> refl(words, 0u);
+    for (int t = 0; t < n; ++t) {
+        const long long k = cell_index[t];
+        if (k < 0 || k >= ncell) return fail(LBM_ERR_INVALID, "reflection table %d: cell index out of range", t);
+        const int sx = (int)(k / ((long long)g.ny * g.nz));
+        const int rem = (int)(k % ((long long)g.ny * g.nz));
+        const int sy = rem / g.nz, sz = rem % g.nz;
+        const unsigned char* rec = (const unsigned char*)tables + (size_t)t * TABLE_BYTES;
+        int32_t dirs[14];
+        float w[81];
+        std::memcpy(dirs, rec, sizeof dirs);
+        std::memcpy(w, rec + sizeof dirs, sizeof w);
+        const long long scell = g.cell(sx, sy, sz);
+        refl[(size_t)(scell >> 5)] |= 1u << (scell & 31);
+        for (int s = 1; s < 81; ++s) {      // slot 0 is never read (SimCalcFuncs.cu:164)
+            const int d = (int)(((uint32_t)dirs[s / 6] >> (5 * (s % 6))) & 0x1Fu);   // SimCalcFuncs.cu:18-30
+            if (d == 0) continue;
+            if (d >= 27) return fail(LBM_ERR_INVALID, "reflection table %d slot %d: direction %d", t, s, d);
+            const int j = s / 3;
+            if (d >= h->cfg.q || j >= h->cfg.q) continue;
+            const int tx = sx + dir_c(d, 0), ty = sy + dir_c(d, 1), tz = sz + dir_c(d, 2);
+            if (tx < 0 || ty < 0 || tz < 0 || tx >= g.nx || ty >= g.ny || tz >= g.nz) continue;   // SimCalcFuncs.cu:175
+            HostLink e;
+            e.tgt = (uint32_t)g.cell(tx, ty, tz);
+            e.l.src_cell = (uint32_t)scell;
+            e.l.j = (uint8_t)j; e.l.d = (uint8_t)d; e.l.slot = (uint8_t)s; e.l.pad = 0;
+            e.l.w = w[s];
+            e.order = k * 81 + s;
+            hl.push_back(e);
+        }
+    }
+    std::sort(hl.begin(), hl.end(), [](const HostLink& a, const HostLink& b) {
+        return a.tgt != b.tgt ? a.tgt < b.tgt : a.order < b.order;
+    });
+    std::vector<uint32_t> tmask(words, 0u), tprefix(words, 0u), toff;
+    std::vector<Link> links(hl.size());
+    for (size_t i = 0; i < hl.size(); ++i) {
+        links[i] = hl[i].l;
+        if (i == 0 || hl[i].tgt != hl[i - 1].tgt) {
+            toff.push_back((uint32_t)i);
+            tmask[hl[i].tgt >> 5] |= 1u << (hl[i].tgt & 31);
+        }
+    }
+    toff.push_back((uint32_t)hl.size());
+    uint32_t run = 0;
+    for (size_t wi = 0; wi < words; ++wi) { tprefix[wi] = run; run += (uint32_t)__builtin_popcount(tmask[wi]); }
+
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->tmask); cudaFree(h->tprefix); cudaFree(h->toff); cudaFree(h->links); cudaFree(h->reflected);
+    h->tmask = h->tprefix = h->toff = h->reflected = nullptr;
+    h->links = nullptr;
+    h->nlinks = 0;
+    CK(cudaMalloc(&h->reflected, words * sizeof(uint32_t)));
+    CK(cudaMemcpy(h->reflected, refl.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!links.empty()) {
+        CK(cudaMalloc(&h->tmask, words * sizeof(uint32_t)));
+        CK(cudaMalloc(&h->tprefix, words * sizeof(uint32_t)));
+        CK(cudaMalloc(&h->toff, toff.size() * sizeof(uint32_t)));
+        CK(cudaMalloc(&h->links, links.size() * sizeof(Link)));
+        CK(cudaMemcpy(h->tmask, tmask.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->tprefix, tprefix.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->toff, toff.data(), toff.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->links, links.data(), links.size() * sizeof(Link), cudaMemcpyHostToDevice));
+        h->nlinks = links.size();
+    }
+    return LBM_OK;
+}
+
+LBM_API int lbm_set_source(lbm_handle h, int kind, const int32_t lo[3], const int32_t hi[3], const float f[27])
+{
+    if (!h) return fail(LBM_ERR_INVALID, "null handle");
+    if (kind == LBM_SOURCE_NONE) { h->src_on = 0; return LBM_OK; }
+    if (kind != LBM_SOURCE_BOX || !lo || !hi || !f) return fail(LBM_ERR_INVALID, "bad source arguments");
+    h->src_on = 1;
+    for (int a = 0; a < 3; ++a) { h->src_lo[a] = lo[a]; h->src_hi[a] = hi[a]; }
+    for (int i = 0; i < 27; ++i) h->src_f[i] = (i < h->cfg.q) ? f[i] : 0.0f;
+    return LBM_OK;
+}
+
+LBM_API int lbm_set_force_accumulator(lbm_handle h, int enable, const float init[3])
+{
+    int rc = use(h);
+    if (rc) return rc;
+    h->force_on = enable != 0;
+    double v[3] = {0.0, 0.0, 0.0};
+    if (init) for (int a = 0; a < 3; ++a) v[a] = init[a];
+    CK(cudaMemcpyAsync(h->force, v, sizeof v, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+LBM_API int lbm_get_force(lbm_handle h, float out[3])
+{
+    int rc = use(h);
+    if (rc) return rc;
+    if (!out) return fail(LBM_ERR_INVALID, "null buffer");
+    double v[3];
+    CK(cudaMemcpyAsync(v, h->force, sizeof v, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int a = 0; a < 3; ++a) out[a] = (float)v[a];
+    return LBM_OK;
+}
+
+// ---- stepping -----------------------------------------------------------------------------------------
+
+LBM_API int lbm_prime_points(lbm_handle h) { return use(h); }
+
+LBM_API int lbm_step_phases(lbm_handle h, int n, unsigned phases)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    if (n < 0 || (phases & ~15u) || phases == 0) return fail(LBM_ERR_INVALID, "bad step arguments");
+    for (int s = 0; s < n; ++s)
+        if ((rc = one_step(h, phases))) return rc;
+    return LBM_OK;
+}
+
+LBM_API int lbm_step(lbm_handle h, int n) { return lbm_step_phases(h, n, LBM_PHASE_ALL); }
+LBM_API int lbm_stream(lbm_handle h) { return lbm_step_phases(h, 1, LBM_PHASE_STREAM); }
+LBM_API int lbm_reflect(lbm_handle h) { return lbm_step_phases(h, 1, LBM_PHASE_REFLECT); }
+LBM_API int lbm_collide(lbm_handle h) { return lbm_step_phases(h, 1, LBM_PHASE_COLLIDE); }
+LBM_API int lbm_source(lbm_handle h) { return lbm_step_phases(h, 1, LBM_PHASE_SOURCE); }
+
+LBM_API int lbm_step_timed(lbm_handle h, int n, unsigned phases, float* ms, int* launches)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    if (!ms) return fail(LBM_ERR_INVALID, "null ms");
+    const long long l0 = h->launches;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    rc = lbm_step_phases(h, n, phases);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaEventSynchronize(h->ev1));
+    CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    if (launches) *launches = (int)(h->launches - l0);
+    return LBM_OK;
+}
+
+// ---- diagnostics ------------------------------------------------------------------------------------------
+
+LBM_API int lbm_moments(lbm_handle h, float* rho, float* ux, float* uy, float* uz)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    const Geom& g = h->g;
+    const size_t n = (size_t)g.nx * g.ny * g.nz;
+    float* dev = nullptr;
+    CK(cudaMalloc(&dev, 4 * n * sizeof(float)));
+    cudaError_t e = launch_moments(h->buf[h->cur], g, h->cfg.q, h->cfg.moment_mode, dev, dev + n, dev + 2 * n, dev + 3 * n, h->stream);
+    float* outs[4] = {rho, ux, uy, uz};
+    for (int k = 0; k < 4 && e == cudaSuccess; ++k)
+        if (outs[k]) e = cudaMemcpyAsync(outs[k], dev + (size_t)k * n, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "moments: %s", cudaGetErrorString(e));
+    return LBM_OK;
+}
+
+static int mass_momentum(lbm_handle h, double out4[4])
+{
+    int rc = use(h);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(h->diag, 0, 4 * sizeof(double), h->stream));
+    CK(launch_mass_momentum(h->buf[h->cur], h->g, h->cfg.q, h->diag, h->stream));
+    CK(cudaMemcpyAsync(out4, h->diag, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+LBM_API int lbm_mass(lbm_handle h, double* mass)
+{
+    if (!mass) return fail(LBM_ERR_INVALID, "null buffer");
+    double v[4];
+    int rc = mass_momentum(h, v);
+    if (rc) return rc;
+    *mass = v[0];
+    return LBM_OK;
+}
+
+LBM_API int lbm_momentum(lbm_handle h, double out[3])
+{
+    if (!out) return fail(LBM_ERR_INVALID, "null buffer");
+    double v[4];
+    int rc = mass_momentum(h, v);
+    if (rc) return rc;
+    out[0] = v[1]; out[1] = v[2]; out[2] = v[3];
+    return LBM_OK;
+}
+
+// ---- slab decomposition ------------------------------------------------------------------------------------
+
+static int plane_ptr(lbm_handle h, float* base, int q, int xp, void** dev_ptr, size_t* bytes)
+{
+    if (!h || !dev_ptr) return fail(LBM_ERR_INVALID, "null argument");
+    if (q < 0 || q >= h->cfg.q || xp < 0 || xp >= h->g.xp) return fail(LBM_ERR_INVALID, "plane (%d, %d) out of range", q, xp);
+    *dev_ptr = base + (size_t)q * h->g.np + (size_t)xp * h->g.plane;
+    if (bytes) *bytes = (size_t)h->g.plane * sizeof(float);
+    return LBM_OK;
+}
+
+LBM_API int lbm_plane_ptr(lbm_handle h, int q, int xp, void** dev_ptr, size_t* bytes)
+{
+    if (!h) return fail(LBM_ERR_INVALID, "null handle");
+    return plane_ptr(h, h->buf[h->cur], q, xp, dev_ptr, bytes);
+}
+
+LBM_API int lbm_next_plane_ptr(lbm_handle h, int q, int xp, void** dev_ptr, size_t* bytes)
+{
+    if (!h) return fail(LBM_ERR_INVALID, "null handle");
+    return plane_ptr(h, h->buf[h->cur ^ 1], q, xp, dev_ptr, bytes);
+}
+
+LBM_API int lbm_face_populations(lbm_handle h, int side, int32_t* qs, int* nq)
+{
+    if (!h || !qs || !nq) return fail(LBM_ERR_INVALID, "null argument");
+    int n = 0;
+    for (int i = 0; i < h->cfg.q; ++i)
+        if (dir_c(i, 0) == (side ? 1 : -1)) qs[n++] = i;
+    *nq = n;
+    return LBM_OK;
+}
+
+LBM_API int lbm_get_stream(lbm_handle h, void** stream)
+{
+    if (!h || !stream) return fail(LBM_ERR_INVALID, "null argument");
+    *stream = (void*)h->stream;
+    return LBM_OK;
+}
+
+LBM_API int lbm_fill_ghosts(lbm_handle h)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    return fill_ghosts(h, h->cfg.bc[0] != LBM_BC_HALO);
+}
+
+LBM_API int lbm_step_range(lbm_handle h, unsigned phases, int x0, int x1, int on_side_stream)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    if (x0 < 0 || x1 > h->g.nx || x0 > x1 || (phases & ~15u) || phases == 0) return fail(LBM_ERR_INVALID, "bad range");
+    if (on_side_stream) {
+        // the side stream starts after everything queued so far on the main stream
+        if (!h->pending_commit || true) {
+            CK(cudaEventRecord(h->ev_main, h->stream));
+            CK(cudaStreamWaitEvent(h->side, h->ev_main, 0));
+        }
+        rc = launch_range(h, phases, x0, x1, h->side);
+    } else {
+        rc = launch_range(h, phases, x0, x1, h->stream);
+    }
+    if (rc) return rc;
+    h->pending_commit = true;
+    return LBM_OK;
+}
+
+LBM_API int lbm_step_commit(lbm_handle h)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    if (!h->pending_commit) return fail(LBM_ERR_STATE, "nothing to commit");
+    // the main stream continues only after the side stream's share of this step
+    CK(cudaEventRecord(h->ev_side, h->side));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_side, 0));
+    h->cur ^= 1;
+    h->pending_commit = false;
+    return LBM_OK;
+}
+
+}  // extern "C"

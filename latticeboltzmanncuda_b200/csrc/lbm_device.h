@@ -1,0 +1,113 @@
+// lbm_device.h -- layout of the lattice in HBM and the launch interface of the kernels.
+//
+// Populations live in a padded structure-of-arrays  f[q][xp][yp][zp]  (fp32, z fastest):
+//   * one ghost layer on every side (xp = nx+2, yp = ny+2); ghost cells implement the
+//     domain-edge rule, so the hot kernel has no bounds tests: zero-inflow ghosts hold 0
+//     (the reference's rule, simulation/source/SimCalcFuncs.cu:37-40,87-94), periodic
+//     ghosts are refreshed from the opposite face, wall ghosts are solid bits, halo ghosts
+//     come from the neighbouring slab;
+//   * the first interior z sits at PAD_Z = 32 floats, so every interior row starts on a
+//     128-byte line and a warp's 32 lanes map to exactly one solid-mask word;
+//   * zp is a multiple of 32, so every row, plane and population starts 128-byte aligned.
+// Solid flags are one bit per padded cell: mask[xp][yp][zp/32].
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "d3q.h"
+
+namespace lbm {
+
+constexpr int PAD_Z = 32;
+
+enum : unsigned { PH_STREAM = 1u, PH_REFLECT = 2u, PH_COLLIDE = 4u, PH_SOURCE = 8u };
+
+struct Geom {
+    int nx, ny, nz;
+    int xp, yp, zp;       // padded extents
+    int wz;               // mask words per row = zp / 32
+    long long plane;      // yp * zp
+    long long np;         // xp * yp * zp  (floats per population)
+    __host__ __device__ long long cell(int x, int y, int z) const
+    {
+        return ((long long)(x + 1) * yp + (y + 1)) * zp + (z + PAD_Z);
+    }
+};
+
+inline Geom make_geom(int nx, int ny, int nz)
+{
+    Geom g;
+    g.nx = nx; g.ny = ny; g.nz = nz;
+    g.xp = nx + 2; g.yp = ny + 2;
+    g.zp = ((PAD_Z + nz + 1 + 31) / 32) * 32;
+    g.wz = g.zp / 32;
+    g.plane = (long long)g.yp * g.zp;
+    g.np = (long long)g.xp * g.plane;
+    return g;
+}
+
+// one reflection link: population j that streamed into solid cell S is handed to fluid
+// cell T = S + c_d as population d with weight w (reference: one (cell, slot) pair of
+// ReflectionValues, simulation/include/LatticePoint.h:3-7, applied at SimCalcFuncs.cu:177)
+struct Link {
+    uint32_t src_cell;    // padded cell index of S
+    uint8_t  j;           // population read at S (= slot / 3)
+    uint8_t  d;           // population written at T
+    uint8_t  slot;        // reference slot index (force bookkeeping)
+    uint8_t  pad;
+    float    w;
+};
+
+struct StepParams {
+    const float* fin;
+    float*       fout;
+    Geom  g;
+    int   x0, x1;             // interior plane range [x0, x1) this launch covers
+    float tau, inv_tau;
+    unsigned phases;
+    int   boundary_mode;      // 0 reflect (reference), 1 bounce-back
+    const uint32_t* solid;    // padded bit mask or nullptr
+    const uint32_t* tmask;    // link-target bits or nullptr
+    const uint32_t* tprefix;  // exclusive popcount prefix per mask word
+    const uint32_t* toff;     // CSR offsets per target cell
+    const Link*     links;
+    double* force;            // 3 doubles or nullptr
+    int   force_mode;
+    int   src_on;
+    int   src_lo[3], src_hi[3];
+    float src_f[27];
+    int   bc[3];
+    int   wall_moving;        // any wall_u component non-zero
+    float wall_u[6][3];
+};
+
+struct LaunchCfg {
+    int q;
+    int moment_mode;
+    int eq64;
+    int general;              // 0: pure stream+collide fluid fast path
+};
+
+// launches (all asynchronous on `stream`)
+cudaError_t launch_step(const LaunchCfg& cfg, const StepParams& p, cudaStream_t stream);
+
+cudaError_t launch_fill_ghosts(float* f, const Geom& g, int q, const int bc[3], bool include_x, cudaStream_t stream);
+
+// AoS (144-byte LatticePoint records, host order) <-> padded SoA; x range [x0, x0+nxc)
+cudaError_t launch_unpack_aos(const void* aos, float* f, uint8_t* solid_bytes, const Geom& g, int q, int x0, int nxc, cudaStream_t stream);
+cudaError_t launch_pack_aos(void* aos, const float* f, const uint32_t* solid, const uint32_t* reflected, const Geom& g, int q, int x0, int nxc, cudaStream_t stream);
+// dense [nxc][ny][nz] chunk of one population <-> padded
+cudaError_t launch_scatter_dense(const float* dense, float* fq, const Geom& g, int x0, int nxc, cudaStream_t stream);
+cudaError_t launch_gather_dense(float* dense, const float* fq, const Geom& g, int x0, int nxc, cudaStream_t stream);
+
+// solid bytes (host order, optionally with x ghost planes) -> padded bit mask incl. ghost bits
+cudaError_t launch_build_mask(const uint8_t* solid_bytes, int has_x_ghost, uint32_t* mask, const Geom& g, const int bc[3], cudaStream_t stream);
+cudaError_t launch_mask_to_bytes(const uint32_t* mask, uint8_t* solid_bytes, const Geom& g, cudaStream_t stream);
+
+// moments / reductions
+cudaError_t launch_moments(const float* f, const Geom& g, int q, int moment_mode, float* rho, float* ux, float* uy, float* uz, cudaStream_t stream);
+cudaError_t launch_mass_momentum(const float* f, const Geom& g, int q, double* out4, cudaStream_t stream);
+
+}  // namespace lbm

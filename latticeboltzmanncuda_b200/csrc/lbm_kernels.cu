@@ -1,0 +1,627 @@
+// lbm_kernels.cu -- sm_100a kernels of the per-timestep path.
+//
+// step_kernel fuses what the reference runs as four kernels with two whole-lattice copies
+// in between (simulation/source/Lattice.cpp:115-220 driving SimCalcFuncs.cu:79-215):
+//   pull-stream  ->  solid-boundary treatment  ->  BGK collide  ->  source
+// One thread owns one cell; a warp owns 32 consecutive z of one (x, y) row, so every one of
+// the 2*Q population accesses of a warp is a single contiguous 128-byte request.
+// Roofline: HBM.  Algorithmic traffic is 2*Q*4 bytes per cell update (152 B for D3Q19,
+// 216 B for D3Q27); the solid mask adds 1 bit per cell.
+#include "lbm_device.h"
+
+#include <cstdio>
+
+namespace lbm {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---- collision ---------------------------------------------------------------------------
+
+// Reference arithmetic (SimCalcFuncs.cu:100-155): fp32 moments accumulated in index order,
+// equilibrium promoted to double by the double literals, narrowed to float, float subtract,
+// float divide by the timescale.  Expression shapes are kept so that nvcc contracts them the
+// way it contracts the reference's.
+template <int Q, int MOMENT>
+__device__ __forceinline__ void collide_fp64(float (&f)[Q], float timescale)
+{
+    float density = 0.0f, ux = 0.0f, uy = 0.0f, uz = 0.0f;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        const float s = (MOMENT == 0) ? dir_split(i) : 1.0f;
+        density += f[i];
+        if (dir_c(i, 0) != 0) ux += f[i] * (float)dir_c(i, 0) * s;
+        if (dir_c(i, 1) != 0) uy += f[i] * (float)dir_c(i, 1) * s;
+        if (dir_c(i, 2) != 0) uz += f[i] * (float)dir_c(i, 2) * s;
+    }
+    if (density != 0.0) {
+        ux /= density; uy /= density; uz /= density;
+    }
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        float common_term = (((float)dir_c(i, 0) * ux) + ((float)dir_c(i, 1) * uy) + ((float)dir_c(i, 2) * uz));
+        float eq = dir_weight<Q>(i) * density *
+                   (1 + (3.0 * common_term) + (4.5 * common_term * common_term) - (1.5 * ((ux * ux) + (uy * uy) + (uz * uz))));
+        f[i] = f[i] + (eq - f[i]) / timescale;
+    }
+}
+
+// Throughput arithmetic: all fp32, opposite directions share the even part of the
+// equilibrium, relaxation by multiplication with 1/tau.
+template <int Q, int MOMENT>
+__device__ __forceinline__ void collide_fp32(float (&f)[Q], float inv_tau)
+{
+    float rho = f[0], mx = 0.0f, my = 0.0f, mz = 0.0f;
+#pragma unroll
+    for (int i = 1; i < Q; ++i) {
+        const float s = (MOMENT == 0) ? dir_split(i) : 1.0f;
+        rho += f[i];
+        if (dir_c(i, 0) != 0) mx = fmaf(f[i], (float)dir_c(i, 0) * s, mx);
+        if (dir_c(i, 1) != 0) my = fmaf(f[i], (float)dir_c(i, 1) * s, my);
+        if (dir_c(i, 2) != 0) mz = fmaf(f[i], (float)dir_c(i, 2) * s, mz);
+    }
+    const float inv_rho = (rho != 0.0f) ? 1.0f / rho : 1.0f;
+    const float ux = mx * inv_rho, uy = my * inv_rho, uz = mz * inv_rho;
+    const float base = fmaf(-1.5f, fmaf(ux, ux, fmaf(uy, uy, uz * uz)), 1.0f);
+    float moving = 0.0f;                               // sum of the equilibria of all moving populations
+#pragma unroll
+    for (int i = 1; i < Q; ++i) {
+        if (dir_inv(i) < i) continue;                  // handle each +/- pair once
+        const int j = dir_inv(i);
+        const float cu = (float)dir_c(i, 0) * ux + (float)dir_c(i, 1) * uy + (float)dir_c(i, 2) * uz;
+        const float wr = (float)dir_weight<Q>(i) * rho;
+        const float even = wr * fmaf(4.5f * cu, cu, base);
+        const float odd = wr * 3.0f * cu;
+        moving = fmaf(2.0f, even, moving);
+        f[i] = fmaf(inv_tau, (even + odd) - f[i], f[i]);
+        f[j] = fmaf(inv_tau, (even - odd) - f[j], f[j]);
+    }
+    // the rest equilibrium is what is left of rho: sum_i feq_i == rho holds to round-off instead of
+    // drifting with the rounding of the fp32 weights (their sum is not exactly 1)
+    f[0] = fmaf(inv_tau, (rho - moving) - f[0], f[0]);
+}
+
+// velocity set for run-time indices (link lists); compile-time indices use dir_c()
+__constant__ int8_t c_dir[27][3] = {
+    { 0, 0, 0},
+    {-1, 0, 0}, { 0,-1, 0}, { 0, 0,-1}, { 0, 0, 1}, { 0, 1, 0}, { 1, 0, 0},
+    {-1,-1, 0}, {-1, 0,-1}, {-1, 0, 1}, {-1, 1, 0}, { 0,-1,-1}, { 0,-1, 1},
+    { 0, 1,-1}, { 0, 1, 1}, { 1,-1, 0}, { 1, 0,-1}, { 1, 0, 1}, { 1, 1, 0},
+    {-1,-1,-1}, {-1,-1, 1}, {-1, 1,-1}, {-1, 1, 1}, { 1,-1,-1}, { 1,-1, 1}, { 1, 1,-1}, { 1, 1, 1}};
+
+// offset (in floats) from a cell to the cell population i is pulled from: x - c_i
+__device__ __forceinline__ long long pull_offset_dyn(const Geom& g, int i)
+{
+    return (long long)c_dir[i][0] * g.plane + (long long)(c_dir[i][1] * g.zp + c_dir[i][2]);
+}
+
+// 27-bit field: bit nb_bit(dx,dy,dz) = solid flag of the neighbour at (dx,dy,dz).  The warp's
+// 32 cells share one mask word per row; lanes 0 and 31 fetch the adjacent word for z-1 / z+1.
+__device__ __forceinline__ uint32_t neighbour_bits(const uint32_t* __restrict__ solid, long long row, int yp, int wz,
+                                                   int w, unsigned lane)
+{
+    uint32_t nb = 0;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const uint32_t* r = solid + (row + (long long)dx * yp + dy) * wz;
+            const uint32_t c = __ldg(r + w);
+            uint32_t lo = (c >> ((lane - 1) & 31)) & 1u;
+            uint32_t hi = (c >> ((lane + 1) & 31)) & 1u;
+            if (lane == 0)  lo = __ldg(r + w - 1) >> 31;
+            if (lane == 31) hi = __ldg(r + w + 1) & 1u;
+            const uint32_t mid = (c >> lane) & 1u;
+            nb |= (lo << nb_bit(dx, dy, -1)) | (mid << nb_bit(dx, dy, 0)) | (hi << nb_bit(dx, dy, 1));
+        }
+    }
+    return nb;
+}
+
+// moving-wall term of half-way bounce-back, 6 w_i (c_i . u_wall) with rho_wall = 1; the wall
+// is the first axis (x, y, z order) along which the pulled-from cell leaves the box
+template <int Q>
+__device__ __forceinline__ float wall_term(const StepParams& p, int i, int x, int y, int z)
+{
+    const int s[3] = {x - dir_c(i, 0), y - dir_c(i, 1), z - dir_c(i, 2)};
+    const int n[3] = {p.g.nx, p.g.ny, p.g.nz};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if ((s[a] < 0 || s[a] >= n[a]) && p.bc[a] == 2) {
+            const float* u = p.wall_u[a * 2 + (s[a] < 0 ? 0 : 1)];
+            const float cu = (float)dir_c(i, 0) * u[0] + (float)dir_c(i, 1) * u[1] + (float)dir_c(i, 2) * u[2];
+            return 6.0f * (float)dir_weight<Q>(i) * cu;
+        }
+    }
+    return 0.0f;
+}
+
+template <int Q, int MOMENT, bool EQ64, bool GENERAL>
+__global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepParams p)
+{
+    const Geom& g = p.g;
+    const unsigned lane = threadIdx.x & 31u;
+    int z = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = p.x0 + blockIdx.z;
+    const bool active = (z < g.nz) && (y < g.ny);
+    if (z >= g.nz) z = g.nz - 1;          // keep whole warps alive for the warp-wide steps
+    if (y >= g.ny) y = g.ny - 1;
+
+    const long long row = (long long)(x + 1) * g.yp + (y + 1);
+    const long long idx = row * g.zp + (z + PAD_Z);
+    const float* __restrict__ fin = p.fin + idx;
+
+    const bool do_stream = !GENERAL || (p.phases & PH_STREAM);
+    float f[Q];
+
+    // ---- pull: f_i(x) <- f_i(x - c_i)   (SimCalcFuncs.cu:83-94, j = INVERSE[i] relabelled)
+    if (do_stream) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i)
+            f[i] = fin[(long long)i * g.np - ((long long)dir_c(i, 0) * g.plane + (long long)(dir_c(i, 1) * g.zp + dir_c(i, 2)))];
+    } else {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) f[i] = fin[(long long)i * g.np];
+    }
+
+    bool skip_collide = false;
+    if (GENERAL) {
+        const int w = (z + PAD_Z) >> 5;
+        bool solid_here = false;
+        float fx = 0.0f, fy = 0.0f, fz = 0.0f;     // this thread's share of the force on the solid
+        bool has_force = false;
+        if (p.solid) {
+            solid_here = (__ldg(p.solid + row * g.wz + w) >> lane) & 1u;
+            if (p.boundary_mode == 1) {
+                // ---- half-way bounce-back off solid neighbours and wall ghosts
+                if (do_stream) {
+                    const uint32_t nb = neighbour_bits(p.solid, row, g.yp, g.wz, w, lane);
+                    if (__any_sync(FULL, nb != 0u)) {
+#pragma unroll
+                        for (int i = 1; i < Q; ++i) {
+                            if ((nb >> nb_bit(-dir_c(i, 0), -dir_c(i, 1), -dir_c(i, 2))) & 1u) {
+                                const float back = fin[(long long)dir_inv(i) * g.np];
+                                float v = back;
+                                if (p.wall_moving) v += wall_term<Q>(p, i, x, y, z);
+                                f[i] = v;
+                                // momentum exchange with an obstacle cell (not a domain wall; periodic or
+                                // halo images of obstacle cells count): population inv(i) goes in with -c_i
+                                // and comes back as i with +c_i
+                                const int sx = x - dir_c(i, 0), sy = y - dir_c(i, 1), sz = z - dir_c(i, 2);
+                                const bool off_wall = (p.bc[0] == 2 && (sx < 0 || sx >= g.nx)) ||
+                                                      (p.bc[1] == 2 && (sy < 0 || sy >= g.ny)) ||
+                                                      (p.bc[2] == 2 && (sz < 0 || sz >= g.nz));
+                                if (p.force && active && !solid_here && !off_wall) {
+                                    const float m = back + v;
+                                    fx -= (float)dir_c(i, 0) * m;
+                                    fy -= (float)dir_c(i, 1) * m;
+                                    fz -= (float)dir_c(i, 2) * m;
+                                    has_force = true;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (solid_here) {
+#pragma unroll
+                    for (int i = 0; i < Q; ++i) f[i] = 0.0f;
+                    skip_collide = true;
+                }
+            }
+        }
+        if ((p.phases & PH_REFLECT) && p.boundary_mode == 0) {
+            // ---- reference reflection as a gather (scatter form: SimCalcFuncs.cu:162-187)
+            if (p.tmask) {
+                const uint32_t tw = __ldg(p.tmask + row * g.wz + w);
+                if (active && ((tw >> lane) & 1u)) {
+                    const uint32_t rank = __ldg(p.tprefix + row * g.wz + w) + __popc(tw & ((1u << lane) - 1u));
+                    const uint32_t e0 = __ldg(p.toff + rank), e1 = __ldg(p.toff + rank + 1);
+                    for (uint32_t e = e0; e < e1; ++e) {
+                        const Link L = p.links[e];
+                        long long src = (long long)L.j * g.np + (long long)L.src_cell;
+                        if (do_stream) src -= pull_offset_dyn(g, L.j);
+                        const float moved = p.fin[src] * L.w;
+#pragma unroll
+                        for (int i = 1; i < Q; ++i)
+                            if (L.d == i) f[i] += moved;
+                        if (p.force) {
+                            // SimCalcFuncs.cu:181-183; incoming direction from the slot index (reference) or slot/3
+                            const int in_dir = (p.force_mode == 0) ? (int)L.slot : (int)L.j;
+                            if (in_dir < 27) {
+                                const float so = dir_split(L.d), si = dir_split(in_dir);
+                                fx += moved * (((float)c_dir[L.d][0] * so) - ((float)c_dir[in_dir][0] * si));
+                                fy += moved * (((float)c_dir[L.d][1] * so) - ((float)c_dir[in_dir][1] * si));
+                                fz += moved * (((float)c_dir[L.d][2] * so) - ((float)c_dir[in_dir][2] * si));
+                                has_force = true;
+                            }
+                        }
+                    }
+                }
+            }
+            // solid cells are emptied after the scatter (SimCalcFuncs.cu:189-197)
+            if (solid_here) {
+#pragma unroll
+                for (int i = 0; i < Q; ++i) f[i] = 0.0f;
+            }
+        }
+        if (p.force && __any_sync(FULL, has_force)) {
+            // one atomic triple per warp (the reference issues three atomics per link on one address)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                fx += __shfl_xor_sync(FULL, fx, o);
+                fy += __shfl_xor_sync(FULL, fy, o);
+                fz += __shfl_xor_sync(FULL, fz, o);
+            }
+            if (lane == 0) {
+                atomicAdd(p.force + 0, (double)fx);
+                atomicAdd(p.force + 1, (double)fy);
+                atomicAdd(p.force + 2, (double)fz);
+            }
+        }
+    }
+
+    // ---- BGK relaxation (SimCalcFuncs.cu:98-156); runs on every cell like the reference
+    if ((!GENERAL || (p.phases & PH_COLLIDE)) && !skip_collide) {
+        if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
+        else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
+    }
+
+    // ---- additive source on the selected cells (SimCalcFuncs.cu:200-215)
+    if (GENERAL && (p.phases & PH_SOURCE) && p.src_on && !skip_collide) {
+        if (x >= p.src_lo[0] && x <= p.src_hi[0] && y >= p.src_lo[1] && y <= p.src_hi[1] &&
+            z >= p.src_lo[2] && z <= p.src_hi[2]) {
+#pragma unroll
+            for (int i = 0; i < Q; ++i) f[i] += p.src_f[i];
+        }
+    }
+
+    if (active) {
+        float* __restrict__ fout = p.fout + idx;
+#pragma unroll
+        for (int i = 0; i < Q; ++i) fout[(long long)i * g.np] = f[i];
+    }
+}
+
+template <int Q, int MOMENT, bool EQ64, bool GENERAL>
+cudaError_t launch_step_t(const StepParams& p, cudaStream_t stream)
+{
+    const Geom& g = p.g;
+    int bz = ((g.nz + 31) / 32) * 32;
+    if (bz > 128) bz = 128;
+    int by = 256 / bz;
+    if (by > g.ny) by = g.ny;
+    dim3 block(bz, by, 1);
+    dim3 grid((g.nz + bz - 1) / bz, (g.ny + by - 1) / by, p.x1 - p.x0);
+    if (p.x1 <= p.x0) return cudaSuccess;
+    step_kernel<Q, MOMENT, EQ64, GENERAL><<<grid, block, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int Q>
+cudaError_t launch_step_q(const LaunchCfg& c, const StepParams& p, cudaStream_t s)
+{
+    const int key = (c.moment_mode ? 4 : 0) | (c.eq64 ? 2 : 0) | (c.general ? 1 : 0);
+    switch (key) {
+        case 0: return launch_step_t<Q, 0, false, false>(p, s);
+        case 1: return launch_step_t<Q, 0, false, true>(p, s);
+        case 2: return launch_step_t<Q, 0, true, false>(p, s);
+        case 3: return launch_step_t<Q, 0, true, true>(p, s);
+        case 4: return launch_step_t<Q, 1, false, false>(p, s);
+        case 5: return launch_step_t<Q, 1, false, true>(p, s);
+        case 6: return launch_step_t<Q, 1, true, false>(p, s);
+        default: return launch_step_t<Q, 1, true, true>(p, s);
+    }
+}
+
+// ---- ghost layers -----------------------------------------------------------------------
+
+// periodic x: plane 0 <- plane nx, plane nx+1 <- plane 1 (whole padded planes)
+__global__ void fill_x_kernel(float* f, Geom g, int q)
+{
+    const long long n = g.plane;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float* fq = f + (long long)blockIdx.y * g.np;
+    fq[i] = fq[(long long)g.nx * g.plane + i];
+    fq[(long long)(g.nx + 1) * g.plane + i] = fq[g.plane + i];
+}
+
+// y rows: mode 1 periodic (row 0 <- row ny, row ny+1 <- row 1)
+__global__ void fill_y_kernel(float* f, Geom g, int q)
+{
+    const int zc = blockIdx.x * blockDim.x + threadIdx.x;
+    const int xpl = blockIdx.y;
+    if (zc >= g.zp) return;
+    float* fq = f + (long long)blockIdx.z * g.np + (long long)xpl * g.plane;
+    fq[zc] = fq[(long long)g.ny * g.zp + zc];
+    fq[(long long)(g.ny + 1) * g.zp + zc] = fq[(long long)g.zp + zc];
+}
+
+// z columns: ghost at PAD_Z-1 <- PAD_Z+nz-1, ghost at PAD_Z+nz <- PAD_Z
+__global__ void fill_z_kernel(float* f, Geom g, int q)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // padded row index over xp*yp
+    const long long rows = (long long)g.xp * g.yp;
+    if (r >= rows) return;
+    float* fq = f + (long long)blockIdx.y * g.np + r * g.zp;
+    fq[PAD_Z - 1] = fq[PAD_Z + g.nz - 1];
+    fq[PAD_Z + g.nz] = fq[PAD_Z];
+}
+
+// ---- AoS <-> SoA (Lattice::load_data / retrieve_data, Lattice.cpp:73-113) ------------------
+
+constexpr int AOS_BYTES = 144;   // sizeof(LatticePoint), simulation/include/LatticePoint.h:9-17
+constexpr int AOS_F = 12;        // offsetof particle_distribution
+constexpr int AOS_REFLECTED = 120;
+constexpr int AOS_INTERNAL = 121;
+
+__global__ void unpack_aos_kernel(const unsigned char* __restrict__ aos, float* __restrict__ f, uint8_t* __restrict__ solid_bytes,
+                                  Geom g, int q, int x0, int nxc)
+{
+    const long long per = (long long)g.ny * g.nz;
+    const long long n = per * nxc;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int xl = (int)(k / per);
+    const int rem = (int)(k - (long long)xl * per);
+    const int y = rem / g.nz, z = rem - y * g.nz;
+    const unsigned char* rec = aos + k * AOS_BYTES;
+    const long long idx = g.cell(x0 + xl, y, z);
+    const float* pf = reinterpret_cast<const float*>(rec + AOS_F);
+    for (int i = 0; i < q; ++i) f[(long long)i * g.np + idx] = pf[i];
+    if (solid_bytes) solid_bytes[(long long)(x0 + xl) * per + rem] = rec[AOS_INTERNAL] ? 1 : 0;
+}
+
+__global__ void pack_aos_kernel(unsigned char* __restrict__ aos, const float* __restrict__ f, const uint32_t* __restrict__ solid,
+                                const uint32_t* __restrict__ reflected, Geom g, int q, int x0, int nxc)
+{
+    const long long per = (long long)g.ny * g.nz;
+    const long long n = per * nxc;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int xl = (int)(k / per);
+    const int rem = (int)(k - (long long)xl * per);
+    const int y = rem / g.nz, z = rem - y * g.nz;
+    const int x = x0 + xl;
+    unsigned char* rec = aos + k * AOS_BYTES;
+    const long long idx = g.cell(x, y, z);
+    int* pc = reinterpret_cast<int*>(rec);
+    pc[0] = x; pc[1] = y; pc[2] = z;
+    float* pf = reinterpret_cast<float*>(rec + AOS_F);
+    for (int i = 0; i < q; ++i) pf[i] = f[(long long)i * g.np + idx];
+    for (int i = q; i < 27; ++i) pf[i] = 0.0f;
+    const long long word = ((long long)(x + 1) * g.yp + (y + 1)) * g.wz + ((z + PAD_Z) >> 5);
+    const unsigned bit = (unsigned)(z + PAD_Z) & 31u;
+    rec[AOS_INTERNAL] = solid ? ((solid[word] >> bit) & 1u) : 0;
+    rec[AOS_REFLECTED] = reflected ? ((reflected[word] >> bit) & 1u) : 0;
+}
+
+__global__ void scatter_dense_kernel(const float* __restrict__ dense, float* __restrict__ fq, Geom g, int x0, int nxc)
+{
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int xl = blockIdx.z;
+    if (z >= g.nz) return;
+    fq[g.cell(x0 + xl, y, z)] = dense[((long long)xl * g.ny + y) * g.nz + z];
+}
+
+__global__ void gather_dense_kernel(float* __restrict__ dense, const float* __restrict__ fq, Geom g, int x0, int nxc)
+{
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int xl = blockIdx.z;
+    if (z >= g.nz) return;
+    dense[((long long)xl * g.ny + y) * g.nz + z] = fq[g.cell(x0 + xl, y, z)];
+}
+
+// ---- solid mask ---------------------------------------------------------------------------
+
+// One warp builds one mask word.  Ghost cells follow the domain-edge rule of each axis they
+// lie outside of: wall -> solid; zero-inflow -> fluid (holding 0); periodic -> the wrapped
+// interior cell; halo (x only) -> the plane handed in by the caller.
+__global__ void build_mask_kernel(const uint8_t* __restrict__ sb, int has_x_ghost, uint32_t* __restrict__ mask, Geom g,
+                                  int bcx, int bcy, int bcz)
+{
+    const long long nwords = (long long)g.xp * g.yp * g.wz;
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    if (wid >= nwords) return;
+    const int w = (int)(wid % g.wz);
+    const long long r = wid / g.wz;
+    const int ypad = (int)(r % g.yp), xpad = (int)(r / g.yp);
+    int c[3] = {xpad - 1, ypad - 1, w * 32 + (int)lane - PAD_Z};
+    const int n[3] = {g.nx, g.ny, g.nz};
+    const int bc[3] = {bcx, bcy, bcz};
+    // padding beyond the single ghost layer in z is never read: leave it clear
+    const bool padding = (c[2] < -1 || c[2] > g.nz);
+    bool wall = false, empty = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (c[a] >= 0 && c[a] < n[a]) continue;
+        if (bc[a] == 2) wall = true;
+        else if (bc[a] == 0) empty = true;
+        else if (bc[a] == 1) c[a] = (c[a] + n[a]) % n[a];
+        else if (!(a == 0 && has_x_ghost)) empty = true;   // halo: keep x = -1 / nx, read the caller's plane
+    }
+    bool bit = false;
+    if (padding) bit = false;
+    else if (wall) bit = true;
+    else if (!empty && sb) {
+        const long long per = (long long)g.ny * g.nz;
+        const long long xi = has_x_ghost ? (long long)c[0] + 1 : (long long)c[0];
+        bit = sb[xi * per + (long long)c[1] * g.nz + c[2]] != 0;
+    }
+    const uint32_t word = __ballot_sync(FULL, bit);
+    if (lane == 0) mask[wid] = word;
+}
+
+__global__ void mask_to_bytes_kernel(const uint32_t* __restrict__ mask, uint8_t* __restrict__ sb, Geom g)
+{
+    const long long per = (long long)g.ny * g.nz;
+    const long long n = per * g.nx;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int x = (int)(k / per);
+    const int rem = (int)(k - (long long)x * per);
+    const int y = rem / g.nz, z = rem - y * g.nz;
+    const long long word = ((long long)(x + 1) * g.yp + (y + 1)) * g.wz + ((z + PAD_Z) >> 5);
+    sb[k] = (mask[word] >> ((unsigned)(z + PAD_Z) & 31u)) & 1u;
+}
+
+// ---- moments and conservation diagnostics ----------------------------------------------------
+
+template <int Q>
+__global__ void moments_kernel(const float* __restrict__ f, Geom g, int moment_mode, float* rho, float* ux, float* uy, float* uz)
+{
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, x = blockIdx.z;
+    if (z >= g.nz) return;
+    const long long idx = g.cell(x, y, z);
+    float r = 0.0f, mx = 0.0f, my = 0.0f, mz = 0.0f;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        const float v = f[(long long)i * g.np + idx];
+        const float s = (moment_mode == 0) ? dir_split(i) : 1.0f;
+        r += v;
+        mx += v * (float)dir_c(i, 0) * s;
+        my += v * (float)dir_c(i, 1) * s;
+        mz += v * (float)dir_c(i, 2) * s;
+    }
+    if (r != 0.0f) { mx /= r; my /= r; mz /= r; }
+    const long long k = ((long long)x * g.ny + y) * g.nz + z;
+    if (rho) rho[k] = r;
+    if (ux) ux[k] = mx;
+    if (uy) uy[k] = my;
+    if (uz) uz[k] = mz;
+}
+
+// mass and momentum in double: per-thread partial over a z-row segment, warp shuffle
+// reduction, one atomic quadruple per warp
+template <int Q>
+__global__ void mass_momentum_kernel(const float* __restrict__ f, Geom g, double* out4)
+{
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, x = blockIdx.z;
+    double m = 0.0, px = 0.0, py = 0.0, pz = 0.0;
+    if (z < g.nz) {
+        const long long idx = g.cell(x, y, z);
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            const double v = (double)f[(long long)i * g.np + idx];
+            m += v;
+            px += v * dir_c(i, 0);
+            py += v * dir_c(i, 1);
+            pz += v * dir_c(i, 2);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m += __shfl_xor_sync(FULL, m, o);
+        px += __shfl_xor_sync(FULL, px, o);
+        py += __shfl_xor_sync(FULL, py, o);
+        pz += __shfl_xor_sync(FULL, pz, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out4 + 0, m);
+        atomicAdd(out4 + 1, px);
+        atomicAdd(out4 + 2, py);
+        atomicAdd(out4 + 3, pz);
+    }
+}
+
+}  // namespace
+
+// ---- launch wrappers ---------------------------------------------------------------------------
+
+cudaError_t launch_step(const LaunchCfg& cfg, const StepParams& p, cudaStream_t stream)
+{
+    if (cfg.q == 27) return launch_step_q<27>(cfg, p, stream);
+    if (cfg.q == 19) return launch_step_q<19>(cfg, p, stream);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_fill_ghosts(float* f, const Geom& g, int q, const int bc[3], bool include_x, cudaStream_t stream)
+{
+    // order x, y, z: later axes copy the ghost layers of earlier ones, which fills edges and corners
+    if (include_x && bc[0] == 1) {
+        dim3 grid((unsigned)((g.plane + 255) / 256), q);
+        fill_x_kernel<<<grid, 256, 0, stream>>>(f, g, q);
+    }
+    if (bc[1] == 1) {
+        dim3 grid((g.zp + 127) / 128, g.xp, q);
+        fill_y_kernel<<<grid, 128, 0, stream>>>(f, g, q);
+    }
+    if (bc[2] == 1) {
+        const long long rows = (long long)g.xp * g.yp;
+        dim3 grid((unsigned)((rows + 127) / 128), q);
+        fill_z_kernel<<<grid, 128, 0, stream>>>(f, g, q);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_aos(const void* aos, float* f, uint8_t* solid_bytes, const Geom& g, int q, int x0, int nxc, cudaStream_t stream)
+{
+    const long long n = (long long)g.ny * g.nz * nxc;
+    if (n <= 0) return cudaSuccess;
+    unpack_aos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const unsigned char*)aos, f, solid_bytes, g, q, x0, nxc);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_aos(void* aos, const float* f, const uint32_t* solid, const uint32_t* reflected, const Geom& g, int q, int x0, int nxc, cudaStream_t stream)
+{
+    const long long n = (long long)g.ny * g.nz * nxc;
+    if (n <= 0) return cudaSuccess;
+    pack_aos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((unsigned char*)aos, f, solid, reflected, g, q, x0, nxc);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_dense(const float* dense, float* fq, const Geom& g, int x0, int nxc, cudaStream_t stream)
+{
+    if (nxc <= 0) return cudaSuccess;
+    dim3 grid((g.nz + 127) / 128, g.ny, nxc);
+    scatter_dense_kernel<<<grid, 128, 0, stream>>>(dense, fq, g, x0, nxc);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_dense(float* dense, const float* fq, const Geom& g, int x0, int nxc, cudaStream_t stream)
+{
+    if (nxc <= 0) return cudaSuccess;
+    dim3 grid((g.nz + 127) / 128, g.ny, nxc);
+    gather_dense_kernel<<<grid, 128, 0, stream>>>(dense, fq, g, x0, nxc);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_build_mask(const uint8_t* solid_bytes, int has_x_ghost, uint32_t* mask, const Geom& g, const int bc[3], cudaStream_t stream)
+{
+    const long long nwords = (long long)g.xp * g.yp * g.wz;
+    const long long threads = nwords * 32;
+    build_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(solid_bytes, has_x_ghost, mask, g, bc[0], bc[1], bc[2]);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mask_to_bytes(const uint32_t* mask, uint8_t* solid_bytes, const Geom& g, cudaStream_t stream)
+{
+    const long long n = (long long)g.nx * g.ny * g.nz;
+    mask_to_bytes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(mask, solid_bytes, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_moments(const float* f, const Geom& g, int q, int moment_mode, float* rho, float* ux, float* uy, float* uz, cudaStream_t stream)
+{
+    dim3 grid((g.nz + 127) / 128, g.ny, g.nx);
+    if (q == 27) moments_kernel<27><<<grid, 128, 0, stream>>>(f, g, moment_mode, rho, ux, uy, uz);
+    else         moments_kernel<19><<<grid, 128, 0, stream>>>(f, g, moment_mode, rho, ux, uy, uz);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mass_momentum(const float* f, const Geom& g, int q, double* out4, cudaStream_t stream)
+{
+    dim3 grid((g.nz + 127) / 128, g.ny, g.nx);
+    if (q == 27) mass_momentum_kernel<27><<<grid, 128, 0, stream>>>(f, g, out4);
+    else         mass_momentum_kernel<19><<<grid, 128, 0, stream>>>(f, g, out4);
+    return cudaGetLastError();
+}
+
+}  // namespace lbm

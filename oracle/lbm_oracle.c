@@ -263,11 +263,12 @@ static inline double q_weight(int q, int i)
 
 void lbo_step_soa(const float *fin, float *fout, int X, int Y, int Z, int q, float tau,
                   const int bc[3], const float wall_u[6][3], const uint8_t *solid,
-                  int moment, int eq64)
+                  int moment, int eq64, double *force)
 {
     const size_t n = (size_t)X * Y * Z;
     const int dims[3] = {X, Y, Z};
-#pragma omp parallel for schedule(static)
+    double Fx = 0.0, Fy = 0.0, Fz = 0.0;
+#pragma omp parallel for schedule(static) reduction(+:Fx,Fy,Fz)
     for (int x = 0; x < X; ++x)
         for (int y = 0; y < Y; ++y)
             for (int z = 0; z < Z; ++z) {
@@ -295,11 +296,20 @@ void lbo_step_soa(const float *fin, float *fout, int X, int Y, int Z, int q, flo
                         f[i] = 0.0f;
                     } else {
                         size_t ks = lbo_index(s[0], s[1], s[2], Y, Z);
-                        if (solid && solid[ks]) f[i] = fin[(size_t)LBO_INVERSE[i] * n + k];   /* bounce-back */
-                        else                    f[i] = fin[(size_t)i * n + ks];
+                        if (solid && solid[ks]) {
+                            /* bounce-back off an obstacle cell; the momentum it takes is -c_i (f_in + f_out) */
+                            float back = fin[(size_t)LBO_INVERSE[i] * n + k];
+                            f[i] = back;
+                            Fx -= LBO_DIRECTIONS[i][0] * (double)(back + back);
+                            Fy -= LBO_DIRECTIONS[i][1] * (double)(back + back);
+                            Fz -= LBO_DIRECTIONS[i][2] * (double)(back + back);
+                        } else {
+                            f[i] = fin[(size_t)i * n + ks];
+                        }
                     }
                 }
                 collide_cell_ext(f, q, tau, moment, eq64);
                 for (int i = 0; i < q; ++i) fout[(size_t)i * n + k] = f[i];
             }
+    if (force) { force[0] += Fx; force[1] += Fy; force[2] += Fz; }
 }

@@ -100,10 +100,11 @@ void lbo_step_lattice(lbo_lattice_point *cells, lbo_lattice_point *scratch, int 
 /* Plain SoA stepper: f[q][x][y][z] (dense, no padding), pull-stream + (bounce-back on
  * solid[] bytes) + BGK collide.  bc[3] per axis: 0 zero-inflow, 1 periodic, 2 wall
  * (half-way bounce-back at the domain face; wall_u[axis*2+side][3] is the wall velocity).
- * moment: REFERENCE/STANDARD.  eq64: evaluate equilibrium in double like the reference. */
+ * moment: REFERENCE/STANDARD.  eq64: evaluate equilibrium in double like the reference.
+ * force: NULL or double[3] += momentum handed to obstacle cells by bounce-back this step. */
 void lbo_step_soa(const float *fin, float *fout, int X, int Y, int Z, int q, float tau,
                   const int bc[3], const float wall_u[6][3], const uint8_t *solid,
-                  int moment, int eq64);
+                  int moment, int eq64, double *force);
 
 /* 5-bit packing helpers, Lattice.cpp:450-477 / SimCalcFuncs.cu:18-30 */
 void lbo_set_reflection_direction(lbo_reflection_values *t, int slot, unsigned value);

@@ -1,4 +1,4 @@
-// ref_harness.cu -- extern "C" doors into the reference's own `Lattice` class and CUDA
+// ref_harness.cpp -- extern "C" doors into the reference's own `Lattice` class and CUDA
 // kernels, compiled UNMODIFIED from /root/reference into oracle/_ref/libref_gpu.so
 // (SimCalcFuncs.cu, FlowCriterion.cu, Lattice.cpp, Geometry.cpp, Constants.cpp, Utils.cpp).
 // Only Model.cpp is replaced (CGAL is absent: ref_model_stub.cpp + cgal_stub/).

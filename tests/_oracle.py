@@ -47,7 +47,7 @@ def lib():
         L.lbo_source.argtypes = [vp, i, i, i, i, vp]
         L.lbo_step_cli.argtypes = [vp, vp, i, i, i, f, vp, vp, vp, i, vp]
         L.lbo_step_lattice.argtypes = [vp, vp, i, i, i, f]
-        L.lbo_step_soa.argtypes = [vp, vp, i, i, i, i, f, vp, vp, vp, i, i]
+        L.lbo_step_soa.argtypes = [vp, vp, i, i, i, i, f, vp, vp, vp, i, i, vp]
         L.lbo_set_reflection_direction.argtypes = [vp, i, C.c_uint]
         L.lbo_get_reflection_direction.argtypes = [vp, i]
         L.lbo_get_reflection_direction.restype = i
@@ -177,7 +177,7 @@ def step_lattice(cells, X, Y, Z, tau, steps=1):
 
 
 def step_soa(f, X, Y, Z, q, tau, bc=(BC_PERIODIC,) * 3, wall_u=None, solid=None,
-             moment=MOMENT_STANDARD, eq64=False, steps=1):
+             moment=MOMENT_STANDARD, eq64=False, steps=1, force=None):
     """f: float32 [q, X, Y, Z] dense.  Returns the state after `steps` steps."""
     a = np.ascontiguousarray(f, np.float32).copy()
     b = np.zeros_like(a)
@@ -185,7 +185,7 @@ def step_soa(f, X, Y, Z, q, tau, bc=(BC_PERIODIC,) * 3, wall_u=None, solid=None,
     wu = None if wall_u is None else np.ascontiguousarray(wall_u, np.float32).reshape(6, 3)
     so = None if solid is None else np.ascontiguousarray(solid, np.uint8)
     for _ in range(steps):
-        lib().lbo_step_soa(ptr(a), ptr(b), X, Y, Z, q, tau, ptr(bcv), ptr(wu), ptr(so), moment, int(eq64))
+        lib().lbo_step_soa(ptr(a), ptr(b), X, Y, Z, q, tau, ptr(bcv), ptr(wu), ptr(so), moment, int(eq64), ptr(force))
         a, b = b, a
     return a
 
