@@ -178,7 +178,12 @@ def test_reference_reflection_known_answer_and_ours():
     assert want[p(2, 1, 2)]["f"][17] == pytest.approx(0.367402, abs=1e-6)
     assert want[p(1, 1, 2)]["f"][4] == pytest.approx(0.341121, abs=1e-6)
     assert want[p(2, 2, 2)]["f"][26] == pytest.approx(0.291477, abs=1e-6)
-    assert np.allclose(wf, [0.28086, -0.194318, 0.648261], atol=1e-6)
+    # The reference's force sum also visits the 75 filled slots >= 6 of this table; for slots >= 27 it
+    # multiplies a zero population by DIRECTIONS[s]/SPLIT[s] read past the end of those tables
+    # (SimCalcFuncs.cu:181-183).  Whatever lies there decides between the gtest's numbers and NaN
+    # (0 * inf); both have been observed on sm_100a, so only a finite result is held to the golden value.
+    golden = [0.28086, -0.194318, 0.648261]
+    assert all(np.isnan(v) or abs(v - g) <= 1e-6 for v, g in zip(wf, golden))
     lat = ours(3, 3, 3, spacing=0.5)
     lat.load_data(cells)
     lat.set_reflection_tables(rtab, ridx)
@@ -187,7 +192,7 @@ def test_reference_reflection_known_answer_and_ours():
     got = lat.retrieve_data()
     assert np.array_equal(got["f"], want["f"])
     r = lat.retrieve_reflection_data()
-    assert np.allclose([r.x, r.y, r.z], wf, rtol=1e-6, atol=1e-7)
+    assert np.allclose([r.x, r.y, r.z], golden, rtol=1e-6, atol=1e-6)
 
 
 @pytest.mark.parametrize("kind", [1, 2])
