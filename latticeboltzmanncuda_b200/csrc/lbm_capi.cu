@@ -55,6 +55,9 @@ struct lbm_lattice_s {
     int cur = 0;
     bool pending_commit = false;
     uint32_t* solid = nullptr;       // padded bit mask
+    int* special = nullptr;          // per mask word: slot of the warp's neighbourhood words or -1
+    uint32_t* cellinfo = nullptr;    // [n_special][32] neighbourhood words
+    size_t n_special = 0;
     bool any_solid = false;          // some bit set (geometry or wall ghosts)
     uint8_t* solid_bytes = nullptr;  // nx*ny*nz (+2 planes) scratch
     uint32_t *tmask = nullptr, *tprefix = nullptr, *toff = nullptr, *reflected = nullptr;
@@ -97,6 +100,35 @@ __global__ void any_nonzero_kernel(const uint32_t* w, size_t n, unsigned* flag)
     if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
+// recompute which warps need the boundary path and their neighbourhood words; call after the solid
+// mask or the link lists change
+int rebuild_special(lbm_handle h)
+{
+    const size_t words = h->mask_words();
+    if (!h->special) CK(cudaMalloc(&h->special, words * sizeof(int)));
+    if (!h->flag) CK(cudaMalloc(&h->flag, sizeof(unsigned)));
+    const uint32_t* solid = h->any_solid ? h->solid : nullptr;
+    const uint32_t* tmask = h->nlinks ? h->tmask : nullptr;
+    CK(cudaMemsetAsync(h->special, 0xFF, words * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->flag, 0, sizeof(unsigned), h->stream));
+    h->n_special = 0;
+    if (!solid && !tmask) { CK(cudaStreamSynchronize(h->stream)); return LBM_OK; }
+    CK(launch_build_cellinfo(solid, tmask, h->special, nullptr, h->flag, h->g, 0, h->stream));
+    unsigned n = 0;
+    CK(cudaMemcpyAsync(&n, h->flag, sizeof n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->cellinfo);
+    h->cellinfo = nullptr;
+    if (n) {
+        CK(cudaMalloc(&h->cellinfo, (size_t)n * 32 * sizeof(uint32_t)));
+        CK(cudaMemsetAsync(h->flag, 0, sizeof(unsigned), h->stream));
+        CK(launch_build_cellinfo(solid, tmask, h->special, h->cellinfo, h->flag, h->g, 1, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    h->n_special = n;
+    return LBM_OK;
+}
+
 int rebuild_mask(lbm_handle h, const uint8_t* dev_bytes, int has_x_ghost)
 {
     if (!h->solid) CK(cudaMalloc(&h->solid, h->mask_words() * sizeof(uint32_t)));
@@ -110,7 +142,7 @@ int rebuild_mask(lbm_handle h, const uint8_t* dev_bytes, int has_x_ghost)
     CK(cudaMemcpyAsync(&f, h->flag, sizeof f, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->any_solid = f != 0;
-    return LBM_OK;
+    return rebuild_special(h);
 }
 
 bool has_wall(const lbm_config& c) { return c.bc[0] == LBM_BC_WALL || c.bc[1] == LBM_BC_WALL || c.bc[2] == LBM_BC_WALL; }
@@ -127,6 +159,8 @@ void fill_params(lbm_handle h, StepParams& p, unsigned phases, int x0, int x1)
     p.phases = phases;
     p.boundary_mode = h->cfg.boundary_mode;
     p.solid = h->any_solid ? h->solid : nullptr;
+    p.special = h->n_special ? h->special : nullptr;
+    p.cellinfo = h->cellinfo;
     if (h->nlinks) {
         p.tmask = h->tmask; p.tprefix = h->tprefix; p.toff = h->toff; p.links = h->links;
     }
@@ -261,8 +295,8 @@ LBM_API int lbm_create(const lbm_config* cfg, lbm_handle* out)
         CKB(cudaMalloc(&h->buf[b], h->state_bytes()));
         CKB(cudaMemsetAsync(h->buf[b], 0, h->state_bytes(), h->stream));
     }
-    CKB(cudaMalloc(&h->force, 3 * sizeof(double)));
-    CKB(cudaMemsetAsync(h->force, 0, 3 * sizeof(double), h->stream));
+    CKB(cudaMalloc(&h->force, 3 * FORCE_SLOTS * sizeof(double)));
+    CKB(cudaMemsetAsync(h->force, 0, 3 * FORCE_SLOTS * sizeof(double), h->stream));
     CKB(cudaMalloc(&h->diag, 4 * sizeof(double)));
 #undef CKB
     if (has_wall(h->cfg)) {
@@ -282,7 +316,7 @@ LBM_API int lbm_destroy(lbm_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->side) cudaStreamSynchronize(h->side);
     for (int b = 0; b < 2; ++b) cudaFree(h->buf[b]);
-    cudaFree(h->solid); cudaFree(h->solid_bytes); cudaFree(h->tmask); cudaFree(h->tprefix); cudaFree(h->toff);
+    cudaFree(h->solid); cudaFree(h->special); cudaFree(h->cellinfo); cudaFree(h->solid_bytes); cudaFree(h->tmask); cudaFree(h->tprefix); cudaFree(h->toff);
     cudaFree(h->reflected); cudaFree(h->links); cudaFree(h->force); cudaFree(h->diag); cudaFree(h->flag);
     cudaFree(h->staging);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -490,7 +524,9 @@ LBM_API int lbm_set_reflection_table(lbm_handle h, const void* tables, const int
         }
     }
     std::sort(hl.begin(), hl.end(), [](const HostLink& a, const HostLink& b) {
-        return a.tgt != b.tgt ? a.tgt < b.tgt : a.order < b.order;
+        if (a.tgt != b.tgt) return a.tgt < b.tgt;
+        if (a.l.d != b.l.d) return a.l.d < b.l.d;      // the kernel walks a target's links population by population
+        return a.order < b.order;
     });
     std::vector<uint32_t> tmask(words, 0u), tprefix(words, 0u), toff;
     std::vector<Link> links(hl.size());
@@ -523,7 +559,7 @@ LBM_API int lbm_set_reflection_table(lbm_handle h, const void* tables, const int
         CK(cudaMemcpy(h->links, links.data(), links.size() * sizeof(Link), cudaMemcpyHostToDevice));
         h->nlinks = links.size();
     }
-    return LBM_OK;
+    return rebuild_special(h);
 }
 
 LBM_API int lbm_set_source(lbm_handle h, int kind, const int32_t lo[3], const int32_t hi[3], const float f[27])
@@ -542,7 +578,7 @@ LBM_API int lbm_set_force_accumulator(lbm_handle h, int enable, const float init
     int rc = use(h);
     if (rc) return rc;
     h->force_on = enable != 0;
-    double v[3] = {0.0, 0.0, 0.0};
+    double v[3 * FORCE_SLOTS] = {0.0};
     if (init) for (int a = 0; a < 3; ++a) v[a] = init[a];
     CK(cudaMemcpyAsync(h->force, v, sizeof v, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -554,10 +590,14 @@ LBM_API int lbm_get_force(lbm_handle h, float out[3])
     int rc = use(h);
     if (rc) return rc;
     if (!out) return fail(LBM_ERR_INVALID, "null buffer");
-    double v[3];
+    double v[3 * FORCE_SLOTS];
     CK(cudaMemcpyAsync(v, h->force, sizeof v, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    for (int a = 0; a < 3; ++a) out[a] = (float)v[a];
+    for (int a = 0; a < 3; ++a) {
+        double t = 0.0;
+        for (int k = 0; k < FORCE_SLOTS; ++k) t += v[3 * k + a];
+        out[a] = (float)t;
+    }
     return LBM_OK;
 }
 

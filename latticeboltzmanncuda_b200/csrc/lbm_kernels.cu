@@ -97,7 +97,8 @@ __device__ __forceinline__ long long pull_offset_dyn(const Geom& g, int i)
 }
 
 // 27-bit field: bit nb_bit(dx,dy,dz) = solid flag of the neighbour at (dx,dy,dz).  The warp's
-// 32 cells share one mask word per row; lanes 0 and 31 fetch the adjacent word for z-1 / z+1.
+// 32 cells share one mask word per row; the words before and after it supply z-1 of lane 0 and
+// z+1 of lane 31 through a funnel shift, so all loads are warp-uniform and nothing branches.
 __device__ __forceinline__ uint32_t neighbour_bits(const uint32_t* __restrict__ solid, long long row, int yp, int wz,
                                                    int w, unsigned lane)
 {
@@ -106,14 +107,12 @@ __device__ __forceinline__ uint32_t neighbour_bits(const uint32_t* __restrict__ 
     for (int dx = -1; dx <= 1; ++dx) {
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
-            const uint32_t* r = solid + (row + (long long)dx * yp + dy) * wz;
-            const uint32_t c = __ldg(r + w);
-            uint32_t lo = (c >> ((lane - 1) & 31)) & 1u;
-            uint32_t hi = (c >> ((lane + 1) & 31)) & 1u;
-            if (lane == 0)  lo = __ldg(r + w - 1) >> 31;
-            if (lane == 31) hi = __ldg(r + w + 1) & 1u;
-            const uint32_t mid = (c >> lane) & 1u;
-            nb |= (lo << nb_bit(dx, dy, -1)) | (mid << nb_bit(dx, dy, 0)) | (hi << nb_bit(dx, dy, 1));
+            const uint32_t* r = solid + (row + (long long)dx * yp + dy) * wz + w;
+            const uint32_t prev = __ldg(r - 1), c = __ldg(r), next = __ldg(r + 1);
+            const uint32_t below = __funnelshift_l(prev, c, 1);   // bit k = solid(z_k - 1)
+            const uint32_t above = __funnelshift_r(c, next, 1);   // bit k = solid(z_k + 1)
+            nb |= (((below >> lane) & 1u) << nb_bit(dx, dy, -1)) | (((c >> lane) & 1u) << nb_bit(dx, dy, 0)) |
+                  (((above >> lane) & 1u) << nb_bit(dx, dy, 1));
         }
     }
     return nb;
@@ -135,6 +134,114 @@ __device__ __forceinline__ float wall_term(const StepParams& p, int i, int x, in
         }
     }
     return 0.0f;
+}
+
+// Boundary work of one warp that touches a solid cell, a wall ghost or a reflection target.
+// nb is the cell's precomputed neighbourhood word (see build_cellinfo_kernel): bit nb_bit(dx,dy,dz)
+// = solid flag of the neighbour at (dx,dy,dz), bit 13 = the cell itself.
+// Returns true when the cell is dead (bounce-back solid): no collision, no source.
+template <int Q>
+__device__ __forceinline__ bool boundary_path(const StepParams& p, float (&f)[Q], const float* __restrict__ fin, long long row,
+                                              int x, int y, int z, unsigned lane, bool active, bool do_stream, uint32_t nb)
+{
+    const Geom& g = p.g;
+    const int w = (z + PAD_Z) >> 5;
+    const bool solid_here = (nb >> nb_bit(0, 0, 0)) & 1u;
+    bool dead = false;
+    float fx = 0.0f, fy = 0.0f, fz = 0.0f;     // this thread's share of the force on the solid
+    bool has_force = false;
+    if (p.boundary_mode == 1) {
+        // ---- half-way bounce-back off solid neighbours and wall ghosts
+        if (do_stream && (nb & 0x7ffffffu)) {
+#pragma unroll
+            for (int i = 1; i < Q; ++i) {
+                if ((nb >> nb_bit(-dir_c(i, 0), -dir_c(i, 1), -dir_c(i, 2))) & 1u) {
+                    const float back = fin[(long long)dir_inv(i) * g.np];
+                    float v = back;
+                    if (p.wall_moving) v += wall_term<Q>(p, i, x, y, z);
+                    f[i] = v;
+                    // momentum exchange with an obstacle cell (not a domain wall; periodic or halo
+                    // images of obstacle cells count): population inv(i) goes in with -c_i and comes
+                    // back as i with +c_i
+                    if (p.force) {
+                        const int sx = x - dir_c(i, 0), sy = y - dir_c(i, 1), sz = z - dir_c(i, 2);
+                        const bool off_wall = (p.bc[0] == 2 && (sx < 0 || sx >= g.nx)) ||
+                                              (p.bc[1] == 2 && (sy < 0 || sy >= g.ny)) ||
+                                              (p.bc[2] == 2 && (sz < 0 || sz >= g.nz));
+                        if (active && !solid_here && !off_wall) {
+                            const float m = back + v;
+                            fx -= (float)dir_c(i, 0) * m;
+                            fy -= (float)dir_c(i, 1) * m;
+                            fz -= (float)dir_c(i, 2) * m;
+                            has_force = true;
+                        }
+                    }
+                }
+            }
+        }
+        if (solid_here) {
+#pragma unroll
+            for (int i = 0; i < Q; ++i) f[i] = 0.0f;
+            dead = true;
+        }
+    }
+    if ((p.phases & PH_REFLECT) && p.boundary_mode == 0) {
+        // ---- reference reflection as a gather (scatter form: SimCalcFuncs.cu:162-187).  The links of a
+        // target cell are sorted by the population they feed, so the walk below only ever touches f[i]
+        // with a compile-time i and f stays in registers.
+        if (p.tmask && ((nb >> 27) & 1u)) {
+            const uint32_t tw = __ldg(p.tmask + row * g.wz + w);
+            if (active) {
+                const uint32_t rank = __ldg(p.tprefix + row * g.wz + w) + __popc(tw & ((1u << lane) - 1u));
+                uint32_t e = __ldg(p.toff + rank);
+                const uint32_t e1 = __ldg(p.toff + rank + 1);
+#pragma unroll
+                for (int i = 1; i < Q; ++i) {
+                    while (e < e1 && p.links[e].d == i) {
+                        const Link L = p.links[e];
+                        long long src = (long long)L.j * g.np + (long long)L.src_cell;
+                        if (do_stream) src -= pull_offset_dyn(g, L.j);
+                        const float moved = p.fin[src] * L.w;
+                        f[i] += moved;
+                        if (p.force) {
+                            // SimCalcFuncs.cu:181-183; incoming direction from the slot index (reference) or slot/3
+                            const int in_dir = (p.force_mode == 0) ? (int)L.slot : (int)L.j;
+                            if (in_dir < 27) {
+                                const float so = dir_split(i), si = dir_split(in_dir);
+                                fx += moved * (((float)dir_c(i, 0) * so) - ((float)c_dir[in_dir][0] * si));
+                                fy += moved * (((float)dir_c(i, 1) * so) - ((float)c_dir[in_dir][1] * si));
+                                fz += moved * (((float)dir_c(i, 2) * so) - ((float)c_dir[in_dir][2] * si));
+                                has_force = true;
+                            }
+                        }
+                        ++e;
+                    }
+                }
+            }
+        }
+        // solid cells are emptied after the scatter (SimCalcFuncs.cu:189-197)
+        if (solid_here) {
+#pragma unroll
+            for (int i = 0; i < Q; ++i) f[i] = 0.0f;
+        }
+    }
+    if (p.force && __any_sync(FULL, has_force)) {
+        // one atomic triple per warp (the reference issues three atomics per link on one address)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            fx += __shfl_xor_sync(FULL, fx, o);
+            fy += __shfl_xor_sync(FULL, fy, o);
+            fz += __shfl_xor_sync(FULL, fz, o);
+        }
+        if (lane == 0) {
+            // spread over FORCE_SLOTS partial sums so that neighbouring blocks do not serialise on one address
+            double* slot = p.force + 3 * ((blockIdx.x + blockIdx.y * 7u + blockIdx.z * 13u) % FORCE_SLOTS);
+            atomicAdd(slot + 0, (double)fx);
+            atomicAdd(slot + 1, (double)fy);
+            atomicAdd(slot + 2, (double)fz);
+        }
+    }
+    return dead;
 }
 
 template <int Q, int MOMENT, bool EQ64, bool GENERAL>
@@ -166,110 +273,27 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
         for (int i = 0; i < Q; ++i) f[i] = fin[(long long)i * g.np];
     }
 
-    bool skip_collide = false;
+    bool dead = false;
     if (GENERAL) {
-        const int w = (z + PAD_Z) >> 5;
-        bool solid_here = false;
-        float fx = 0.0f, fy = 0.0f, fz = 0.0f;     // this thread's share of the force on the solid
-        bool has_force = false;
-        if (p.solid) {
-            solid_here = (__ldg(p.solid + row * g.wz + w) >> lane) & 1u;
-            if (p.boundary_mode == 1) {
-                // ---- half-way bounce-back off solid neighbours and wall ghosts
-                if (do_stream) {
-                    const uint32_t nb = neighbour_bits(p.solid, row, g.yp, g.wz, w, lane);
-                    if (__any_sync(FULL, nb != 0u)) {
-#pragma unroll
-                        for (int i = 1; i < Q; ++i) {
-                            if ((nb >> nb_bit(-dir_c(i, 0), -dir_c(i, 1), -dir_c(i, 2))) & 1u) {
-                                const float back = fin[(long long)dir_inv(i) * g.np];
-                                float v = back;
-                                if (p.wall_moving) v += wall_term<Q>(p, i, x, y, z);
-                                f[i] = v;
-                                // momentum exchange with an obstacle cell (not a domain wall; periodic or
-                                // halo images of obstacle cells count): population inv(i) goes in with -c_i
-                                // and comes back as i with +c_i
-                                const int sx = x - dir_c(i, 0), sy = y - dir_c(i, 1), sz = z - dir_c(i, 2);
-                                const bool off_wall = (p.bc[0] == 2 && (sx < 0 || sx >= g.nx)) ||
-                                                      (p.bc[1] == 2 && (sy < 0 || sy >= g.ny)) ||
-                                                      (p.bc[2] == 2 && (sz < 0 || sz >= g.nz));
-                                if (p.force && active && !solid_here && !off_wall) {
-                                    const float m = back + v;
-                                    fx -= (float)dir_c(i, 0) * m;
-                                    fy -= (float)dir_c(i, 1) * m;
-                                    fz -= (float)dir_c(i, 2) * m;
-                                    has_force = true;
-                                }
-                            }
-                        }
-                    }
-                }
-                if (solid_here) {
-#pragma unroll
-                    for (int i = 0; i < Q; ++i) f[i] = 0.0f;
-                    skip_collide = true;
-                }
-            }
-        }
-        if ((p.phases & PH_REFLECT) && p.boundary_mode == 0) {
-            // ---- reference reflection as a gather (scatter form: SimCalcFuncs.cu:162-187)
-            if (p.tmask) {
-                const uint32_t tw = __ldg(p.tmask + row * g.wz + w);
-                if (active && ((tw >> lane) & 1u)) {
-                    const uint32_t rank = __ldg(p.tprefix + row * g.wz + w) + __popc(tw & ((1u << lane) - 1u));
-                    const uint32_t e0 = __ldg(p.toff + rank), e1 = __ldg(p.toff + rank + 1);
-                    for (uint32_t e = e0; e < e1; ++e) {
-                        const Link L = p.links[e];
-                        long long src = (long long)L.j * g.np + (long long)L.src_cell;
-                        if (do_stream) src -= pull_offset_dyn(g, L.j);
-                        const float moved = p.fin[src] * L.w;
-#pragma unroll
-                        for (int i = 1; i < Q; ++i)
-                            if (L.d == i) f[i] += moved;
-                        if (p.force) {
-                            // SimCalcFuncs.cu:181-183; incoming direction from the slot index (reference) or slot/3
-                            const int in_dir = (p.force_mode == 0) ? (int)L.slot : (int)L.j;
-                            if (in_dir < 27) {
-                                const float so = dir_split(L.d), si = dir_split(in_dir);
-                                fx += moved * (((float)c_dir[L.d][0] * so) - ((float)c_dir[in_dir][0] * si));
-                                fy += moved * (((float)c_dir[L.d][1] * so) - ((float)c_dir[in_dir][1] * si));
-                                fz += moved * (((float)c_dir[L.d][2] * so) - ((float)c_dir[in_dir][2] * si));
-                                has_force = true;
-                            }
-                        }
-                    }
-                }
-            }
-            // solid cells are emptied after the scatter (SimCalcFuncs.cu:189-197)
-            if (solid_here) {
-#pragma unroll
-                for (int i = 0; i < Q; ++i) f[i] = 0.0f;
-            }
-        }
-        if (p.force && __any_sync(FULL, has_force)) {
-            // one atomic triple per warp (the reference issues three atomics per link on one address)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                fx += __shfl_xor_sync(FULL, fx, o);
-                fy += __shfl_xor_sync(FULL, fy, o);
-                fz += __shfl_xor_sync(FULL, fz, o);
-            }
-            if (lane == 0) {
-                atomicAdd(p.force + 0, (double)fx);
-                atomicAdd(p.force + 1, (double)fy);
-                atomicAdd(p.force + 2, (double)fz);
+        // one int per (row, 32-cell word): -1 for an ordinary fluid warp, which skips all boundary work
+        // on this uniform test, else the slot of the warp's 32 precomputed neighbourhood words
+        if (p.special) {
+            const int slot = __ldg(p.special + row * g.wz + ((z + PAD_Z) >> 5));     // warp-uniform
+            if (slot >= 0) {
+                const uint32_t nb = __ldg(p.cellinfo + (long long)slot * 32 + lane);
+                dead = boundary_path<Q>(p, f, fin, row, x, y, z, lane, active, do_stream, nb);
             }
         }
     }
 
     // ---- BGK relaxation (SimCalcFuncs.cu:98-156); runs on every cell like the reference
-    if ((!GENERAL || (p.phases & PH_COLLIDE)) && !skip_collide) {
+    if ((!GENERAL || (p.phases & PH_COLLIDE)) && !dead) {
         if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
         else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
     }
 
     // ---- additive source on the selected cells (SimCalcFuncs.cu:200-215)
-    if (GENERAL && (p.phases & PH_SOURCE) && p.src_on && !skip_collide) {
+    if (GENERAL && (p.phases & PH_SOURCE) && p.src_on && !dead) {
         if (x >= p.src_lo[0] && x <= p.src_hi[0] && y >= p.src_lo[1] && y <= p.src_hi[1] &&
             z >= p.src_lo[2] && z <= p.src_hi[2]) {
 #pragma unroll
@@ -457,6 +481,49 @@ __global__ void build_mask_kernel(const uint8_t* __restrict__ sb, int has_x_ghos
     if (lane == 0) mask[wid] = word;
 }
 
+// Classifies every interior mask word and precomputes the neighbourhood words of the special ones.
+// One warp per interior (row, word).  A word is special if any of the 27 mask words around it has a
+// solid bit or it holds a reflection target.  fill == 0: count special words into *counter.
+// fill == 1: give each a slot (order is irrelevant), write special[word] = slot and the 32
+// neighbourhood words (bit 27 = reflection target) at cellinfo[slot*32 ..].
+__global__ void build_cellinfo_kernel(const uint32_t* __restrict__ solid, const uint32_t* __restrict__ tmask,
+                                      int* __restrict__ special, uint32_t* __restrict__ cellinfo, unsigned* counter,
+                                      Geom g, int fill)
+{
+    const int wlo = PAD_Z / 32, wcount = (g.nz + 31) / 32;            // words that hold interior cells
+    const long long nwarps = (long long)g.nx * g.ny * wcount;
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    if (wid >= nwarps) return;
+    const int w = wlo + (int)(wid % wcount);
+    const long long r = wid / wcount;
+    const int y = (int)(r % g.ny), x = (int)(r / g.ny);
+    const long long row = (long long)(x + 1) * g.yp + (y + 1);
+    const long long widx = row * g.wz + w;
+    uint32_t near = 0, nb = 0;
+    if (solid) {
+        // lanes 0..26 each look at one of the 27 surrounding words
+        if (lane < 27) {
+            const int dx = (int)lane / 9 - 1, dy = ((int)lane / 3) % 3 - 1, dw = (int)lane % 3 - 1;
+            near = solid[(row + (long long)dx * g.yp + dy) * g.wz + w + dw];
+        }
+        near = __any_sync(FULL, near != 0u);
+        if (near) nb = neighbour_bits(solid, row, g.yp, g.wz, w, lane);
+    }
+    const uint32_t tw = tmask ? tmask[widx] : 0u;
+    if (!near && !tw) return;
+    nb |= ((tw >> lane) & 1u) << 27;
+    if (!fill) {
+        if (lane == 0) atomicAdd(counter, 1u);
+        return;
+    }
+    unsigned slot = 0;
+    if (lane == 0) slot = atomicAdd(counter, 1u);
+    slot = __shfl_sync(FULL, slot, 0);
+    if (lane == 0) special[widx] = (int)slot;
+    cellinfo[(long long)slot * 32 + lane] = nb;
+}
+
 __global__ void mask_to_bytes_kernel(const uint32_t* __restrict__ mask, uint8_t* __restrict__ sb, Geom g)
 {
     const long long per = (long long)g.ny * g.nz;
@@ -497,23 +564,27 @@ __global__ void moments_kernel(const float* __restrict__ f, Geom g, int moment_m
     if (uz) uz[k] = mz;
 }
 
-// mass and momentum in double: per-thread partial over a z-row segment, warp shuffle
-// reduction, one atomic quadruple per warp
+// mass and momentum in double: warps stride over the interior rows, lanes over z; shuffle reduction
+// per warp, shared-memory reduction per block, one atomic quadruple per block
 template <int Q>
-__global__ void mass_momentum_kernel(const float* __restrict__ f, Geom g, double* out4)
+__global__ void __launch_bounds__(256) mass_momentum_kernel(const float* __restrict__ f, Geom g, double* out4)
 {
-    const int z = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y, x = blockIdx.z;
+    const long long rows = (long long)g.nx * g.ny;
+    const int warps_per_block = blockDim.x >> 5;
+    const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     double m = 0.0, px = 0.0, py = 0.0, pz = 0.0;
-    if (z < g.nz) {
-        const long long idx = g.cell(x, y, z);
+    for (long long r = (long long)blockIdx.x * warps_per_block + wib; r < rows; r += (long long)gridDim.x * warps_per_block) {
+        const int x = (int)(r / g.ny), y = (int)(r % g.ny);
+        const long long base = g.cell(x, y, 0);
+        for (int z = (int)lane; z < g.nz; z += 32) {
 #pragma unroll
-        for (int i = 0; i < Q; ++i) {
-            const double v = (double)f[(long long)i * g.np + idx];
-            m += v;
-            px += v * dir_c(i, 0);
-            py += v * dir_c(i, 1);
-            pz += v * dir_c(i, 2);
+            for (int i = 0; i < Q; ++i) {
+                const double v = (double)f[(long long)i * g.np + base + z];
+                m += v;
+                px += v * dir_c(i, 0);
+                py += v * dir_c(i, 1);
+                pz += v * dir_c(i, 2);
+            }
         }
     }
 #pragma unroll
@@ -523,11 +594,13 @@ __global__ void mass_momentum_kernel(const float* __restrict__ f, Geom g, double
         py += __shfl_xor_sync(FULL, py, o);
         pz += __shfl_xor_sync(FULL, pz, o);
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(out4 + 0, m);
-        atomicAdd(out4 + 1, px);
-        atomicAdd(out4 + 2, py);
-        atomicAdd(out4 + 3, pz);
+    __shared__ double part[8][4];
+    if (lane == 0) { part[wib][0] = m; part[wib][1] = px; part[wib][2] = py; part[wib][3] = pz; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int k = 0; k < warps_per_block; ++k) t += part[k][threadIdx.x];
+        atomicAdd(out4 + threadIdx.x, t);
     }
 }
 
@@ -601,6 +674,15 @@ cudaError_t launch_build_mask(const uint8_t* solid_bytes, int has_x_ghost, uint3
     return cudaGetLastError();
 }
 
+cudaError_t launch_build_cellinfo(const uint32_t* solid, const uint32_t* tmask, int* special, uint32_t* cellinfo,
+                                  unsigned* counter, const Geom& g, int fill, cudaStream_t stream)
+{
+    const long long nwarps = (long long)g.nx * g.ny * ((g.nz + 31) / 32);
+    const long long threads = nwarps * 32;
+    build_cellinfo_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(solid, tmask, special, cellinfo, counter, g, fill);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mask_to_bytes(const uint32_t* mask, uint8_t* solid_bytes, const Geom& g, cudaStream_t stream)
 {
     const long long n = (long long)g.nx * g.ny * g.nz;
@@ -618,9 +700,9 @@ cudaError_t launch_moments(const float* f, const Geom& g, int q, int moment_mode
 
 cudaError_t launch_mass_momentum(const float* f, const Geom& g, int q, double* out4, cudaStream_t stream)
 {
-    dim3 grid((g.nz + 127) / 128, g.ny, g.nx);
-    if (q == 27) mass_momentum_kernel<27><<<grid, 128, 0, stream>>>(f, g, out4);
-    else         mass_momentum_kernel<19><<<grid, 128, 0, stream>>>(f, g, out4);
+    const int grid = 148 * 8;      // one resident wave: 8 blocks of 256 threads per SM
+    if (q == 27) mass_momentum_kernel<27><<<grid, 256, 0, stream>>>(f, g, out4);
+    else         mass_momentum_kernel<19><<<grid, 256, 0, stream>>>(f, g, out4);
     return cudaGetLastError();
 }
 

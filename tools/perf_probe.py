@@ -1,0 +1,56 @@
+"""Quick throughput probe of the step kernel variants (device-resident, CUDA-event timed).
+usage: python tools/perf_probe.py [size] [steps]"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import latticeboltzmanncuda_b200 as lb
+from latticeboltzmanncuda_b200.shapes import tapered_hexahedron_mask
+
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+PEAK = 6546.2
+
+
+def run(name, q, eq, bc, boundary, obstacle, source, moment=lb.MOMENT_STANDARD, engine=lb.ENGINE_AUTO):
+    lat = lb.Lattice(S, S, S, None, None, lb.FluidData(1.0, 0.6), 1.0 / S, q=q, bc=bc, moment_mode=moment,
+                     eq_precision=eq, boundary_mode=boundary, engine=engine)
+    w = np.array([1 / 3] + [1 / 18] * 6 + [1 / 36] * 12, np.float32) if q == 19 else \
+        np.array([8 / 27] + [2 / 27] * 6 + [1 / 54] * 12 + [1 / 216] * 8, np.float32)
+    f = np.empty((q, S, S, S), np.float32)
+    for i in range(q):
+        f[i] = w[i]
+    if obstacle:
+        solid = tapered_hexahedron_mask(S, S, S)
+        f[:, solid.astype(bool)] = 0
+        lat.set_solid_mask(solid)
+    lat.load_populations(f)
+    del f
+    if source:
+        flow = np.zeros(27, np.float32); flow[:q] = 0.001; flow[6] = 0.002
+        lat.setFlowData(lb.FlowData(((0, None, None), (0, None, None)), flow))
+    lat.step(5)
+    lat.sync()
+    ms, launches = lat.step_timed(K)
+    mlups = S ** 3 * K / (ms * 1e-3) / 1e6
+    gbs = mlups * 1e6 * 2 * q * 4 / 1e9
+    print("%-44s %8.0f MLUPS %7.0f GB/s %5.1f%% of %.0f  (%.3f ms/step, %d launches)" %
+          (name, mlups, gbs, 100 * gbs / PEAK, PEAK, ms / K, launches), flush=True)
+    lat.close()
+
+
+Z, P, W = lb.BC_ZERO_INFLOW, lb.BC_PERIODIC, lb.BC_WALL
+BB, RF = lb.BOUNDARY_BOUNCE_BACK, lb.BOUNDARY_REFLECT
+which = sys.argv[3] if len(sys.argv) > 3 else "all"
+if which in ("all", "fast"):
+    run("q19 fp32 fast (no geometry, zero-inflow)", 19, lb.EQ_FP32, (Z, Z, Z), BB, False, False)
+if which in ("all", "headline"):
+    run("q19 fp32 general obstacle+walls+source", 19, lb.EQ_FP32, (Z, W, W), BB, True, True)
+if which in ("all",):
+    run("q19 fp32 periodic xyz (3 ghost fills)", 19, lb.EQ_FP32, (P, P, P), BB, False, False)
+    run("q27 fp32 fast", 27, lb.EQ_FP32, (Z, Z, Z), BB, False, False)
+    run("q27 fp32 general obstacle+walls+source", 27, lb.EQ_FP32, (Z, W, W), BB, True, True)
+    run("q27 fp64-eq reference mode fast", 27, lb.EQ_FP64, (Z, Z, Z), RF, False, False, moment=lb.MOMENT_REFERENCE)
+    run("q19 fp64-eq fast", 19, lb.EQ_FP64, (Z, Z, Z), BB, False, False)
