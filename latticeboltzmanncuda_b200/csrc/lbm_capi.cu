@@ -54,9 +54,14 @@ struct lbm_lattice_s {
     float* buf[2] = {nullptr, nullptr};
     int cur = 0;
     bool pending_commit = false;
+    unsigned pending_phases = 0;
     uint32_t* solid = nullptr;       // padded bit mask
-    int* special = nullptr;          // per mask word: slot of the warp's neighbourhood words or -1
-    uint32_t* cellinfo = nullptr;    // [n_special][32] neighbourhood words
+    uint8_t* cls = nullptr;          // class of every interior 32-cell word, [x][word][y]
+    int cls_pitch = 0;
+    size_t cls_bytes = 0;
+    int dead_dirty = 2;              // steps for which all-solid words must still be written as zeros
+    uint32_t* cellinfo = nullptr;    // neighbourhood word per padded cell (special words only)
+    uint32_t* special_list = nullptr;   // mask-word indices of the special words
     size_t n_special = 0;
     bool any_solid = false;          // some bit set (geometry or wall ghosts)
     uint8_t* solid_bytes = nullptr;  // nx*ny*nz (+2 planes) scratch
@@ -100,32 +105,55 @@ __global__ void any_nonzero_kernel(const uint32_t* w, size_t n, unsigned* flag)
     if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
-// recompute which warps need the boundary path and their neighbourhood words; call after the solid
-// mask or the link lists change
+// keep the class array resident in L2: it is a few MB, read by every warp before anything else, and
+// would otherwise be evicted by the population stream every step
+void pin_classes_in_l2(lbm_handle h)
+{
+    int dev = h->device, max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    if (max_persist <= 0 || max_window <= 0) return;
+    size_t want = h->cls_bytes < (size_t)max_persist ? h->cls_bytes : (size_t)max_persist;
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    cudaStreamAttrValue attr;
+    std::memset(&attr, 0, sizeof attr);
+    attr.accessPolicyWindow.base_ptr = h->cls;
+    attr.accessPolicyWindow.num_bytes = h->cls_bytes < (size_t)max_window ? h->cls_bytes : (size_t)max_window;
+    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaStreamSetAttribute(h->side, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();   // best effort: an unsupported attribute must not poison later calls
+}
+
+// rebuild the classification of every interior 32-cell word and the neighbourhood words of the special
+// ones; call after the solid mask or the link lists change
 int rebuild_special(lbm_handle h)
 {
-    const size_t words = h->mask_words();
-    if (!h->special) CK(cudaMalloc(&h->special, words * sizeof(int)));
-    if (!h->flag) CK(cudaMalloc(&h->flag, sizeof(unsigned)));
+    const Geom& g = h->g;
+    const int wcount = (g.nz + 31) / 32;
+    if (!h->cls) {
+        h->cls_pitch = ((g.ny + 3) / 4) * 4;
+        h->cls_bytes = (size_t)g.nx * wcount * h->cls_pitch;
+        CK(cudaMalloc(&h->cls, h->cls_bytes));
+        pin_classes_in_l2(h);
+    }
     const uint32_t* solid = h->any_solid ? h->solid : nullptr;
     const uint32_t* tmask = h->nlinks ? h->tmask : nullptr;
-    CK(cudaMemsetAsync(h->special, 0xFF, words * sizeof(int), h->stream));
+    if ((solid || tmask) && !h->cellinfo) {
+        CK(cudaMalloc(&h->cellinfo, (size_t)g.np * sizeof(uint32_t)));
+        CK(cudaMalloc(&h->special_list, (size_t)g.nx * g.ny * wcount * sizeof(uint32_t)));
+    }
+    if (!h->flag) CK(cudaMalloc(&h->flag, sizeof(unsigned)));
     CK(cudaMemsetAsync(h->flag, 0, sizeof(unsigned), h->stream));
-    h->n_special = 0;
-    if (!solid && !tmask) { CK(cudaStreamSynchronize(h->stream)); return LBM_OK; }
-    CK(launch_build_cellinfo(solid, tmask, h->special, nullptr, h->flag, h->g, 0, h->stream));
+    CK(cudaMemsetAsync(h->cls, 0, h->cls_bytes, h->stream));
+    CK(launch_build_cellinfo(solid, tmask, h->cls, h->cls_pitch, h->cellinfo, h->special_list, h->flag, g, h->stream));
     unsigned n = 0;
     CK(cudaMemcpyAsync(&n, h->flag, sizeof n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(h->cellinfo);
-    h->cellinfo = nullptr;
-    if (n) {
-        CK(cudaMalloc(&h->cellinfo, (size_t)n * 32 * sizeof(uint32_t)));
-        CK(cudaMemsetAsync(h->flag, 0, sizeof(unsigned), h->stream));
-        CK(launch_build_cellinfo(solid, tmask, h->special, h->cellinfo, h->flag, h->g, 1, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-    }
     h->n_special = n;
+    h->dead_dirty = 2;
     return LBM_OK;
 }
 
@@ -159,8 +187,16 @@ void fill_params(lbm_handle h, StepParams& p, unsigned phases, int x0, int x1)
     p.phases = phases;
     p.boundary_mode = h->cfg.boundary_mode;
     p.solid = h->any_solid ? h->solid : nullptr;
-    p.special = h->n_special ? h->special : nullptr;
+    p.cls = h->cls;
+    p.cls_pitch = h->cls_pitch;
     p.cellinfo = h->cellinfo;
+    p.special_list = h->special_list;
+    p.n_special = (long long)h->n_special;
+    // all-solid words hold zeros and are never read: bounce-back solids are dead in every phase, the
+    // reference's solids are emptied by the reflect phase.  They are written while stale values may remain.
+    const bool dead_ok = h->cfg.boundary_mode == LBM_BOUNDARY_BOUNCE_BACK || (phases & PH_REFLECT);
+    const bool src_hits_dead = h->cfg.boundary_mode == LBM_BOUNDARY_REFLECT && (phases & PH_SOURCE) && h->src_on;
+    p.dead_mode = !dead_ok ? 0 : ((h->dead_dirty > 0 || src_hits_dead) ? 1 : 2);
     if (h->nlinks) {
         p.tmask = h->tmask; p.tprefix = h->tprefix; p.toff = h->toff; p.links = h->links;
     }
@@ -196,8 +232,16 @@ int launch_range(lbm_handle h, unsigned phases, int x0, int x1, cudaStream_t s)
     c.eq64 = h->cfg.eq_precision == LBM_EQ_FP64;
     c.general = fast_path_ok(h, phases) ? 0 : 1;
     CK(launch_step(c, p, s));
-    h->launches += 1;
+    h->launches += 1 + ((c.general && h->n_special) ? 1 : 0);
     return LBM_OK;
+}
+
+// after a step: the buffer just written has clean (zero) all-solid words if the step wrote or skipped them
+void note_step_done(lbm_handle h, unsigned phases)
+{
+    const bool dead_ok = h->cfg.boundary_mode == LBM_BOUNDARY_BOUNCE_BACK || (phases & PH_REFLECT);
+    if (!dead_ok) h->dead_dirty = 2;
+    else if (h->dead_dirty > 0) h->dead_dirty -= 1;
 }
 
 int fill_ghosts(lbm_handle h, bool include_x)
@@ -223,6 +267,7 @@ int one_step(lbm_handle h, unsigned phases)
     int rc = launch_range(h, phases, 0, h->g.nx, h->stream);
     if (rc) return rc;
     h->cur ^= 1;
+    note_step_done(h, phases);
     return LBM_OK;
 }
 
@@ -299,8 +344,9 @@ LBM_API int lbm_create(const lbm_config* cfg, lbm_handle* out)
     CKB(cudaMemsetAsync(h->force, 0, 3 * FORCE_SLOTS * sizeof(double), h->stream));
     CKB(cudaMalloc(&h->diag, 4 * sizeof(double)));
 #undef CKB
-    if (has_wall(h->cfg)) {
-        int rc = rebuild_mask(h, nullptr, 0);   // wall ghosts are solid bits even without geometry
+    {
+        // wall ghosts are solid bits even without geometry; the task list exists in every case
+        int rc = has_wall(h->cfg) ? rebuild_mask(h, nullptr, 0) : rebuild_special(h);
         if (rc) return bail(rc);
     }
     cudaError_t e = cudaStreamSynchronize(h->stream);
@@ -316,7 +362,7 @@ LBM_API int lbm_destroy(lbm_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->side) cudaStreamSynchronize(h->side);
     for (int b = 0; b < 2; ++b) cudaFree(h->buf[b]);
-    cudaFree(h->solid); cudaFree(h->special); cudaFree(h->cellinfo); cudaFree(h->solid_bytes); cudaFree(h->tmask); cudaFree(h->tprefix); cudaFree(h->toff);
+    cudaFree(h->solid); cudaFree(h->cls); cudaFree(h->cellinfo); cudaFree(h->special_list); cudaFree(h->solid_bytes); cudaFree(h->tmask); cudaFree(h->tprefix); cudaFree(h->toff);
     cudaFree(h->reflected); cudaFree(h->links); cudaFree(h->force); cudaFree(h->diag); cudaFree(h->flag);
     cudaFree(h->staging);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -370,6 +416,7 @@ LBM_API int lbm_upload_aos(lbm_handle h, const void* cells, size_t count)
         CK(launch_unpack_aos(h->staging, h->buf[h->cur], h->solid_bytes, g, h->cfg.q, x0, nxc, h->stream));
         CK(cudaStreamSynchronize(h->stream));   // staging is reused by the next chunk
     }
+    h->dead_dirty = 2;
     return rebuild_mask(h, h->solid_bytes, 0);
 }
 
@@ -421,6 +468,7 @@ LBM_API int lbm_upload_f_soa(lbm_handle h, const float* f)
     }
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaStreamSynchronize(h->side));
+    h->dead_dirty = 2;
     return LBM_OK;
 }
 
@@ -753,6 +801,7 @@ LBM_API int lbm_step_range(lbm_handle h, unsigned phases, int x0, int x1, int on
     }
     if (rc) return rc;
     h->pending_commit = true;
+    h->pending_phases = phases;
     return LBM_OK;
 }
 
@@ -766,6 +815,7 @@ LBM_API int lbm_step_commit(lbm_handle h)
     CK(cudaStreamWaitEvent(h->stream, h->ev_side, 0));
     h->cur ^= 1;
     h->pending_commit = false;
+    note_step_done(h, h->pending_phases);
     return LBM_OK;
 }
 

@@ -70,8 +70,12 @@ struct StepParams {
     unsigned phases;
     int   boundary_mode;      // 0 reflect (reference), 1 bounce-back
     const uint32_t* solid;    // padded bit mask or nullptr
-    const int*      special;  // per mask word: -1 ordinary warp, else slot of its 32 neighbourhood words (nullptr: none)
-    const uint32_t* cellinfo; // [slot][32]: bits 0..26 solid flags of the 3x3x3 neighbourhood, bit 27 reflection target
+    const uint8_t*  cls;      // class of every interior 32-cell word, [x][word][y], pitch cls_pitch
+    int   cls_pitch;
+    const uint32_t* special_list;   // mask-word indices of the special words
+    long long n_special;
+    int   dead_mode;          // all-solid words: 0 process like any other, 1 write zeros, 2 skip
+    const uint32_t* cellinfo; // per padded cell of special words: bits 0..26 solid flags of the 3x3x3 neighbourhood, bit 27 reflection target
     const uint32_t* tmask;    // link-target bits or nullptr
     const uint32_t* tprefix;  // exclusive popcount prefix per mask word
     const uint32_t* toff;     // CSR offsets per target cell
@@ -107,9 +111,9 @@ cudaError_t launch_gather_dense(float* dense, const float* fq, const Geom& g, in
 
 // solid bytes (host order, optionally with x ghost planes) -> padded bit mask incl. ghost bits
 cudaError_t launch_build_mask(const uint8_t* solid_bytes, int has_x_ghost, uint32_t* mask, const Geom& g, const int bc[3], cudaStream_t stream);
-// classify interior mask words (fill = 0 counts the special ones, fill = 1 assigns slots and writes cellinfo)
-cudaError_t launch_build_cellinfo(const uint32_t* solid, const uint32_t* tmask, int* special, uint32_t* cellinfo,
-                                  unsigned* counter, const Geom& g, int fill, cudaStream_t stream);
+// classify interior mask words and write the neighbourhood words of the special ones
+cudaError_t launch_build_cellinfo(const uint32_t* solid, const uint32_t* tmask, uint8_t* cls, int cls_pitch,
+                                  uint32_t* cellinfo, uint32_t* special_list, unsigned* counter, const Geom& g, cudaStream_t stream);
 cudaError_t launch_mask_to_bytes(const uint32_t* mask, uint8_t* solid_bytes, const Geom& g, cudaStream_t stream);
 
 // moments / reductions

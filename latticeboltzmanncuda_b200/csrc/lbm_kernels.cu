@@ -10,6 +10,7 @@
 #include "lbm_device.h"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace lbm {
 
@@ -141,11 +142,10 @@ __device__ __forceinline__ float wall_term(const StepParams& p, int i, int x, in
 // = solid flag of the neighbour at (dx,dy,dz), bit 13 = the cell itself.
 // Returns true when the cell is dead (bounce-back solid): no collision, no source.
 template <int Q>
-__device__ __forceinline__ bool boundary_path(const StepParams& p, float (&f)[Q], const float* __restrict__ fin, long long row,
+__device__ __forceinline__ bool boundary_path(const StepParams& p, float (&f)[Q], const float* __restrict__ fin, long long widx,
                                               int x, int y, int z, unsigned lane, bool active, bool do_stream, uint32_t nb)
 {
     const Geom& g = p.g;
-    const int w = (z + PAD_Z) >> 5;
     const bool solid_here = (nb >> nb_bit(0, 0, 0)) & 1u;
     bool dead = false;
     float fx = 0.0f, fy = 0.0f, fz = 0.0f;     // this thread's share of the force on the solid
@@ -190,9 +190,9 @@ __device__ __forceinline__ bool boundary_path(const StepParams& p, float (&f)[Q]
         // target cell are sorted by the population they feed, so the walk below only ever touches f[i]
         // with a compile-time i and f stays in registers.
         if (p.tmask && ((nb >> 27) & 1u)) {
-            const uint32_t tw = __ldg(p.tmask + row * g.wz + w);
+            const uint32_t tw = __ldg(p.tmask + widx);
             if (active) {
-                const uint32_t rank = __ldg(p.tprefix + row * g.wz + w) + __popc(tw & ((1u << lane) - 1u));
+                const uint32_t rank = __ldg(p.tprefix + widx) + __popc(tw & ((1u << lane) - 1u));
                 uint32_t e = __ldg(p.toff + rank);
                 const uint32_t e1 = __ldg(p.toff + rank + 1);
 #pragma unroll
@@ -235,7 +235,7 @@ __device__ __forceinline__ bool boundary_path(const StepParams& p, float (&f)[Q]
         }
         if (lane == 0) {
             // spread over FORCE_SLOTS partial sums so that neighbouring blocks do not serialise on one address
-            double* slot = p.force + 3 * ((blockIdx.x + blockIdx.y * 7u + blockIdx.z * 13u) % FORCE_SLOTS);
+            double* slot = p.force + 3 * ((unsigned)(widx >> 2) % FORCE_SLOTS);
             atomicAdd(slot + 0, (double)fx);
             atomicAdd(slot + 1, (double)fy);
             atomicAdd(slot + 2, (double)fz);
@@ -244,26 +244,127 @@ __device__ __forceinline__ bool boundary_path(const StepParams& p, float (&f)[Q]
     return dead;
 }
 
-template <int Q, int MOMENT, bool EQ64, bool GENERAL>
+// Dense kernel for an all-fluid lattice: one warp per 32 consecutive z of an (x, y) row, pull +
+// collide, nothing else.  Used when there is no geometry, no wall, no source and the phases are
+// stream + collide.
+template <int Q, int MOMENT, bool EQ64>
 __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepParams p)
 {
     const Geom& g = p.g;
-    const unsigned lane = threadIdx.x & 31u;
-    int z = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int x = p.x0 + blockIdx.z;
-    const bool active = (z < g.nz) && (y < g.ny);
-    if (z >= g.nz) z = g.nz - 1;          // keep whole warps alive for the warp-wide steps
-    if (y >= g.ny) y = g.ny - 1;
+    if (z >= g.nz || y >= g.ny) return;
 
-    const long long row = (long long)(x + 1) * g.yp + (y + 1);
-    const long long idx = row * g.zp + (z + PAD_Z);
+    const long long idx = ((long long)(x + 1) * g.yp + (y + 1)) * g.zp + (z + PAD_Z);
     const float* __restrict__ fin = p.fin + idx;
-
-    const bool do_stream = !GENERAL || (p.phases & PH_STREAM);
     float f[Q];
-
     // ---- pull: f_i(x) <- f_i(x - c_i)   (SimCalcFuncs.cu:83-94, j = INVERSE[i] relabelled)
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+        f[i] = fin[(long long)i * g.np - ((long long)dir_c(i, 0) * g.plane + (long long)(dir_c(i, 1) * g.zp + dir_c(i, 2)))];
+    // ---- BGK relaxation (SimCalcFuncs.cu:98-156)
+    if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
+    else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
+    float* __restrict__ fout = p.fout + idx;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) fout[(long long)i * g.np] = f[i];
+}
+
+// General kernel.  Every 32-cell word of every interior row was classified when the geometry was set
+// (build_cellinfo_kernel): ordinary fluid, dead (all cells solid) or special (touches a solid cell, a
+// wall ghost or a reflection target).  A warp owns one z-word and walks ROWS_PER_WARP consecutive rows;
+// the classes of those rows are adjacent bytes, fetched with one 4-byte load from an array that is kept
+// resident in L2 (persisting access window), so dead words cost no population traffic at all and
+// ordinary words run the same code as the dense kernel:
+//   ordinary  pull, collide, (source), store;
+//   dead      nothing to read; zeros are written while the buffers may still hold stale values there
+//             (dead_mode 1) and nothing at all afterwards (dead_mode 2);
+//   special   skipped here: step_special_kernel walks the compact list of special words.
+constexpr int ROWS_PER_WARP = 4;
+enum : unsigned { CLS_ORDINARY = 0, CLS_DEAD = 1, CLS_SPECIAL = 2 };
+
+template <int Q, int MOMENT, bool EQ64, int MINB>
+__global__ void __launch_bounds__(128, MINB) step_general_kernel(const __grid_constant__ StepParams p)
+{
+    const Geom& g = p.g;
+    const unsigned lane = threadIdx.x & 31u;
+    const int wi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // z-word of this warp
+    const int wcount = (g.nz + 31) >> 5;
+    if (wi >= wcount) return;
+    const int x = p.x0 + blockIdx.z;
+    const int y0 = blockIdx.y * ROWS_PER_WARP;
+    const int z = wi * 32 + (int)lane;
+    const bool active = z < g.nz;
+    const bool do_stream = p.phases & PH_STREAM;
+    const uint32_t cls4 = __ldg(reinterpret_cast<const uint32_t*>(p.cls + ((long long)x * wcount + wi) * p.cls_pitch + y0));
+
+#pragma unroll 1
+    for (int r = 0; r < ROWS_PER_WARP; ++r) {
+        const int y = y0 + r;
+        if (y >= g.ny) break;
+        const unsigned cls = (cls4 >> (8 * r)) & 0xffu;
+        if (cls == CLS_SPECIAL) continue;              // step_special_kernel owns these words
+        const long long idx = ((long long)(x + 1) * g.yp + (y + 1)) * g.zp + (z + PAD_Z);
+        float f[Q];
+        bool dead = false;
+        if (cls == CLS_DEAD && p.dead_mode) {
+            if (p.dead_mode == 2) continue;
+            dead = true;
+#pragma unroll
+            for (int i = 0; i < Q; ++i) f[i] = 0.0f;
+        } else {
+            const float* __restrict__ fin = p.fin + idx;
+            if (do_stream) {
+#pragma unroll
+                for (int i = 0; i < Q; ++i)
+                    f[i] = fin[(long long)i * g.np - ((long long)dir_c(i, 0) * g.plane + (long long)(dir_c(i, 1) * g.zp + dir_c(i, 2)))];
+            } else {
+#pragma unroll
+                for (int i = 0; i < Q; ++i) f[i] = fin[(long long)i * g.np];
+            }
+            // ---- BGK relaxation (SimCalcFuncs.cu:98-156); runs on every live cell like the reference
+            if (p.phases & PH_COLLIDE) {
+                if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
+                else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
+            }
+        }
+        // ---- additive source on the selected cells (SimCalcFuncs.cu:200-215); bounce-back solids take none
+        if ((p.phases & PH_SOURCE) && p.src_on && !(dead && p.boundary_mode == 1)) {
+            if (x >= p.src_lo[0] && x <= p.src_hi[0] && y >= p.src_lo[1] && y <= p.src_hi[1] &&
+                z >= p.src_lo[2] && z <= p.src_hi[2]) {
+#pragma unroll
+                for (int i = 0; i < Q; ++i) f[i] += p.src_f[i];
+            }
+        }
+        if (active) {
+            float* __restrict__ fout = p.fout + idx;
+#pragma unroll
+            for (int i = 0; i < Q; ++i) fout[(long long)i * g.np] = f[i];
+        }
+    }
+}
+
+// Special words (touching a solid cell, a wall ghost or a reflection target): one warp per entry of the
+// compact list built with the classification.  Same step as everywhere else plus boundary_path().
+template <int Q, int MOMENT, bool EQ64>
+__global__ void __launch_bounds__(128) step_special_kernel(const __grid_constant__ StepParams p)
+{
+    const Geom& g = p.g;
+    const unsigned lane = threadIdx.x & 31u;
+    const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= p.n_special) return;
+    const uint32_t widx = __ldg(p.special_list + k);          // mask-word index = padded cell index / 32
+    const int w = (int)(widx % (uint32_t)g.wz);
+    const uint32_t row = widx / (uint32_t)g.wz;
+    const int x = (int)(row / (uint32_t)g.yp) - 1, y = (int)(row % (uint32_t)g.yp) - 1;
+    if (x < p.x0 || x >= p.x1) return;
+    const int z = w * 32 - PAD_Z + (int)lane;
+    const bool active = z < g.nz;
+    const bool do_stream = p.phases & PH_STREAM;
+    const long long idx = (long long)widx * 32 + lane;
+    const float* __restrict__ fin = p.fin + idx;
+    float f[Q];
     if (do_stream) {
 #pragma unroll
         for (int i = 0; i < Q; ++i)
@@ -272,35 +373,19 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
 #pragma unroll
         for (int i = 0; i < Q; ++i) f[i] = fin[(long long)i * g.np];
     }
-
-    bool dead = false;
-    if (GENERAL) {
-        // one int per (row, 32-cell word): -1 for an ordinary fluid warp, which skips all boundary work
-        // on this uniform test, else the slot of the warp's 32 precomputed neighbourhood words
-        if (p.special) {
-            const int slot = __ldg(p.special + row * g.wz + ((z + PAD_Z) >> 5));     // warp-uniform
-            if (slot >= 0) {
-                const uint32_t nb = __ldg(p.cellinfo + (long long)slot * 32 + lane);
-                dead = boundary_path<Q>(p, f, fin, row, x, y, z, lane, active, do_stream, nb);
-            }
-        }
-    }
-
-    // ---- BGK relaxation (SimCalcFuncs.cu:98-156); runs on every cell like the reference
-    if ((!GENERAL || (p.phases & PH_COLLIDE)) && !dead) {
+    const uint32_t nb = __ldg(p.cellinfo + idx);
+    const bool dead = boundary_path<Q>(p, f, fin, (long long)widx, x, y, z, lane, active, do_stream, nb);
+    if ((p.phases & PH_COLLIDE) && !dead) {
         if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
         else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
     }
-
-    // ---- additive source on the selected cells (SimCalcFuncs.cu:200-215)
-    if (GENERAL && (p.phases & PH_SOURCE) && p.src_on && !dead) {
+    if ((p.phases & PH_SOURCE) && p.src_on && !(dead && p.boundary_mode == 1)) {
         if (x >= p.src_lo[0] && x <= p.src_hi[0] && y >= p.src_lo[1] && y <= p.src_hi[1] &&
             z >= p.src_lo[2] && z <= p.src_hi[2]) {
 #pragma unroll
             for (int i = 0; i < Q; ++i) f[i] += p.src_f[i];
         }
     }
-
     if (active) {
         float* __restrict__ fout = p.fout + idx;
 #pragma unroll
@@ -308,18 +393,52 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
     }
 }
 
-template <int Q, int MOMENT, bool EQ64, bool GENERAL>
-cudaError_t launch_step_t(const StepParams& p, cudaStream_t stream)
+// threads per block of the step kernel (tuning knob, LBM_BLOCK_THREADS = 64 / 128 / 256)
+static int step_block_threads()
+{
+    static int v = [] {
+        const char* e = getenv("LBM_BLOCK_THREADS");
+        int t = e ? atoi(e) : 128;
+        return (t == 64 || t == 128 || t == 256) ? t : 128;
+    }();
+    return v;
+}
+
+template <int Q, int MOMENT, bool EQ64>
+cudaError_t launch_step_dense(const StepParams& p, cudaStream_t stream)
 {
     const Geom& g = p.g;
+    const int threads = step_block_threads();
     int bz = ((g.nz + 31) / 32) * 32;
     if (bz > 128) bz = 128;
-    int by = 256 / bz;
+    if (bz > threads) bz = threads;
+    int by = threads / bz;
     if (by > g.ny) by = g.ny;
     dim3 block(bz, by, 1);
     dim3 grid((g.nz + bz - 1) / bz, (g.ny + by - 1) / by, p.x1 - p.x0);
     if (p.x1 <= p.x0) return cudaSuccess;
-    step_kernel<Q, MOMENT, EQ64, GENERAL><<<grid, block, 0, stream>>>(p);
+    static int smem = [] { const char* e = getenv("LBM_DENSE_SMEM"); return e ? atoi(e) : 0; }();   // occupancy experiment
+    if (smem > 48 * 1024) cudaFuncSetAttribute(step_kernel<Q, MOMENT, EQ64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    step_kernel<Q, MOMENT, EQ64><<<grid, block, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int Q, int MOMENT, bool EQ64>
+cudaError_t launch_step_tasks(const StepParams& p, cudaStream_t stream)
+{
+    if (p.x1 <= p.x0) return cudaSuccess;
+    const Geom& g = p.g;
+    const int wcount = (g.nz + 31) / 32;
+    const int warps = wcount < 4 ? wcount : 4;
+    dim3 block(32 * warps, 1, 1);
+    dim3 grid((wcount + warps - 1) / warps, (g.ny + ROWS_PER_WARP - 1) / ROWS_PER_WARP, p.x1 - p.x0);
+    static int minb = [] { const char* e = getenv("LBM_GENERAL_MINB"); return e ? atoi(e) : 10; }();   // tuning knob
+    if (minb >= 12) step_general_kernel<Q, MOMENT, EQ64, 12><<<grid, block, 0, stream>>>(p);
+    else            step_general_kernel<Q, MOMENT, EQ64, 10><<<grid, block, 0, stream>>>(p);
+    if (p.n_special > 0) {
+        const long long blocks = (p.n_special + 3) / 4;
+        step_special_kernel<Q, MOMENT, EQ64><<<(unsigned)blocks, 128, 0, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 
@@ -328,14 +447,14 @@ cudaError_t launch_step_q(const LaunchCfg& c, const StepParams& p, cudaStream_t 
 {
     const int key = (c.moment_mode ? 4 : 0) | (c.eq64 ? 2 : 0) | (c.general ? 1 : 0);
     switch (key) {
-        case 0: return launch_step_t<Q, 0, false, false>(p, s);
-        case 1: return launch_step_t<Q, 0, false, true>(p, s);
-        case 2: return launch_step_t<Q, 0, true, false>(p, s);
-        case 3: return launch_step_t<Q, 0, true, true>(p, s);
-        case 4: return launch_step_t<Q, 1, false, false>(p, s);
-        case 5: return launch_step_t<Q, 1, false, true>(p, s);
-        case 6: return launch_step_t<Q, 1, true, false>(p, s);
-        default: return launch_step_t<Q, 1, true, true>(p, s);
+        case 0: return launch_step_dense<Q, 0, false>(p, s);
+        case 1: return launch_step_tasks<Q, 0, false>(p, s);
+        case 2: return launch_step_dense<Q, 0, true>(p, s);
+        case 3: return launch_step_tasks<Q, 0, true>(p, s);
+        case 4: return launch_step_dense<Q, 1, false>(p, s);
+        case 5: return launch_step_tasks<Q, 1, false>(p, s);
+        case 6: return launch_step_dense<Q, 1, true>(p, s);
+        default: return launch_step_tasks<Q, 1, true>(p, s);
     }
 }
 
@@ -483,45 +602,46 @@ __global__ void build_mask_kernel(const uint8_t* __restrict__ sb, int has_x_ghos
 
 // Classifies every interior mask word and precomputes the neighbourhood words of the special ones.
 // One warp per interior (row, word).  A word is special if any of the 27 mask words around it has a
-// solid bit or it holds a reflection target.  fill == 0: count special words into *counter.
-// fill == 1: give each a slot (order is irrelevant), write special[word] = slot and the 32
-// neighbourhood words (bit 27 = reflection target) at cellinfo[slot*32 ..].
+// solid bit or it holds a reflection target; it is dead if every one of its interior cells is solid.
+// cls is laid out [x][word][y] (y fastest, pitch cls_pitch) so that the classes of consecutive rows of
+// one z-word are adjacent bytes; cellinfo is indexed like the populations (one word per padded cell,
+// only the cells of special words are ever written or read; bit 27 = reflection target).
 __global__ void build_cellinfo_kernel(const uint32_t* __restrict__ solid, const uint32_t* __restrict__ tmask,
-                                      int* __restrict__ special, uint32_t* __restrict__ cellinfo, unsigned* counter,
-                                      Geom g, int fill)
+                                      uint8_t* __restrict__ cls, int cls_pitch, uint32_t* __restrict__ cellinfo,
+                                      uint32_t* __restrict__ special_list, unsigned* counter, Geom g)
 {
     const int wlo = PAD_Z / 32, wcount = (g.nz + 31) / 32;            // words that hold interior cells
     const long long nwarps = (long long)g.nx * g.ny * wcount;
     const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned lane = threadIdx.x & 31u;
     if (wid >= nwarps) return;
-    const int w = wlo + (int)(wid % wcount);
+    const int wi = (int)(wid % wcount), w = wlo + wi;
     const long long r = wid / wcount;
     const int y = (int)(r % g.ny), x = (int)(r / g.ny);
     const long long row = (long long)(x + 1) * g.yp + (y + 1);
     const long long widx = row * g.wz + w;
-    uint32_t near = 0, nb = 0;
+    uint32_t near = 0, nb = 0, own = 0;
     if (solid) {
         // lanes 0..26 each look at one of the 27 surrounding words
         if (lane < 27) {
             const int dx = (int)lane / 9 - 1, dy = ((int)lane / 3) % 3 - 1, dw = (int)lane % 3 - 1;
             near = solid[(row + (long long)dx * g.yp + dy) * g.wz + w + dw];
         }
+        own = __shfl_sync(FULL, near, 13);
         near = __any_sync(FULL, near != 0u);
         if (near) nb = neighbour_bits(solid, row, g.yp, g.wz, w, lane);
     }
     const uint32_t tw = tmask ? tmask[widx] : 0u;
-    if (!near && !tw) return;
-    nb |= ((tw >> lane) & 1u) << 27;
-    if (!fill) {
-        if (lane == 0) atomicAdd(counter, 1u);
-        return;
+    const int cells = min(32, g.nz - wi * 32);
+    const uint32_t live_lanes = cells == 32 ? 0xffffffffu : ((1u << cells) - 1u);
+    unsigned c = CLS_ORDINARY;
+    if ((own & live_lanes) == live_lanes) c = CLS_DEAD;
+    else if (near || tw) {
+        c = CLS_SPECIAL;
+        cellinfo[widx * 32 + lane] = nb | (((tw >> lane) & 1u) << 27);
+        if (lane == 0) special_list[atomicAdd(counter, 1u)] = (uint32_t)widx;
     }
-    unsigned slot = 0;
-    if (lane == 0) slot = atomicAdd(counter, 1u);
-    slot = __shfl_sync(FULL, slot, 0);
-    if (lane == 0) special[widx] = (int)slot;
-    cellinfo[(long long)slot * 32 + lane] = nb;
+    if (lane == 0) cls[((long long)x * wcount + wi) * cls_pitch + y] = (uint8_t)c;
 }
 
 __global__ void mask_to_bytes_kernel(const uint32_t* __restrict__ mask, uint8_t* __restrict__ sb, Geom g)
@@ -674,12 +794,12 @@ cudaError_t launch_build_mask(const uint8_t* solid_bytes, int has_x_ghost, uint3
     return cudaGetLastError();
 }
 
-cudaError_t launch_build_cellinfo(const uint32_t* solid, const uint32_t* tmask, int* special, uint32_t* cellinfo,
-                                  unsigned* counter, const Geom& g, int fill, cudaStream_t stream)
+cudaError_t launch_build_cellinfo(const uint32_t* solid, const uint32_t* tmask, uint8_t* cls, int cls_pitch,
+                                  uint32_t* cellinfo, uint32_t* special_list, unsigned* counter, const Geom& g, cudaStream_t stream)
 {
     const long long nwarps = (long long)g.nx * g.ny * ((g.nz + 31) / 32);
     const long long threads = nwarps * 32;
-    build_cellinfo_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(solid, tmask, special, cellinfo, counter, g, fill);
+    build_cellinfo_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(solid, tmask, cls, cls_pitch, cellinfo, special_list, counter, g);
     return cudaGetLastError();
 }
 

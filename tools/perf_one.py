@@ -1,0 +1,13 @@
+"""run one probe config by name: python tools/perf_one.py <name> [size] [steps]"""
+import os, sys
+sys.argv = [sys.argv[0], sys.argv[2] if len(sys.argv) > 2 else "512", sys.argv[3] if len(sys.argv) > 3 else "3", "none"] + sys.argv[1:2]
+exec(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "perf_probe.py")).read())
+name = sys.argv[4]
+if name == "dense":
+    run("dense fast", 19, lb.EQ_FP32, (Z, Z, Z), BB, False, False)
+elif name == "tasks_plain":
+    run("tasks, source only", 19, lb.EQ_FP32, (Z, Z, Z), BB, False, True)
+elif name == "tasks_obst":
+    run("tasks, obstacle", 19, lb.EQ_FP32, (Z, Z, Z), BB, True, False)
+elif name == "headline":
+    run("headline", 19, lb.EQ_FP32, (Z, W, W), BB, True, True)

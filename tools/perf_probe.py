@@ -48,6 +48,11 @@ if which in ("all", "fast"):
     run("q19 fp32 fast (no geometry, zero-inflow)", 19, lb.EQ_FP32, (Z, Z, Z), BB, False, False)
 if which in ("all", "headline"):
     run("q19 fp32 general obstacle+walls+source", 19, lb.EQ_FP32, (Z, W, W), BB, True, True)
+if which in ("parts",):
+    run("q19 general, source only (all ordinary)", 19, lb.EQ_FP32, (Z, Z, Z), BB, False, True)
+    run("q19 general, walls y/z only", 19, lb.EQ_FP32, (Z, W, W), BB, False, False)
+    run("q19 general, walls y only", 19, lb.EQ_FP32, (Z, W, Z), BB, False, False)
+    run("q19 general, obstacle only", 19, lb.EQ_FP32, (Z, Z, Z), BB, True, False)
 if which in ("all",):
     run("q19 fp32 periodic xyz (3 ghost fills)", 19, lb.EQ_FP32, (P, P, P), BB, False, False)
     run("q27 fp32 fast", 27, lb.EQ_FP32, (Z, Z, Z), BB, False, False)
