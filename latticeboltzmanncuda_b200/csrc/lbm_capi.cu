@@ -134,7 +134,7 @@ int rebuild_special(lbm_handle h)
     const Geom& g = h->g;
     const int wcount = (g.nz + 31) / 32;
     if (!h->cls) {
-        h->cls_pitch = ((g.ny + 3) / 4) * 4;
+        h->cls_pitch = ((g.ny + 15) / 16) * 16;
         h->cls_bytes = (size_t)g.nx * wcount * h->cls_pitch;
         CK(cudaMalloc(&h->cls, h->cls_bytes));
         pin_classes_in_l2(h);
@@ -173,8 +173,6 @@ int rebuild_mask(lbm_handle h, const uint8_t* dev_bytes, int has_x_ghost)
     return rebuild_special(h);
 }
 
-bool has_wall(const lbm_config& c) { return c.bc[0] == LBM_BC_WALL || c.bc[1] == LBM_BC_WALL || c.bc[2] == LBM_BC_WALL; }
-
 void fill_params(lbm_handle h, StepParams& p, unsigned phases, int x0, int x1)
 {
     std::memset(&p, 0, sizeof p);
@@ -204,18 +202,19 @@ void fill_params(lbm_handle h, StepParams& p, unsigned phases, int x0, int x1)
     p.force_mode = h->cfg.force_mode;
     p.src_on = h->src_on;
     for (int a = 0; a < 3; ++a) { p.src_lo[a] = h->src_lo[a]; p.src_hi[a] = h->src_hi[a]; p.bc[a] = h->cfg.bc[a]; }
-    std::memcpy(p.src_f, h->src_f, sizeof p.src_f);
-    std::memcpy(p.wall_u, h->cfg.wall_u, sizeof p.wall_u);
-    p.wall_moving = 0;
-    for (int i = 0; i < 6; ++i)
+    std::memcpy(p.wall_z, h->cfg.wall_u[4], sizeof p.wall_z);
+    p.wall_z_moving = 0;
+    for (int k = 4; k < 6; ++k)
         for (int a = 0; a < 3; ++a)
-            if (h->cfg.wall_u[i][a] != 0.0f) p.wall_moving = 1;
+            if (h->cfg.wall_u[k][a] != 0.0f) p.wall_z_moving = 1;
+    std::memcpy(p.src_f, h->src_f, sizeof p.src_f);
 }
 
-// is the cheap kernel (pull + collide on an all-fluid lattice) enough for these phases?
+// is the dense kernel (pull + collide on an all-fluid lattice) enough for these phases?
 bool fast_path_ok(lbm_handle h, unsigned phases)
 {
     if (!(phases & PH_STREAM) || !(phases & PH_COLLIDE)) return false;
+    if (h->cfg.bc[2] != LBM_BC_ZERO_INFLOW) return false;     // periodic / wall z edges are resolved by the general kernels
     if (h->any_solid) return false;
     if ((phases & PH_REFLECT) && h->nlinks) return false;
     if ((phases & PH_SOURCE) && h->src_on) return false;
@@ -246,13 +245,8 @@ void note_step_done(lbm_handle h, unsigned phases)
 
 int fill_ghosts(lbm_handle h, bool include_x)
 {
-    const int* bc = h->cfg.bc;
     int n = 0;
-    if (include_x && bc[0] == LBM_BC_PERIODIC) ++n;
-    if (bc[1] == LBM_BC_PERIODIC) ++n;
-    if (bc[2] == LBM_BC_PERIODIC) ++n;
-    if (!n) return LBM_OK;
-    CK(launch_fill_ghosts(h->buf[h->cur], h->g, h->cfg.q, bc, include_x, h->stream));
+    CK(launch_fill_ghosts(h->buf[h->cur], h->g, h->cfg.q, h->cfg.bc, h->cfg.wall_u, include_x, h->stream, &n));
     h->launches += n;
     return LBM_OK;
 }
@@ -345,8 +339,7 @@ LBM_API int lbm_create(const lbm_config* cfg, lbm_handle* out)
     CKB(cudaMalloc(&h->diag, 4 * sizeof(double)));
 #undef CKB
     {
-        // wall ghosts are solid bits even without geometry; the task list exists in every case
-        int rc = has_wall(h->cfg) ? rebuild_mask(h, nullptr, 0) : rebuild_special(h);
+        int rc = rebuild_special(h);      // the word classes exist even without geometry
         if (rc) return bail(rc);
     }
     cudaError_t e = cudaStreamSynchronize(h->stream);

@@ -4,8 +4,9 @@
 //   * one ghost layer on every side (xp = nx+2, yp = ny+2); ghost cells implement the
 //     domain-edge rule, so the hot kernel has no bounds tests: zero-inflow ghosts hold 0
 //     (the reference's rule, simulation/source/SimCalcFuncs.cu:37-40,87-94), periodic
-//     ghosts are refreshed from the opposite face, wall ghosts are solid bits, halo ghosts
-//     come from the neighbouring slab;
+//     ghosts are refreshed from the opposite face, wall ghosts are refreshed with the bounced-back
+//     populations of the cells that pull from them, halo ghosts come from the neighbouring slab
+//     (x and y faces; the z edge is resolved by address selection when the populations are pulled);
 //   * the first interior z sits at PAD_Z = 32 floats, so every interior row starts on a
 //     128-byte line and a warp's 32 lanes map to exactly one solid-mask word;
 //   * zp is a multiple of 32, so every row, plane and population starts 128-byte aligned.
@@ -86,8 +87,8 @@ struct StepParams {
     int   src_lo[3], src_hi[3];
     float src_f[27];
     int   bc[3];
-    int   wall_moving;        // any wall_u component non-zero
-    float wall_u[6][3];
+    float wall_z[2][3];       // velocity of the z walls (x and y walls are ghost fills)
+    int   wall_z_moving;
 };
 
 struct LaunchCfg {
@@ -100,7 +101,8 @@ struct LaunchCfg {
 // launches (all asynchronous on `stream`)
 cudaError_t launch_step(const LaunchCfg& cfg, const StepParams& p, cudaStream_t stream);
 
-cudaError_t launch_fill_ghosts(float* f, const Geom& g, int q, const int bc[3], bool include_x, cudaStream_t stream);
+cudaError_t launch_fill_ghosts(float* f, const Geom& g, int q, const int bc[3], const float wall_u[6][3], bool include_x,
+                               cudaStream_t stream, int* launches);
 
 // AoS (144-byte LatticePoint records, host order) <-> padded SoA; x range [x0, x0+nxc)
 cudaError_t launch_unpack_aos(const void* aos, float* f, uint8_t* solid_bytes, const Geom& g, int q, int x0, int nxc, cudaStream_t stream);

@@ -119,24 +119,6 @@ __device__ __forceinline__ uint32_t neighbour_bits(const uint32_t* __restrict__ 
     return nb;
 }
 
-// moving-wall term of half-way bounce-back, 6 w_i (c_i . u_wall) with rho_wall = 1; the wall
-// is the first axis (x, y, z order) along which the pulled-from cell leaves the box
-template <int Q>
-__device__ __forceinline__ float wall_term(const StepParams& p, int i, int x, int y, int z)
-{
-    const int s[3] = {x - dir_c(i, 0), y - dir_c(i, 1), z - dir_c(i, 2)};
-    const int n[3] = {p.g.nx, p.g.ny, p.g.nz};
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        if ((s[a] < 0 || s[a] >= n[a]) && p.bc[a] == 2) {
-            const float* u = p.wall_u[a * 2 + (s[a] < 0 ? 0 : 1)];
-            const float cu = (float)dir_c(i, 0) * u[0] + (float)dir_c(i, 1) * u[1] + (float)dir_c(i, 2) * u[2];
-            return 6.0f * (float)dir_weight<Q>(i) * cu;
-        }
-    }
-    return 0.0f;
-}
-
 // Boundary work of one warp that touches a solid cell, a wall ghost or a reflection target.
 // nb is the cell's precomputed neighbourhood word (see build_cellinfo_kernel): bit nb_bit(dx,dy,dz)
 // = solid flag of the neighbour at (dx,dy,dz), bit 13 = the cell itself.
@@ -157,19 +139,13 @@ __device__ __forceinline__ bool boundary_path(const StepParams& p, float (&f)[Q]
             for (int i = 1; i < Q; ++i) {
                 if ((nb >> nb_bit(-dir_c(i, 0), -dir_c(i, 1), -dir_c(i, 2))) & 1u) {
                     const float back = fin[(long long)dir_inv(i) * g.np];
-                    float v = back;
-                    if (p.wall_moving) v += wall_term<Q>(p, i, x, y, z);
-                    f[i] = v;
-                    // momentum exchange with an obstacle cell (not a domain wall; periodic or halo
-                    // images of obstacle cells count): population inv(i) goes in with -c_i and comes
-                    // back as i with +c_i
+                    f[i] = back;
+                    // momentum exchange with an obstacle cell (domain walls are ghost fills and never get
+                    // here; periodic or halo images of obstacle cells count): population inv(i) goes in
+                    // with -c_i and comes back as i with +c_i
                     if (p.force) {
-                        const int sx = x - dir_c(i, 0), sy = y - dir_c(i, 1), sz = z - dir_c(i, 2);
-                        const bool off_wall = (p.bc[0] == 2 && (sx < 0 || sx >= g.nx)) ||
-                                              (p.bc[1] == 2 && (sy < 0 || sy >= g.ny)) ||
-                                              (p.bc[2] == 2 && (sz < 0 || sz >= g.nz));
-                        if (active && !solid_here && !off_wall) {
-                            const float m = back + v;
+                        if (active && !solid_here) {
+                            const float m = back + back;
                             fx -= (float)dir_c(i, 0) * m;
                             fy -= (float)dir_c(i, 1) * m;
                             fz -= (float)dir_c(i, 2) * m;
@@ -200,7 +176,13 @@ __device__ __forceinline__ bool boundary_path(const StepParams& p, float (&f)[Q]
                     while (e < e1 && p.links[e].d == i) {
                         const Link L = p.links[e];
                         long long src = (long long)L.j * g.np + (long long)L.src_cell;
-                        if (do_stream) src -= pull_offset_dyn(g, L.j);
+                        if (do_stream) {
+                            src -= pull_offset_dyn(g, L.j);
+                            if (p.bc[2] == 1 && c_dir[L.j][2] != 0) {       // periodic z: wrap a source beyond the edge
+                                const int sz = (int)(L.src_cell % (uint32_t)g.zp) - PAD_Z - c_dir[L.j][2];
+                                if (sz < 0) src += g.nz; else if (sz >= g.nz) src -= g.nz;
+                            }
+                        }
                         const float moved = p.fin[src] * L.w;
                         f[i] += moved;
                         if (p.force) {
@@ -244,9 +226,47 @@ __device__ __forceinline__ bool boundary_path(const StepParams& p, float (&f)[Q]
     return dead;
 }
 
+// Pull f_i(x) <- f_i(x - c_i)  (SimCalcFuncs.cu:83-94, j = INVERSE[i] relabelled).
+// x and y edges are ghost planes / rows (filled by launch_fill_ghosts or left at zero); the z edge is
+// resolved here, by choosing the address the edge lane reads from, because a z ghost shares its row with
+// the interior and any separate pass over it would move one 32-byte sector per 4-byte value:
+//   zero inflow: the ghost column holds 0 (the reference's rule);
+//   periodic   : the lane reads the cell on the far side of the row (+/- nz);
+//   wall       : half-way bounce-back, the lane reads its own cell's opposite population and adds
+//                6 w_i (c_i . u_wall) for a moving wall (rho_wall = 1).
+// edge_word is warp-uniform: only the first and last word of a row take the second branch.
+template <int Q>
+__device__ __forceinline__ void pull_populations(const StepParams& p, const float* __restrict__ fin, int z, bool edge_word,
+                                                 float (&f)[Q])
+{
+    const Geom& g = p.g;
+    if (!edge_word || p.bc[2] == 0) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i)
+            f[i] = fin[(long long)i * g.np - ((long long)dir_c(i, 0) * g.plane + (long long)(dir_c(i, 1) * g.zp + dir_c(i, 2)))];
+        return;
+    }
+    const bool lo = (z == 0), hi = (z == g.nz - 1);
+    const bool wall = p.bc[2] == 2;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        const long long off = (long long)i * g.np - ((long long)dir_c(i, 0) * g.plane + (long long)(dir_c(i, 1) * g.zp + dir_c(i, 2)));
+        if (dir_c(i, 2) == 0) { f[i] = fin[off]; continue; }
+        const bool outside = dir_c(i, 2) > 0 ? lo : hi;          // the cell this population comes from is beyond the z edge
+        long long a = off;
+        if (outside) a = wall ? (long long)dir_inv(i) * g.np : off + (dir_c(i, 2) > 0 ? g.nz : -g.nz);
+        float v = fin[a];
+        if (outside && wall && p.wall_z_moving) {
+            const float* u = p.wall_z[dir_c(i, 2) > 0 ? 0 : 1];
+            v += 6.0f * (float)dir_weight<Q>(i) * ((float)dir_c(i, 0) * u[0] + (float)dir_c(i, 1) * u[1] + (float)dir_c(i, 2) * u[2]);
+        }
+        f[i] = v;
+    }
+}
+
 // Dense kernel for an all-fluid lattice: one warp per 32 consecutive z of an (x, y) row, pull +
-// collide, nothing else.  Used when there is no geometry, no wall, no source and the phases are
-// stream + collide.
+// collide, nothing else.  Used when there is no geometry, no source, the phases are stream + collide and
+// the z edge is open (zero inflow), so that no z ghost values have to be produced.
 template <int Q, int MOMENT, bool EQ64>
 __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepParams p)
 {
@@ -259,10 +279,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
     const long long idx = ((long long)(x + 1) * g.yp + (y + 1)) * g.zp + (z + PAD_Z);
     const float* __restrict__ fin = p.fin + idx;
     float f[Q];
-    // ---- pull: f_i(x) <- f_i(x - c_i)   (SimCalcFuncs.cu:83-94, j = INVERSE[i] relabelled)
-#pragma unroll
-    for (int i = 0; i < Q; ++i)
-        f[i] = fin[(long long)i * g.np - ((long long)dir_c(i, 0) * g.plane + (long long)(dir_c(i, 1) * g.zp + dir_c(i, 2)))];
+    pull_populations<Q>(p, fin, z, false, f);      // open z edge: the ghost columns hold zeros
     // ---- BGK relaxation (SimCalcFuncs.cu:98-156)
     if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
     else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
@@ -281,10 +298,9 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
 //   dead      nothing to read; zeros are written while the buffers may still hold stale values there
 //             (dead_mode 1) and nothing at all afterwards (dead_mode 2);
 //   special   skipped here: step_special_kernel walks the compact list of special words.
-constexpr int ROWS_PER_WARP = 4;
 enum : unsigned { CLS_ORDINARY = 0, CLS_DEAD = 1, CLS_SPECIAL = 2 };
 
-template <int Q, int MOMENT, bool EQ64, int MINB>
+template <int Q, int MOMENT, bool EQ64, int MINB, int ROWS_PER_WARP>
 __global__ void __launch_bounds__(128, MINB) step_general_kernel(const __grid_constant__ StepParams p)
 {
     const Geom& g = p.g;
@@ -297,13 +313,23 @@ __global__ void __launch_bounds__(128, MINB) step_general_kernel(const __grid_co
     const int z = wi * 32 + (int)lane;
     const bool active = z < g.nz;
     const bool do_stream = p.phases & PH_STREAM;
-    const uint32_t cls4 = __ldg(reinterpret_cast<const uint32_t*>(p.cls + ((long long)x * wcount + wi) * p.cls_pitch + y0));
+    const uint8_t* cp = p.cls + ((long long)x * wcount + wi) * p.cls_pitch + y0;
+    uint32_t clsw[ROWS_PER_WARP / 4];
+    if (ROWS_PER_WARP == 4) {
+        clsw[0] = __ldg(reinterpret_cast<const uint32_t*>(cp));
+    } else if (ROWS_PER_WARP == 8) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(cp));
+        clsw[0] = v.x; clsw[1 % (ROWS_PER_WARP / 4)] = v.y;
+    } else {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(cp));
+        clsw[0] = v.x; clsw[1 % (ROWS_PER_WARP / 4)] = v.y; clsw[2 % (ROWS_PER_WARP / 4)] = v.z; clsw[3 % (ROWS_PER_WARP / 4)] = v.w;
+    }
 
 #pragma unroll 1
     for (int r = 0; r < ROWS_PER_WARP; ++r) {
         const int y = y0 + r;
         if (y >= g.ny) break;
-        const unsigned cls = (cls4 >> (8 * r)) & 0xffu;
+        const unsigned cls = (clsw[r >> 2] >> (8 * (r & 3))) & 0xffu;
         if (cls == CLS_SPECIAL) continue;              // step_special_kernel owns these words
         const long long idx = ((long long)(x + 1) * g.yp + (y + 1)) * g.zp + (z + PAD_Z);
         float f[Q];
@@ -316,9 +342,7 @@ __global__ void __launch_bounds__(128, MINB) step_general_kernel(const __grid_co
         } else {
             const float* __restrict__ fin = p.fin + idx;
             if (do_stream) {
-#pragma unroll
-                for (int i = 0; i < Q; ++i)
-                    f[i] = fin[(long long)i * g.np - ((long long)dir_c(i, 0) * g.plane + (long long)(dir_c(i, 1) * g.zp + dir_c(i, 2)))];
+                pull_populations<Q>(p, fin, z, wi == 0 || wi == wcount - 1, f);
             } else {
 #pragma unroll
                 for (int i = 0; i < Q; ++i) f[i] = fin[(long long)i * g.np];
@@ -366,9 +390,7 @@ __global__ void __launch_bounds__(128) step_special_kernel(const __grid_constant
     const float* __restrict__ fin = p.fin + idx;
     float f[Q];
     if (do_stream) {
-#pragma unroll
-        for (int i = 0; i < Q; ++i)
-            f[i] = fin[(long long)i * g.np - ((long long)dir_c(i, 0) * g.plane + (long long)(dir_c(i, 1) * g.zp + dir_c(i, 2)))];
+        pull_populations<Q>(p, fin, z, w == PAD_Z / 32 || w == PAD_Z / 32 + ((g.nz + 31) >> 5) - 1, f);
     } else {
 #pragma unroll
         for (int i = 0; i < Q; ++i) f[i] = fin[(long long)i * g.np];
@@ -423,18 +445,28 @@ cudaError_t launch_step_dense(const StepParams& p, cudaStream_t stream)
     return cudaGetLastError();
 }
 
-template <int Q, int MOMENT, bool EQ64>
-cudaError_t launch_step_tasks(const StepParams& p, cudaStream_t stream)
+template <int Q, int MOMENT, bool EQ64, int ROWS>
+cudaError_t launch_step_general_r(const StepParams& p, cudaStream_t stream)
 {
-    if (p.x1 <= p.x0) return cudaSuccess;
     const Geom& g = p.g;
     const int wcount = (g.nz + 31) / 32;
     const int warps = wcount < 4 ? wcount : 4;
     dim3 block(32 * warps, 1, 1);
-    dim3 grid((wcount + warps - 1) / warps, (g.ny + ROWS_PER_WARP - 1) / ROWS_PER_WARP, p.x1 - p.x0);
-    static int minb = [] { const char* e = getenv("LBM_GENERAL_MINB"); return e ? atoi(e) : 10; }();   // tuning knob
-    if (minb >= 12) step_general_kernel<Q, MOMENT, EQ64, 12><<<grid, block, 0, stream>>>(p);
-    else            step_general_kernel<Q, MOMENT, EQ64, 10><<<grid, block, 0, stream>>>(p);
+    dim3 grid((wcount + warps - 1) / warps, (g.ny + ROWS - 1) / ROWS, p.x1 - p.x0);
+    step_general_kernel<Q, MOMENT, EQ64, 10, ROWS><<<grid, block, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int Q, int MOMENT, bool EQ64>
+cudaError_t launch_step_tasks(const StepParams& p, cudaStream_t stream)
+{
+    if (p.x1 <= p.x0) return cudaSuccess;
+    static int rows = [] { const char* e = getenv("LBM_GENERAL_ROWS"); return e ? atoi(e) : 8; }();   // tuning knob
+    cudaError_t e;
+    if (rows >= 16 && p.cls_pitch % 16 == 0) e = launch_step_general_r<Q, MOMENT, EQ64, 16>(p, stream);
+    else if (rows >= 8 && p.cls_pitch % 8 == 0) e = launch_step_general_r<Q, MOMENT, EQ64, 8>(p, stream);
+    else e = launch_step_general_r<Q, MOMENT, EQ64, 4>(p, stream);
+    if (e != cudaSuccess) return e;
     if (p.n_special > 0) {
         const long long blocks = (p.n_special + 3) / 4;
         step_special_kernel<Q, MOMENT, EQ64><<<(unsigned)blocks, 128, 0, stream>>>(p);
@@ -460,37 +492,61 @@ cudaError_t launch_step_q(const LaunchCfg& c, const StepParams& p, cudaStream_t 
 
 // ---- ghost layers -----------------------------------------------------------------------
 
-// periodic x: plane 0 <- plane nx, plane nx+1 <- plane 1 (whole padded planes)
-__global__ void fill_x_kernel(float* f, Geom g, int q)
-{
-    const long long n = g.plane;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float* fq = f + (long long)blockIdx.y * g.np;
-    fq[i] = fq[(long long)g.nx * g.plane + i];
-    fq[(long long)(g.nx + 1) * g.plane + i] = fq[g.plane + i];
-}
+// One launch per axis fills both ghost faces of that axis for the populations that enter through them
+// (c_i[axis] = +1 through the low face, -1 through the high face).
+//   periodic: G_i(g) = F_i(g shifted by n along the axis)
+//   wall    : half-way bounce-back written into the ghost cell, G_i(g) = F_inv(i)(g + c_i) + 6 w_i (c_i.u_wall)
+//             with rho_wall = 1, only where g + c_i is an interior cell (the only cell that pulls G_i(g)).
+// Faces span the full padded range of the other two axes, so running the axes in order fills edges and
+// corners; walls are filled after all periodic axes and in z, y, x order so that the wall named first
+// in x, y, z order wins where two walls meet.
+struct FillParams {
+    float* f;
+    Geom g;
+    int axis, mode;          // mode 1 periodic, 2 wall
+    int bc[3];
+    float wall_u[2][3];      // low / high face velocity of this axis
+};
 
-// y rows: mode 1 periodic (row 0 <- row ny, row ny+1 <- row 1)
-__global__ void fill_y_kernel(float* f, Geom g, int q)
+template <int Q>
+__global__ void fill_axis_kernel(const __grid_constant__ FillParams p)
 {
-    const int zc = blockIdx.x * blockDim.x + threadIdx.x;
-    const int xpl = blockIdx.y;
-    if (zc >= g.zp) return;
-    float* fq = f + (long long)blockIdx.z * g.np + (long long)xpl * g.plane;
-    fq[zc] = fq[(long long)g.ny * g.zp + zc];
-    fq[(long long)(g.ny + 1) * g.zp + zc] = fq[(long long)g.zp + zc];
-}
-
-// z columns: ghost at PAD_Z-1 <- PAD_Z+nz-1, ghost at PAD_Z+nz <- PAD_Z
-__global__ void fill_z_kernel(float* f, Geom g, int q)
-{
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // padded row index over xp*yp
-    const long long rows = (long long)g.xp * g.yp;
-    if (r >= rows) return;
-    float* fq = f + (long long)blockIdx.y * g.np + r * g.zp;
-    fq[PAD_Z - 1] = fq[PAD_Z + g.nz - 1];
-    fq[PAD_Z + g.nz] = fq[PAD_Z];
+    const Geom& g = p.g;
+    const int n[3] = {g.nx, g.ny, g.nz};
+    // face coordinates (a, b): the two axes other than p.axis, b is the faster one in memory
+    const int ax = p.axis;
+    const int a_ax = ax == 0 ? 1 : 0, b_ax = ax == 2 ? 1 : 2;
+    const int nb = n[b_ax] + 2, na = n[a_ax] + 2;
+    const long long cell_count = (long long)na * nb;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cell_count) return;
+    const int side = blockIdx.y;                     // 0 low face, 1 high face
+    int c[3];
+    c[a_ax] = (int)(k / nb) - 1;
+    c[b_ax] = (int)(k % nb) - 1;
+    c[ax] = side ? n[ax] : -1;
+    const int inward = side ? -1 : 1;
+    // ghost cells that also lie outside a wall axis belong to that wall (bounce-back wins over the wrap)
+    if (p.mode == 1 && ((p.bc[a_ax] == 2 && (c[a_ax] < 0 || c[a_ax] >= n[a_ax])) ||
+                        (p.bc[b_ax] == 2 && (c[b_ax] < 0 || c[b_ax] >= n[b_ax])))) return;
+    const long long gidx = g.cell(c[0], c[1], c[2]);
+#pragma unroll
+    for (int i = 1; i < Q; ++i) {
+        if (dir_c(i, ax) != inward) continue;
+        if (p.mode == 1) {
+            int s[3] = {c[0], c[1], c[2]};
+            s[ax] += side ? -n[ax] : n[ax];
+            p.f[(long long)i * g.np + gidx] = p.f[(long long)i * g.np + g.cell(s[0], s[1], s[2])];
+        } else {
+            int t[3] = {c[0] + dir_c(i, 0), c[1] + dir_c(i, 1), c[2] + dir_c(i, 2)};
+            if (p.bc[2] == 1 && ax != 2) t[2] = (t[2] + n[2]) % n[2];
+            if (t[0] < 0 || t[0] >= n[0] || t[1] < 0 || t[1] >= n[1] || t[2] < 0 || t[2] >= n[2]) continue;
+            const float* u = p.wall_u[side];
+            const float cu = (float)dir_c(i, 0) * u[0] + (float)dir_c(i, 1) * u[1] + (float)dir_c(i, 2) * u[2];
+            p.f[(long long)i * g.np + gidx] =
+                p.f[(long long)dir_inv(i) * g.np + g.cell(t[0], t[1], t[2])] + 6.0f * (float)dir_weight<Q>(i) * cu;
+        }
+    }
 }
 
 // ---- AoS <-> SoA (Lattice::load_data / retrieve_data, Lattice.cpp:73-113) ------------------
@@ -562,8 +618,8 @@ __global__ void gather_dense_kernel(float* __restrict__ dense, const float* __re
 // ---- solid mask ---------------------------------------------------------------------------
 
 // One warp builds one mask word.  Ghost cells follow the domain-edge rule of each axis they
-// lie outside of: wall -> solid; zero-inflow -> fluid (holding 0); periodic -> the wrapped
-// interior cell; halo (x only) -> the plane handed in by the caller.
+// lie outside of: wall and zero-inflow -> fluid (their populations are ghost values); periodic ->
+// the wrapped interior cell; halo (x only) -> the plane handed in by the caller.
 __global__ void build_mask_kernel(const uint8_t* __restrict__ sb, int has_x_ghost, uint32_t* __restrict__ mask, Geom g,
                                   int bcx, int bcy, int bcz)
 {
@@ -583,15 +639,12 @@ __global__ void build_mask_kernel(const uint8_t* __restrict__ sb, int has_x_ghos
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         if (c[a] >= 0 && c[a] < n[a]) continue;
-        if (bc[a] == 2) wall = true;
-        else if (bc[a] == 0) empty = true;
+        if (bc[a] == 2 || bc[a] == 0) empty = true;     // wall and zero-inflow ghosts carry values, not solid bits
         else if (bc[a] == 1) c[a] = (c[a] + n[a]) % n[a];
         else if (!(a == 0 && has_x_ghost)) empty = true;   // halo: keep x = -1 / nx, read the caller's plane
     }
     bool bit = false;
-    if (padding) bit = false;
-    else if (wall) bit = true;
-    else if (!empty && sb) {
+    if (!padding && !wall && !empty && sb) {
         const long long per = (long long)g.ny * g.nz;
         const long long xi = has_x_ghost ? (long long)c[0] + 1 : (long long)c[0];
         bit = sb[xi * per + (long long)c[1] * g.nz + c[2]] != 0;
@@ -735,23 +788,36 @@ cudaError_t launch_step(const LaunchCfg& cfg, const StepParams& p, cudaStream_t 
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_fill_ghosts(float* f, const Geom& g, int q, const int bc[3], bool include_x, cudaStream_t stream)
+static cudaError_t launch_fill_axis(float* f, const Geom& g, int q, int axis, int mode, const int bc[3], const float wall_u[6][3], cudaStream_t stream)
 {
-    // order x, y, z: later axes copy the ghost layers of earlier ones, which fills edges and corners
-    if (include_x && bc[0] == 1) {
-        dim3 grid((unsigned)((g.plane + 255) / 256), q);
-        fill_x_kernel<<<grid, 256, 0, stream>>>(f, g, q);
-    }
-    if (bc[1] == 1) {
-        dim3 grid((g.zp + 127) / 128, g.xp, q);
-        fill_y_kernel<<<grid, 128, 0, stream>>>(f, g, q);
-    }
-    if (bc[2] == 1) {
-        const long long rows = (long long)g.xp * g.yp;
-        dim3 grid((unsigned)((rows + 127) / 128), q);
-        fill_z_kernel<<<grid, 128, 0, stream>>>(f, g, q);
-    }
+    FillParams fp;
+    fp.f = f; fp.g = g; fp.axis = axis; fp.mode = mode;
+    for (int a = 0; a < 3; ++a) fp.bc[a] = bc[a];
+    for (int s = 0; s < 2; ++s)
+        for (int a = 0; a < 3; ++a) fp.wall_u[s][a] = wall_u ? wall_u[axis * 2 + s][a] : 0.0f;
+    const int n[3] = {g.nx, g.ny, g.nz};
+    const int a_ax = axis == 0 ? 1 : 0, b_ax = axis == 2 ? 1 : 2;
+    const long long cells = (long long)(n[a_ax] + 2) * (n[b_ax] + 2);
+    dim3 grid((unsigned)((cells + 127) / 128), 2);
+    if (q == 27) fill_axis_kernel<27><<<grid, 128, 0, stream>>>(fp);
+    else         fill_axis_kernel<19><<<grid, 128, 0, stream>>>(fp);
     return cudaGetLastError();
+}
+
+// x and y faces only: the z edge is resolved by the step kernels at pull time (pull_populations)
+cudaError_t launch_fill_ghosts(float* f, const Geom& g, int q, const int bc[3], const float wall_u[6][3], bool include_x,
+                               cudaStream_t stream, int* launches)
+{
+    int n = 0;
+    cudaError_t e = cudaSuccess;
+    const int first = include_x ? 0 : 1;
+    // periodic axes first, walls afterwards in y, x order so that the wall named first wins where two meet
+    for (int axis = first; axis <= 1 && e == cudaSuccess; ++axis)
+        if (bc[axis] == 1) { e = launch_fill_axis(f, g, q, axis, 1, bc, wall_u, stream); ++n; }
+    for (int axis = 1; axis >= first && e == cudaSuccess; --axis)
+        if (bc[axis] == 2) { e = launch_fill_axis(f, g, q, axis, 2, bc, wall_u, stream); ++n; }
+    if (launches) *launches = n;
+    return e;
 }
 
 cudaError_t launch_unpack_aos(const void* aos, float* f, uint8_t* solid_bytes, const Geom& g, int q, int x0, int nxc, cudaStream_t stream)
