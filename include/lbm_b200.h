@@ -206,6 +206,16 @@ typedef struct lbm_layout {
 } lbm_layout;
 LBM_API int lbm_get_layout(lbm_handle h, lbm_layout *out);
 
+/* classification of the 32-cell words of the lattice (set when the geometry is set): ordinary fluid words,
+ * dead words (every cell solid, never touched by a step) and special words (next to a solid cell or
+ * holding a reflection target) */
+typedef struct lbm_stats {
+    int64_t words_total, words_dead, words_special;
+    int64_t links;            /* reflection links (table mode) */
+    int64_t kernel_launches;  /* launches issued by this handle so far */
+} lbm_stats;
+LBM_API int lbm_get_stats(lbm_handle h, lbm_stats *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,11 @@ class Layout(C.Structure):
     ]
 
 
+class Stats(C.Structure):
+    _fields_ = [("words_total", C.c_int64), ("words_dead", C.c_int64), ("words_special", C.c_int64),
+                ("links", C.c_int64), ("kernel_launches", C.c_int64)]
+
+
 class LbmError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("lbm_b200 error %d: %s" % (code, msg))
@@ -100,6 +105,7 @@ SYMBOLS = [
     ("lbm_step_commit", _i, [_vp]),
     ("lbm_fill_ghosts", _i, [_vp]),
     ("lbm_get_layout", _i, [_vp, C.POINTER(Layout)]),
+    ("lbm_get_stats", _i, [_vp, C.POINTER(Stats)]),
 ]
 
 _lib = None

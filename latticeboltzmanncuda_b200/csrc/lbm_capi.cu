@@ -377,6 +377,30 @@ LBM_API int lbm_sync(lbm_handle h)
     return LBM_OK;
 }
 
+LBM_API int lbm_get_stats(lbm_handle h, lbm_stats* o)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    if (!o) return fail(LBM_ERR_INVALID, "null argument");
+    const Geom& g = h->g;
+    const int wcount = (g.nz + 31) / 32;
+    std::vector<uint8_t> cls(h->cls_bytes);
+    CK(cudaMemcpy(cls.data(), h->cls, h->cls_bytes, cudaMemcpyDeviceToHost));
+    int64_t dead = 0, special = 0;
+    for (long long r = 0; r < (long long)g.nx * wcount; ++r)
+        for (int y = 0; y < g.ny; ++y) {
+            const uint8_t c = cls[(size_t)r * h->cls_pitch + y];
+            dead += c == 1;
+            special += c == 2;
+        }
+    o->words_total = (int64_t)g.nx * g.ny * wcount;
+    o->words_dead = dead;
+    o->words_special = special;
+    o->links = (int64_t)h->nlinks;
+    o->kernel_launches = h->launches;
+    return LBM_OK;
+}
+
 LBM_API int lbm_get_layout(lbm_handle h, lbm_layout* o)
 {
     if (!h || !o) return fail(LBM_ERR_INVALID, "null argument");

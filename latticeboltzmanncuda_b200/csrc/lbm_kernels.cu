@@ -508,14 +508,14 @@ struct FillParams {
     float wall_u[2][3];      // low / high face velocity of this axis
 };
 
-template <int Q>
+template <int Q, int AX>
 __global__ void fill_axis_kernel(const __grid_constant__ FillParams p)
 {
     const Geom& g = p.g;
     const int n[3] = {g.nx, g.ny, g.nz};
-    // face coordinates (a, b): the two axes other than p.axis, b is the faster one in memory
-    const int ax = p.axis;
-    const int a_ax = ax == 0 ? 1 : 0, b_ax = ax == 2 ? 1 : 2;
+    // face coordinates (a, b): the two axes other than AX, b is the faster one in memory
+    constexpr int ax = AX;
+    constexpr int a_ax = ax == 0 ? 1 : 0, b_ax = ax == 2 ? 1 : 2;
     const int nb = n[b_ax] + 2, na = n[a_ax] + 2;
     const long long cell_count = (long long)na * nb;
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -688,8 +688,10 @@ __global__ void build_cellinfo_kernel(const uint32_t* __restrict__ solid, const 
     const int cells = min(32, g.nz - wi * 32);
     const uint32_t live_lanes = cells == 32 ? 0xffffffffu : ((1u << cells) - 1u);
     unsigned c = CLS_ORDINARY;
+    const bool lane_live = (live_lanes >> lane) & 1u;
+    const bool touches = __any_sync(FULL, lane_live && (nb & 0x7ffffffu) != 0u);   // exact: some cell sees a solid cell
     if ((own & live_lanes) == live_lanes) c = CLS_DEAD;
-    else if (near || tw) {
+    else if (touches || (tw & live_lanes)) {
         c = CLS_SPECIAL;
         cellinfo[widx * 32 + lane] = nb | (((tw >> lane) & 1u) << 27);
         if (lane == 0) special_list[atomicAdd(counter, 1u)] = (uint32_t)widx;
@@ -799,8 +801,13 @@ static cudaError_t launch_fill_axis(float* f, const Geom& g, int q, int axis, in
     const int a_ax = axis == 0 ? 1 : 0, b_ax = axis == 2 ? 1 : 2;
     const long long cells = (long long)(n[a_ax] + 2) * (n[b_ax] + 2);
     dim3 grid((unsigned)((cells + 127) / 128), 2);
-    if (q == 27) fill_axis_kernel<27><<<grid, 128, 0, stream>>>(fp);
-    else         fill_axis_kernel<19><<<grid, 128, 0, stream>>>(fp);
+    if (axis == 0) {
+        if (q == 27) fill_axis_kernel<27, 0><<<grid, 128, 0, stream>>>(fp);
+        else         fill_axis_kernel<19, 0><<<grid, 128, 0, stream>>>(fp);
+    } else {
+        if (q == 27) fill_axis_kernel<27, 1><<<grid, 128, 0, stream>>>(fp);
+        else         fill_axis_kernel<19, 1><<<grid, 128, 0, stream>>>(fp);
+    }
     return cudaGetLastError();
 }
 

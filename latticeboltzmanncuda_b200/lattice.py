@@ -249,6 +249,11 @@ class Lattice:
         capi.check(self._lib.lbm_momentum(self._h, capi.ptr(out)))
         return out
 
+    def stats(self):
+        st = capi.Stats()
+        capi.check(self._lib.lbm_get_stats(self._h, C.byref(st)))
+        return {k: int(getattr(st, k)) for k, _ in capi.Stats._fields_}
+
     def layout(self):
         lay = capi.Layout()
         capi.check(self._lib.lbm_get_layout(self._h, C.byref(lay)))

@@ -36,6 +36,8 @@ def run(name, q, eq, bc, boundary, obstacle, source, moment=lb.MOMENT_STANDARD, 
     ms, launches = lat.step_timed(K)
     mlups = S ** 3 * K / (ms * 1e-3) / 1e6
     gbs = mlups * 1e6 * 2 * q * 4 / 1e9
+    st = lat.stats()
+    name = "%s [dead %.0f%% special %.1f%%]" % (name, 100.0 * st["words_dead"] / st["words_total"], 100.0 * st["words_special"] / st["words_total"])
     print("%-44s %8.0f MLUPS %7.0f GB/s %5.1f%% of %.0f  (%.3f ms/step, %d launches)" %
           (name, mlups, gbs, 100 * gbs / PEAK, PEAK, ms / K, launches), flush=True)
     lat.close()
