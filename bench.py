@@ -161,6 +161,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     q, S = args.q, args.size
@@ -201,12 +202,6 @@ def run_ours(args):
     # synthetic inputs: obstacle mask + uniform initial state (host, pinned) + inflow plane source at global x == 0
     solid = tapered_hexahedron_mask(gx, gy, gz, (x_off - (1 if world > 1 else 0), x_off + nx + (1 if world > 1 else 0))) \
         if world > 1 else tapered_hexahedron_mask(gx, gy, gz)
-    if world > 1:
-        # planes outside the global domain carry no geometry
-        if rank == 0:
-            solid[0] = 0
-        if rank == world - 1:
-            solid[-1] = 0
     w = np.array([1 / 3] + [1 / 18] * 6 + [1 / 36] * 12, np.float32) if q == 19 else \
         np.array([8 / 27] + [2 / 27] * 6 + [1 / 54] * 12 + [1 / 216] * 8, np.float32)
     host_f = torch.empty((q, nx, gy, gz), dtype=torch.float32, pin_memory=True)
@@ -218,17 +213,16 @@ def run_ours(args):
         hf[i] = w[i] * (1.0 + 3.0 * cx[i] * u0 + 4.5 * (cx[i] * u0) ** 2 - 1.5 * u0 * u0)   # equilibrium at rho = 1, u = (u0, 0, 0)
         hf[i][interior.astype(bool)] = 0.0
 
+    stepper = slab if slab is not None else lat
     lat.set_solid_mask(solid, x_ghost_planes=(world > 1))
-    lat.load_populations(hf)
+    stepper.load_populations(hf)
     if x_off == 0:
         lat.setFlowData(lb.FlowData(((0, None, None), (0, None, None)), flow))
     lat.setReflectionData(lb.ReflectionData())
 
-    stepper = slab if slab is not None else lat
-
     def barrier():
-        lat.sync()
         torch.cuda.synchronize()
+        lat.sync()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
@@ -266,7 +260,7 @@ def run_ours(args):
         force = np.zeros(3, np.float32)
         barrier()
         t0 = time.perf_counter()
-        lat.load_populations(hf)
+        stepper.load_populations(hf)
         for _ in range(args.steps):
             if x_off == 0:
                 lat.setFlowData(lb.FlowData(((0, None, None), (0, None, None)), flow))   # this step's inflow, from the host

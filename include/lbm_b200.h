@@ -184,6 +184,9 @@ LBM_API int lbm_plane_ptr(lbm_handle h, int q, int xp, void **dev_ptr, size_t *b
 LBM_API int lbm_face_populations(lbm_handle h, int side, int32_t *qs, int *nq);
 /* the handle's stream as a cudaStream_t */
 LBM_API int lbm_get_stream(lbm_handle h, void **stream);
+/* run all further work of this handle on a caller-owned cudaStream_t (NULL: back to the handle's own
+ * stream), e.g. the stream a communication library orders its transfers against */
+LBM_API int lbm_set_stream(lbm_handle h, void *stream);
 /* step only planes [x0, x1) of the slab (0-based interior planes), without swapping
  * buffers; lbm_step_commit swaps.  Lets the caller compute edge planes first, start the
  * halo exchange, then the interior. */

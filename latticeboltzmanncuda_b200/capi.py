@@ -101,6 +101,7 @@ SYMBOLS = [
     ("lbm_next_plane_ptr", _i, [_vp, _i, _i, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     ("lbm_face_populations", _i, [_vp, _i, _vp, C.POINTER(_i)]),
     ("lbm_get_stream", _i, [_vp, C.POINTER(_vp)]),
+    ("lbm_set_stream", _i, [_vp, _vp]),
     ("lbm_step_range", _i, [_vp, _u, _i, _i, _i]),
     ("lbm_step_commit", _i, [_vp]),
     ("lbm_fill_ghosts", _i, [_vp]),

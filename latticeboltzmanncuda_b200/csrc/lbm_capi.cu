@@ -49,7 +49,7 @@ struct lbm_lattice_s {
     lbm_config cfg;
     Geom g;
     int device = 0;
-    cudaStream_t stream = nullptr, side = nullptr;
+    cudaStream_t stream = nullptr, side = nullptr, own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_side = nullptr, ev_main = nullptr;
     float* buf[2] = {nullptr, nullptr};
     int cur = 0;
@@ -324,7 +324,8 @@ LBM_API int lbm_create(const lbm_config* cfg, lbm_handle* out)
         if (e_ != cudaSuccess)                                                             \
             return bail(fail(e_ == cudaErrorMemoryAllocation ? LBM_ERR_NOMEM : LBM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_))); \
     } while (0)
-    CKB(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKB(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
     CKB(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
     CKB(cudaEventCreate(&h->ev0));
     CKB(cudaEventCreate(&h->ev1));
@@ -362,7 +363,7 @@ LBM_API int lbm_destroy(lbm_handle h)
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_side) cudaEventDestroy(h->ev_side);
     if (h->ev_main) cudaEventDestroy(h->ev_main);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->side) cudaStreamDestroy(h->side);
     delete h;
     return LBM_OK;
@@ -791,6 +792,16 @@ LBM_API int lbm_get_stream(lbm_handle h, void** stream)
 {
     if (!h || !stream) return fail(LBM_ERR_INVALID, "null argument");
     *stream = (void*)h->stream;
+    return LBM_OK;
+}
+
+LBM_API int lbm_set_stream(lbm_handle h, void* stream)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    if (h->cls) pin_classes_in_l2(h);
     return LBM_OK;
 }
 

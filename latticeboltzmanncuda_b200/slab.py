@@ -1,0 +1,187 @@
+"""Slab decomposition of the lattice along x across the GPUs of one box (one process per GPU).
+
+The reference is single-GPU (no cudaSetDevice, no NCCL/MPI anywhere); this is a build
+extension with one requirement: the same answer as one GPU.  x is the slowest axis of the SoA layout
+f[q][x][y][z], so a ghost plane of one population is one contiguous run of yp*zp floats and needs no
+packing.  Per step every rank hands the populations that leave through its +x face (c_x = +1) to the low
+ghost plane of its right neighbour and those that leave through its -x face (c_x = -1) to the high ghost
+plane of its left neighbour: 5 planes per face for D3Q19, 9 for D3Q27.
+
+`HaloExchange` holds the neighbour logic and runs on any torch.distributed backend (NCCL on the GPUs,
+gloo in the CPU tests).  `SlabLattice` drives one `Lattice` handle per rank: edge planes first, then the
+exchange of the new edge planes into the neighbours' ghost planes, overlapped with the interior planes.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .lattice import FlowData, Lattice
+
+_DIRS_X = np.array([0, -1, 0, 0, 0, 0, 1, -1, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 1, -1, -1, -1, -1, 1, 1, 1, 1])
+
+
+def face_populations(q, side):
+    """populations that cross the +x face (side=1, c_x=+1) or the -x face (side=0, c_x=-1)"""
+    want = 1 if side else -1
+    return [i for i in range(q) if _DIRS_X[i] == want]
+
+
+def slab_range(gx, rank, world):
+    """[x0, x1) of the global x planes owned by `rank` (as even as possible, larger slabs first)"""
+    base, extra = divmod(gx, world)
+    x0 = rank * base + min(rank, extra)
+    return x0, x0 + base + (1 if rank < extra else 0)
+
+
+class HaloExchange:
+    """who sends which plane to whom.  `periodic` closes the ring; otherwise the end slabs keep their
+    outer ghost planes as the domain-edge rule left them (zero inflow)."""
+
+    def __init__(self, rank, world, periodic, q):
+        self.rank, self.world, self.periodic, self.q = rank, world, bool(periodic), q
+        self.right = (rank + 1) % world if (periodic or rank + 1 < world) else None
+        self.left = (rank - 1) % world if (periodic or rank > 0) else None
+        self.up = face_populations(q, 1)      # leave through +x, enter the right neighbour's low ghost plane
+        self.down = face_populations(q, 0)    # leave through -x, enter the left neighbour's high ghost plane
+
+    def transfers(self, send_plane, recv_plane):
+        """list of ("send"|"recv", tensor, peer, tag).  send_plane(q, which) gives my edge plane of population
+        q (which = "lo" first interior plane, "hi" last interior plane); recv_plane(q, which) gives my ghost plane
+        (which = "lo" ghost below x=0, "hi" ghost above x=nx-1).  Tags keep the two directions apart when
+        left == right (two ranks, periodic)."""
+        # NCCL matches the sends and receives of a rank pair in the order they are posted and ignores tags,
+        # so every rank posts the rightward wave first and the leftward wave second; with two ranks on a
+        # ring (left == right) the pair then sees "up, down" on both ends.
+        ops = []
+        if self.right is not None:
+            for i in self.up:
+                ops.append(("send", send_plane(i, "hi"), self.right, i))
+        if self.left is not None:
+            for i in self.up:
+                ops.append(("recv", recv_plane(i, "lo"), self.left, i))
+            for i in self.down:
+                ops.append(("send", send_plane(i, "lo"), self.left, 100 + i))
+        if self.right is not None:
+            for i in self.down:
+                ops.append(("recv", recv_plane(i, "hi"), self.right, 100 + i))
+        return ops
+
+    def run(self, send_plane, recv_plane, dist):
+        """posts every transfer of one exchange and returns the work handles"""
+        ops = self.transfers(send_plane, recv_plane)
+        if not ops:
+            return []
+        p2p = [dist.P2POp(dist.isend if kind == "send" else dist.irecv, t, peer, tag=tag) for kind, t, peer, tag in ops]
+        return dist.batch_isend_irecv(p2p)
+
+
+class _DevicePlane:
+    """zero-copy view of a device plane for torch.as_tensor (CUDA array interface)"""
+
+    def __init__(self, ptr, nfloat):
+        self.__cuda_array_interface__ = {"shape": (nfloat,), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+class SlabLattice:
+    """one x-slab of a gx x gy x gz lattice, driven like a `Lattice`"""
+
+    def __init__(self, gx, gy, gz, fluid, rank, world, device, bc_x=capi.BC_PERIODIC, bc_yz=(capi.BC_PERIODIC,) * 2,
+                 overlap=True, **kw):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        if bc_x not in (capi.BC_PERIODIC, capi.BC_ZERO_INFLOW):
+            raise ValueError("the global x edge must be periodic or zero-inflow in slab mode")
+        self.rank, self.world = rank, world
+        self.x0, self.x1 = slab_range(gx, rank, world)
+        self.gx, self.nx = gx, self.x1 - self.x0
+        if self.nx < 2:
+            raise ValueError("every slab needs at least two x planes")
+        self.lattice = Lattice(self.nx, gy, gz, None, None, fluid, 1.0, bc=(capi.BC_HALO, bc_yz[0], bc_yz[1]),
+                               device=device, **kw)
+        self.q = self.lattice.q
+        self.halo = HaloExchange(rank, world, bc_x == capi.BC_PERIODIC, self.q)
+        self.overlap = bool(overlap)
+        self._lib = capi.load()
+        self._views = {}
+        # everything this handle launches is ordered on a torch stream, which NCCL transfers order against
+        self.stream = torch.cuda.Stream(device=device)
+        capi.check(self._lib.lbm_set_stream(self.lattice.handle, C.c_void_p(self.stream.cuda_stream)))
+        self._ghosts_current = False
+
+    # ---- plane views ----------------------------------------------------------------------------
+    def _plane(self, q, xp, nxt):
+        ptr, nbytes = C.c_void_p(), C.c_size_t()
+        fn = self._lib.lbm_next_plane_ptr if nxt else self._lib.lbm_plane_ptr
+        capi.check(fn(self.lattice.handle, q, xp, C.byref(ptr), C.byref(nbytes)))
+        key = ptr.value
+        v = self._views.get(key)
+        if v is None:
+            v = self.torch.as_tensor(_DevicePlane(ptr.value, nbytes.value // 4), device=self.torch.device("cuda", self.lattice.cfg.device))
+            self._views[key] = v
+        return v
+
+    def _exchange(self, nxt):
+        """edge planes of the (next or current) state -> the neighbours' ghost planes of the same state"""
+        nx = self.nx
+        send = lambda q, which: self._plane(q, 1 if which == "lo" else nx, nxt)
+        recv = lambda q, which: self._plane(q, 0 if which == "lo" else nx + 1, nxt)
+        with self.torch.cuda.stream(self.stream):
+            return self.halo.run(send, recv, self.dist)
+
+    # ---- stepping --------------------------------------------------------------------------------
+    def prime(self):
+        """fill the ghost planes of the freshly loaded state (needed once before the first step)"""
+        for w in self._exchange(nxt=False):
+            w.wait()
+        self._ghosts_current = True
+
+    def step(self, n=1, phases=capi.PHASE_ALL):
+        lib, h = self._lib, self.lattice.handle
+        if not self._ghosts_current:
+            self.prime()
+        with self.torch.cuda.stream(self.stream):
+            for _ in range(int(n)):
+                capi.check(lib.lbm_fill_ghosts(h))                 # y faces, including the x ghost planes
+                if self.overlap and self.nx >= 4:
+                    # edge planes first, their exchange overlaps the interior planes on the side stream
+                    capi.check(lib.lbm_step_range(h, phases, 0, 1, 0))
+                    capi.check(lib.lbm_step_range(h, phases, self.nx - 1, self.nx, 0))
+                    capi.check(lib.lbm_step_range(h, phases, 1, self.nx - 1, 1))
+                    works = self._exchange(nxt=True)
+                else:
+                    capi.check(lib.lbm_step_range(h, phases, 0, self.nx, 0))
+                    works = self._exchange(nxt=True)
+                for w in works:
+                    w.wait()                                       # stream-ordered for NCCL, blocking for gloo
+                capi.check(lib.lbm_step_commit(h))
+
+    def step_timed(self, n, phases=capi.PHASE_ALL):
+        torch = self.torch
+        st0 = self.lattice.stats()["kernel_launches"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if not self._ghosts_current:
+            self.prime()
+        self.stream.synchronize()
+        e0.record(self.stream)
+        self.step(n, phases)
+        e1.record(self.stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1), self.lattice.stats()["kernel_launches"] - st0
+
+    # ---- inputs in global coordinates ---------------------------------------------------------------
+    def load_populations(self, f_local):
+        self.lattice.load_populations(f_local)
+        self._ghosts_current = False
+
+    def set_source_global(self, lo, hi, flow):
+        """source box in global cell coordinates (None = whole axis); ranks the box misses get none"""
+        gl = 0 if lo[0] is None else lo[0]
+        gh = self.gx - 1 if hi[0] is None else hi[0]
+        l, hgh = max(gl, self.x0) - self.x0, min(gh, self.x1 - 1) - self.x0
+        if l > hgh:
+            self.lattice.setFlowData(None)
+        else:
+            self.lattice.setFlowData(FlowData(((l, lo[1], lo[2]), (hgh, hi[1], hi[2])), flow))

@@ -1,0 +1,117 @@
+"""Slab decomposition along x with world_size 2 and 3 over gloo on the CPU: the neighbour logic and plane
+selection of latticeboltzmanncuda_b200.slab.HaloExchange, with the CPU oracle standing in for the step
+kernel.  The decomposed run must reproduce the single-domain run bit for bit (no arithmetic crosses the
+cut, every cell sees exactly the same operands)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import _oracle as O
+from latticeboltzmanncuda_b200.slab import HaloExchange, face_populations, slab_range
+
+
+def test_face_populations_match_velocity_set():
+    for q, n in ((19, 5), (27, 9)):
+        up, down = face_populations(q, 1), face_populations(q, 0)
+        assert len(up) == n and len(down) == n
+        assert all(O.DIRECTIONS[i][0] == 1 for i in up) and all(O.DIRECTIONS[i][0] == -1 for i in down)
+        assert sorted(int(O.INVERSE[i]) for i in up) == down          # the two faces carry opposite populations
+
+
+def test_slab_ranges_tile_the_axis():
+    for gx, world in ((16, 2), (17, 3), (1024, 8), (10, 4)):
+        edges = [slab_range(gx, r, world) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == gx
+        assert all(edges[r][1] == edges[r + 1][0] for r in range(world - 1))
+        assert max(b - a for a, b in edges) - min(b - a for a, b in edges) <= 1
+
+
+def test_neighbours_and_tags():
+    h = HaloExchange(0, 2, True, 19)
+    assert (h.left, h.right) == (1, 1)
+    ops = h.transfers(lambda q, w: ("s", q, w), lambda q, w: ("r", q, w))
+    assert len(ops) == 20                                   # 5 + 5 sends, 5 + 5 receives
+    # with left == right the two directions must not share a tag
+    sends = {(peer, tag) for kind, t, peer, tag in ops if kind == "send"}
+    recvs = {(peer, tag) for kind, t, peer, tag in ops if kind == "recv"}
+    assert len(sends) == 10 and sends == recvs
+    # NCCL ignores tags and matches a pair's sends and receives in posting order: the order in which rank 0
+    # posts its sends to rank 1 must be the order in which rank 1 posts its receives from rank 0
+    other = HaloExchange(1, 2, True, 19).transfers(lambda q, w: ("s", q, w), lambda q, w: ("r", q, w))
+    assert [tag for kind, t, peer, tag in ops if kind == "send"] == [tag for kind, t, peer, tag in other if kind == "recv"]
+    h = HaloExchange(0, 4, False, 27)
+    assert h.left is None and h.right == 1
+    assert len(h.transfers(lambda q, w: 0, lambda q, w: 0)) == 18
+    assert HaloExchange(3, 4, False, 27).right is None
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, q, gx, Y, Z, periodic_x, bc_yz, steps, f_global, solid_global, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x0, x1 = slab_range(gx, rank, world)
+        nx = x1 - x0
+        # local state with one ghost plane on each side of x: [q, nx+2, Y, Z]
+        loc = torch.zeros((q, nx + 2, Y, Z), dtype=torch.float32)
+        loc[:, 1:nx + 1] = torch.from_numpy(f_global[:, x0:x1])
+        xs = np.arange(x0 - 1, x1 + 1)
+        if periodic_x:
+            solid = solid_global[xs % gx]
+        else:
+            solid = np.zeros((nx + 2, Y, Z), np.uint8)
+            ok = (xs >= 0) & (xs < gx)
+            solid[ok] = solid_global[xs[ok]]
+        halo = HaloExchange(rank, world, periodic_x, q)
+        for _ in range(steps):
+            loc[:, 0] = 0
+            loc[:, nx + 1] = 0
+            bufs = {}
+
+            def send_plane(i, which):
+                return loc[i, 1 if which == "lo" else nx].contiguous()
+
+            def recv_plane(i, which):
+                bufs[(i, which)] = torch.zeros((Y, Z), dtype=torch.float32)
+                return bufs[(i, which)]
+
+            for w in halo.run(send_plane, recv_plane, dist):
+                w.wait()
+            for (i, which), t in bufs.items():
+                loc[i, 0 if which == "lo" else nx + 1] = t
+            # the oracle steps the slab with its ghost planes as ordinary cells behind an open x edge
+            new = O.step_soa(loc.numpy(), nx + 2, Y, Z, q, 0.7, bc=(O.BC_ZERO,) + tuple(bc_yz), solid=solid,
+                             moment=O.MOMENT_STANDARD, eq64=False, steps=1)
+            loc[:, 1:nx + 1] = torch.from_numpy(new[:, 1:nx + 1])
+        np.save(out_path % rank, loc[:, 1:nx + 1].numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,q,periodic_x,bc_yz", [(2, 19, True, (1, 1)), (2, 27, False, (2, 1)), (3, 19, True, (2, 2))])
+def test_decomposed_run_equals_single_domain(tmp_path, world, q, periodic_x, bc_yz):
+    gx, Y, Z, steps = 11, 5, 6, 6
+    rng = np.random.default_rng(3)
+    w = O.weights(q).astype(np.float32)
+    f = (w[:, None, None, None] * (1 + 0.05 * rng.standard_normal((q, gx, Y, Z)))).astype(np.float32)
+    solid = (rng.random((gx, Y, Z)) < 0.1).astype(np.uint8)
+    f[:, solid.astype(bool)] = 0
+    bc = ((O.BC_PERIODIC if periodic_x else O.BC_ZERO),) + tuple(bc_yz)
+    want = O.step_soa(f, gx, Y, Z, q, 0.7, bc=bc, solid=solid, moment=O.MOMENT_STANDARD, eq64=False, steps=steps)
+    out = str(tmp_path / "slab_%d.npy")
+    mp.spawn(_worker, args=(world, _free_port(), q, gx, Y, Z, periodic_x, bc_yz, steps, f, solid, out), nprocs=world, join=True)
+    got = np.concatenate([np.load(out % r) for r in range(world)], axis=1)
+    assert np.array_equal(got, want)
