@@ -219,6 +219,41 @@ typedef struct lbm_stats {
 } lbm_stats;
 LBM_API int lbm_get_stats(lbm_handle h, lbm_stats *out);
 
+/* ---- geometry side inputs (the callers of the path) ---------------------- */
+
+typedef struct lbm_mesh_s *lbm_mesh;
+
+/* Model::importModel (simulation/source/Model.cpp:22-44): reads an OBJ file.  A missing file gives an empty
+ * model, like the reference; a mesh that is not all triangles or not closed is "invalid" (nothing is inside). */
+LBM_API int lbm_mesh_load(const char *path, lbm_mesh *out);
+LBM_API int lbm_mesh_destroy(lbm_mesh m);
+/* number_of_vertices / faces, Model::isModelClosed (Model.cpp:46-49), !Model::checkError (Model.h:34) */
+LBM_API int lbm_mesh_info(lbm_mesh m, int *n_vertices, int *n_faces, int *closed, int *valid);
+/* Model::bounding_box (Model.cpp:70-73) */
+LBM_API int lbm_mesh_bounding_box(lbm_mesh m, float lo[3], float hi[3]);
+/* Model::isPointInsideModel (Model.cpp:51-63): inside or on the boundary */
+LBM_API int lbm_mesh_point_inside(lbm_mesh m, const float p[3], int *inside);
+/* Model::reflectionVector (Model.cpp:75-91): mirror of the direction p1 - p2 about the first facet the ray
+ * from p1 towards p2 hits; (0,0,0) when it hits nothing */
+LBM_API int lbm_mesh_reflection_vector(lbm_mesh m, const float p1[3], const float p2[3], float out[3]);
+/* rotateVectorAroundAxis (simulation/source/Geometry.cpp:22-42) */
+LBM_API int lbm_rotate_vector_around_axis(const float axis[3], const float vec[3], float angle, float out[3]);
+/* Lattice::distributeVector (Lattice.cpp:262-321): the 27 directions ranked by closeness to v */
+LBM_API int lbm_distribute_vector(const float v[3], float scores[27], int32_t dirs[27]);
+/* Utils::compressInts (simulation/source/Utils.cpp:4-29) */
+LBM_API unsigned lbm_compress_ints(const int *array, int num, int bit_length);
+
+/* Lattice::insertModel (Lattice.cpp:228-260): voxelise the mesh on the lattice points (index * spacing) on
+ * the GPU and make the result the solid mask.  *accepted = 0 when the bounding-box guard rejects the mesh
+ * (or the file was missing): the lattice is left alone, as in the reference. */
+LBM_API int lbm_insert_model(lbm_handle h, lbm_mesh m, float spacing, int *accepted);
+/* Lattice::preProcessModel (Lattice.cpp:323-426): build the reflection tables of the boundary-solid cells on
+ * the GPU and install them (as lbm_set_reflection_table would). */
+LBM_API int lbm_preprocess_model(lbm_handle h, lbm_mesh m, float spacing);
+/* the tables currently installed: up to `capacity` 380-byte records and the host index of their cells.
+ * Pass NULL buffers to query *n only. */
+LBM_API int lbm_get_reflection_tables(lbm_handle h, void *tables, int64_t *cell_index, int capacity, int *n);
+
 #ifdef __cplusplus
 }
 #endif

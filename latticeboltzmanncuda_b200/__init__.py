@@ -11,5 +11,6 @@ from .capi import (ENGINE_AUTO, ENGINE_INPLACE, ENGINE_PULL2, ENGINE_TMA, BC_HAL
                    MOMENT_REFERENCE, MOMENT_STANDARD, PHASE_ALL, PHASE_COLLIDE, PHASE_REFLECT, PHASE_SOURCE,
                    PHASE_STREAM, REFLECTION_VALUES, LbmError)
 from .lattice import FlowCriterion, FlowData, FluidData, Lattice, ReflectionData
+from .model import Model, compressInts, distributeVector, getReflectionDirection, rotateVectorAroundAxis
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -7,8 +7,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblbm_b200.so")
-SOURCES = ["lbm_kernels.cu", "lbm_capi.cu", "lbm_tma.cu", "lbm_geometry.cu"]
-HEADERS = ["d3q.h", "lbm_device.h", os.path.join("..", "..", "include", "lbm_b200.h")]
+SOURCES = ["lbm_kernels.cu", "lbm_capi.cu", "lbm_geometry.cu"]
+# per-file extra flags: the geometry predicates must evaluate identically on host and device
+EXTRA = {"lbm_geometry.cu": ["-fmad=false"]}
+HEADERS = ["d3q.h", "lbm_device.h", "lbm_internal.h", os.path.join("..", "..", "include", "lbm_b200.h")]
 
 
 def nvcc_path():
@@ -34,11 +36,22 @@ def build_native(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a -> latticeboltzmanncuda_b200/liblbm_b200.so"""
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-o", LIB] + sources()
+    nvcc = nvcc_path()
+    common = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC,-fvisibility=hidden"]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.check_call(cmd, cwd=CSRC)
+        common.append("-Xptxas=-v")
+    objdir = os.path.join(CSRC, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    procs, objs = [], []
+    for src in sources():
+        obj = os.path.join(objdir, src + ".o")
+        objs.append(obj)
+        procs.append(subprocess.Popen([nvcc] + common + EXTRA.get(src, []) + ["-c", src, "-o", obj], cwd=CSRC))
+    for pr in procs:
+        if pr.wait() != 0:
+            raise RuntimeError("nvcc failed")
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs, cwd=CSRC)
     return LIB
 
 

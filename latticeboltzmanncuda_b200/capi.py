@@ -107,6 +107,18 @@ SYMBOLS = [
     ("lbm_fill_ghosts", _i, [_vp]),
     ("lbm_get_layout", _i, [_vp, C.POINTER(Layout)]),
     ("lbm_get_stats", _i, [_vp, C.POINTER(Stats)]),
+    ("lbm_mesh_load", _i, [C.c_char_p, C.POINTER(_vp)]),
+    ("lbm_mesh_destroy", _i, [_vp]),
+    ("lbm_mesh_info", _i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    ("lbm_mesh_bounding_box", _i, [_vp, _vp, _vp]),
+    ("lbm_mesh_point_inside", _i, [_vp, _vp, C.POINTER(_i)]),
+    ("lbm_mesh_reflection_vector", _i, [_vp, _vp, _vp, _vp]),
+    ("lbm_rotate_vector_around_axis", _i, [_vp, _vp, C.c_float, _vp]),
+    ("lbm_distribute_vector", _i, [_vp, _vp, _vp]),
+    ("lbm_compress_ints", _u, [_vp, _i, _i]),
+    ("lbm_insert_model", _i, [_vp, _vp, C.c_float, C.POINTER(_i)]),
+    ("lbm_preprocess_model", _i, [_vp, _vp, C.c_float]),
+    ("lbm_get_reflection_tables", _i, [_vp, _vp, _vp, _i, C.POINTER(_i)]),
 ]
 
 _lib = None

@@ -5,6 +5,7 @@
 // and only their roles swap).
 #include "../../include/lbm_b200.h"
 #include "lbm_device.h"
+#include "lbm_internal.h"
 
 #include <algorithm>
 #include <cstdarg>
@@ -44,44 +45,6 @@ constexpr int AOS_BYTES = 144;     // sizeof(LatticePoint), simulation/include/L
 constexpr int TABLE_BYTES = 380;   // sizeof(ReflectionValues), LatticePoint.h:3-7
 
 }  // namespace
-
-struct lbm_lattice_s {
-    lbm_config cfg;
-    Geom g;
-    int device = 0;
-    cudaStream_t stream = nullptr, side = nullptr, own_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_side = nullptr, ev_main = nullptr;
-    float* buf[2] = {nullptr, nullptr};
-    int cur = 0;
-    bool pending_commit = false;
-    unsigned pending_phases = 0;
-    uint32_t* solid = nullptr;       // padded bit mask
-    uint8_t* cls = nullptr;          // class of every interior 32-cell word, [x][word][y]
-    int cls_pitch = 0;
-    size_t cls_bytes = 0;
-    int dead_dirty = 2;              // steps for which all-solid words must still be written as zeros
-    uint32_t* cellinfo = nullptr;    // neighbourhood word per padded cell (special words only)
-    uint32_t* special_list = nullptr;   // mask-word indices of the special words
-    size_t n_special = 0;
-    bool any_solid = false;          // some bit set (geometry or wall ghosts)
-    uint8_t* solid_bytes = nullptr;  // nx*ny*nz (+2 planes) scratch
-    uint32_t *tmask = nullptr, *tprefix = nullptr, *toff = nullptr, *reflected = nullptr;
-    Link* links = nullptr;
-    size_t nlinks = 0;
-    double* force = nullptr;         // 3 doubles
-    bool force_on = false;
-    int src_on = 0;
-    int src_lo[3] = {0, 0, 0}, src_hi[3] = {0, 0, 0};
-    float src_f[27] = {0};
-    double* diag = nullptr;          // 4 doubles
-    unsigned* flag = nullptr;
-    void* staging = nullptr;
-    long long launches = 0;
-
-    size_t pop_bytes() const { return (size_t)g.np * sizeof(float); }
-    size_t state_bytes() const { return pop_bytes() * (size_t)cfg.q; }
-    size_t mask_words() const { return (size_t)g.xp * g.yp * g.wz; }
-};
 
 namespace {
 
@@ -266,6 +229,11 @@ int one_step(lbm_handle h, unsigned phases)
 }
 
 }  // namespace
+
+// doors for the other translation units of the library (lbm_internal.h)
+int lbm_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
+int lbm_internal_use(lbm_handle h) { return use(h); }
+int lbm_internal_rebuild_mask(lbm_handle h, const uint8_t* dev_bytes, int has_x_ghost) { return rebuild_mask(h, dev_bytes, has_x_ghost); }
 
 // ---- C ABI -------------------------------------------------------------------------------------
 
@@ -589,6 +557,8 @@ LBM_API int lbm_set_reflection_table(lbm_handle h, const void* tables, const int
             hl.push_back(e);
         }
     }
+    h->host_tables.assign((const unsigned char*)tables, (const unsigned char*)tables + (size_t)n * TABLE_BYTES);
+    h->host_table_cells.assign(cell_index, cell_index + n);
     std::sort(hl.begin(), hl.end(), [](const HostLink& a, const HostLink& b) {
         if (a.tgt != b.tgt) return a.tgt < b.tgt;
         if (a.l.d != b.l.d) return a.l.d < b.l.d;      // the kernel walks a target's links population by population

@@ -166,6 +166,35 @@ class Lattice:
         self.m_reflections, self._table_cells = t, k
         capi.check(self._lib.lbm_set_reflection_table(self._h, capi.ptr(t), capi.ptr(k), t.size))
 
+    def insertModel(self, filename):
+        """Lattice::insertModel (Lattice.cpp:228-260): voxelise the mesh on the GPU; a missing file or a mesh
+        that leaves the box is silently ignored, like the reference"""
+        from .model import Model
+        self.m_simModel = Model(filename)
+        accepted = C.c_int()
+        capi.check(self._lib.lbm_insert_model(self._h, self.m_simModel.handle, self.m_latticeSpacing, C.byref(accepted)))
+        return bool(accepted.value)
+
+    def preProcessModel(self):
+        """Lattice::preProcessModel (Lattice.cpp:323-426): build and install the reflection tables on the GPU"""
+        if getattr(self, "m_simModel", None) is None:
+            return
+        capi.check(self._lib.lbm_preprocess_model(self._h, self.m_simModel.handle, self.m_latticeSpacing))
+        self.m_reflections, self._table_cells = self.reflection_tables()
+
+    def reflection_tables(self):
+        n = C.c_int()
+        capi.check(self._lib.lbm_get_reflection_tables(self._h, None, None, 0, C.byref(n)))
+        t = np.zeros(n.value, REFLECTION_VALUES)
+        k = np.zeros(n.value, np.int64)
+        if n.value:
+            capi.check(self._lib.lbm_get_reflection_tables(self._h, capi.ptr(t), capi.ptr(k), n.value, C.byref(n)))
+        return t, k
+
+    def distributeVector(self, vector):
+        from .model import distributeVector
+        return distributeVector(vector)[0]
+
     def setFlowData(self, flowData):
         """Lattice.cpp:428-436"""
         self.m_flowData = flowData
