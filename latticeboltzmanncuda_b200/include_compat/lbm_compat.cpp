@@ -1,0 +1,338 @@
+// lbm_compat.cpp -- the reference's C++ interface (Lattice, RunCudaFunctions, Model, rotateVectorAroundAxis,
+// CONSTANTS, Utils, FlowCriterion) implemented on the C ABI of liblbm_b200.so (include/lbm_b200.h).
+// Host code only: every line of device work sits behind the C ABI.
+#include "Lattice.h"
+#include "SimCalcFuncs.cuh"
+#include "Model.h"
+#include "Constants.h"
+#include "Utils.h"
+
+#include "../../include/lbm_b200.h"
+
+#include <cstdio>
+#include <cstring>
+
+// ---- Constants / Utils / Geometry / FlowCriterion ---------------------------------------------------------
+
+namespace CONSTANTS
+{
+    const float GEOMETRIC_TOLERANCE = 1e-6;
+    const int DIRECTIONS[27][3] = {
+        { 0, 0, 0},
+        {-1, 0, 0}, { 0,-1, 0}, { 0, 0,-1}, { 0, 0, 1}, { 0, 1, 0}, { 1, 0, 0},
+        {-1,-1, 0}, {-1, 0,-1}, {-1, 0, 1}, {-1, 1, 0}, { 0,-1,-1}, { 0,-1, 1},
+        { 0, 1,-1}, { 0, 1, 1}, { 1,-1, 0}, { 1, 0,-1}, { 1, 0, 1}, { 1, 1, 0},
+        {-1,-1,-1}, {-1,-1, 1}, {-1, 1,-1}, {-1, 1, 1}, { 1,-1,-1}, { 1,-1, 1}, { 1, 1,-1}, { 1, 1, 1}};
+    const int INVERSE_DIRECTIONS[27] = {0, 6, 5, 4, 3, 2, 1, 18, 17, 16, 15, 14, 13, 12, 11, 10, 9, 8, 7,
+                                        26, 25, 24, 23, 22, 21, 20, 19};
+}
+
+namespace Utils
+{
+    unsigned int compressInts(int* array, const int num, const int bitLength) { return lbm_compress_ints(array, num, bitLength); }
+}
+
+Point_3 rotateVectorAroundAxis(Point_3 axis, Point_3 vector, float angle)
+{
+    const float a[3] = {axis.x, axis.y, axis.z}, v[3] = {vector.x, vector.y, vector.z};
+    float out[3] = {0, 0, 0};
+    lbm_rotate_vector_around_axis(a, v, angle, out);
+    return Point_3(out[0], out[1], out[2]);
+}
+
+namespace FlowCriterion
+{
+    bool testCriteria(int x, int y, int z) { return x == 1 && y == 1 && z == 1; }
+    bool testPlaneCriteria(int x, int, int) { return x == 0; }
+    bool (*ptestCriteria)(int, int, int) = &FlowCriterion::testCriteria;
+    bool (*ptestPlaneCriteria)(int, int, int) = &FlowCriterion::testPlaneCriteria;
+}
+
+// ---- Model ---------------------------------------------------------------------------------------------------
+
+Model::~Model() { lbm_mesh_destroy(m_mesh); }
+
+void Model::importModel(std::string filename)
+{
+    lbm_mesh_destroy(m_mesh);
+    m_mesh = nullptr;
+    lbm_mesh_load(filename.c_str(), &m_mesh);
+}
+
+bool Model::isModelClosed()
+{
+    int closed = 0;
+    if (m_mesh) lbm_mesh_info(m_mesh, nullptr, nullptr, &closed, nullptr);
+    return closed != 0;
+}
+
+int Model::number_of_vertices()
+{
+    int n = 0;
+    if (m_mesh) lbm_mesh_info(m_mesh, &n, nullptr, nullptr, nullptr);
+    return n;
+}
+
+bool Model::checkError()
+{
+    int valid = 1;
+    if (m_mesh) lbm_mesh_info(m_mesh, nullptr, nullptr, nullptr, &valid);
+    return !valid;
+}
+
+bool Model::isPointInsideModel(Point_3 point)
+{
+    int inside = 0;
+    const float p[3] = {point.x, point.y, point.z};
+    if (m_mesh) lbm_mesh_point_inside(m_mesh, p, &inside);
+    return inside != 0;
+}
+
+BoundingBox Model::bounding_box()
+{
+    BoundingBox b;
+    std::memset(&b, 0, sizeof b);
+    if (m_mesh) lbm_mesh_bounding_box(m_mesh, b.lo, b.hi);
+    return b;
+}
+
+Point_3 Model::reflectionVector(Point_3 point_1, Point_3 point_2)
+{
+    const float a[3] = {point_1.x, point_1.y, point_1.z}, b[3] = {point_2.x, point_2.y, point_2.z};
+    float out[3] = {0, 0, 0};
+    if (m_mesh) lbm_mesh_reflection_vector(m_mesh, a, b, out);
+    return Point_3(out[0], out[1], out[2]);
+}
+
+// ---- Lattice -------------------------------------------------------------------------------------------------
+
+bool Lattice::check(int rc, const char* what)
+{
+    if (rc == LBM_OK) return true;
+    m_lastError = std::string(what) + ": " + lbm_last_error();
+    printf("Lattice::%s failed: %s\n", what, lbm_last_error());     // the reference prints and carries on
+    return false;
+}
+
+Lattice::Lattice(int x, int y, int z, dim3 blocks, dim3 threads, FluidData fluid, float spacing)
+{
+    m_xResolution = x; m_yResolution = y; m_zResolution = z;
+    m_blocks = blocks; m_threads = threads;
+    m_fluid = fluid;
+    m_latticeSpacing = spacing;
+    lbm_config cfg;
+    lbm_config_default(&cfg);          // the reference's behaviour: D3Q27, SPLIT moments, fp64 equilibrium, zero inflow, tables
+    cfg.nx = x; cfg.ny = y; cfg.nz = z;
+    cfg.tau = fluid.m_characteristicTimescale;
+    check(lbm_create(&cfg, &m_handle), "Lattice");
+}
+
+Lattice::~Lattice()
+{
+    lbm_destroy(m_handle);
+    delete m_simModel;
+}
+
+cudaPitchedPtr Lattice::getCudaDataPointer()
+{
+    flush();
+    return make_cudaPitchedPtr((void*)m_handle, sizeof(LatticePoint) * m_xResolution, m_xResolution, m_yResolution);
+}
+
+// Phases arrive one call at a time in the CLI's order stream, reflect, collide, source
+// (LatticeBoltzmannCuda.cpp:89-92).  They are queued while they extend that order and executed as ONE fused
+// kernel step when the sequence is complete; anything else executes what is queued phase by phase first.
+void Lattice::queue(unsigned phase)
+{
+    if (!m_handle) return;
+    // `phase` extends the queued prefix iff it is the next phase in CLI order: S -> S|R -> S|R|C -> S|R|C|F
+    const bool extends = m_pending != 0 && (m_pending & LBM_PHASE_STREAM) && phase == ((m_pending + 1) & ~m_pending) &&
+                         (m_pending | phase) == ((phase << 1) - 1);
+    if (!extends) flush();
+    m_pending |= phase;
+    if (m_pending == LBM_PHASE_ALL) flush();
+}
+
+void Lattice::flush()
+{
+    if (!m_handle || m_pending == 0) return;
+    const unsigned p = m_pending;
+    m_pending = 0;
+    check(lbm_step_phases(m_handle, 1, p), "simulate");      // one launch for whatever prefix was queued
+}
+
+void Lattice::simulateStreaming() { queue(LBM_PHASE_STREAM); }
+void Lattice::simulateReflections() { queue(LBM_PHASE_REFLECT); }
+void Lattice::simulateCollision() { queue(LBM_PHASE_COLLIDE); }
+void Lattice::simulateFlow() { if (m_flowData != nullptr) queue(LBM_PHASE_SOURCE); else flush(); }
+
+void Lattice::simulateLattice()
+{
+    flush();
+    if (m_handle) check(lbm_step_phases(m_handle, 1, LBM_PHASE_STREAM | LBM_PHASE_COLLIDE), "simulateLattice");
+}
+
+void Lattice::simulateSteps(int n)
+{
+    flush();
+    if (m_handle) check(lbm_step(m_handle, n), "simulateSteps");
+}
+
+void Lattice::synchronize()
+{
+    flush();
+    if (m_handle) check(lbm_sync(m_handle), "synchronize");
+}
+
+void Lattice::load_data(LatticePoint* lattice_array)
+{
+    flush();
+    if (!m_handle) return;
+    check(lbm_upload_aos(m_handle, lattice_array, (size_t)m_xResolution * m_yResolution * m_zResolution), "load_data");
+}
+
+LatticePoint* Lattice::retrieve_data()
+{
+    flush();
+    if (!m_handle) return nullptr;
+    const size_t n = (size_t)m_xResolution * m_yResolution * m_zResolution;
+    LatticePoint* out = new LatticePoint[n];
+    if (!check(lbm_download_aos(m_handle, out, n), "retrieve_data")) {
+        delete[] out;
+        return nullptr;
+    }
+    // reflecting cells point at their host table, as in the reference (tests read point->reflections)
+    for (size_t i = 0; i < m_reflectionCells.size(); ++i) out[m_reflectionCells[i]].reflections = &m_reflections[i];
+    return out;
+}
+
+void Lattice::setReflectionData(ReflectionData* reflection)
+{
+    flush();
+    m_reflectionData = reflection;
+    if (!m_handle) return;
+    if (!reflection) { check(lbm_set_force_accumulator(m_handle, 0, nullptr), "setReflectionData"); return; }
+    const float init[3] = {reflection->x, reflection->y, reflection->z};
+    check(lbm_set_force_accumulator(m_handle, 1, init), "setReflectionData");
+}
+
+ReflectionData* Lattice::retrieve_reflection_data()
+{
+    flush();
+    if (!m_handle || !m_reflectionData) return m_reflectionData;
+    float f[3] = {0, 0, 0};
+    if (check(lbm_get_force(m_handle, f), "retrieve_reflection_data")) {
+        m_reflectionData->x = f[0]; m_reflectionData->y = f[1]; m_reflectionData->z = f[2];
+    }
+    return m_reflectionData;
+}
+
+void Lattice::setFlowData(FlowData* flowData)
+{
+    flush();
+    m_flowData = flowData;
+    if (!m_handle) return;
+    if (!flowData) { check(lbm_set_source(m_handle, LBM_SOURCE_NONE, nullptr, nullptr, nullptr), "setFlowData"); return; }
+    const int dims[3] = {m_xResolution, m_yResolution, m_zResolution};
+    int32_t lo[3] = {0, 0, 0}, hi[3] = {dims[0] - 1, dims[1] - 1, dims[2] - 1};
+    if (flowData->pointCriterion == &FlowCriterion::testCriteria) {
+        lo[0] = lo[1] = lo[2] = hi[0] = hi[1] = hi[2] = 1;
+    } else if (flowData->pointCriterion == &FlowCriterion::testPlaneCriteria) {
+        hi[0] = 0;
+    } else {
+        // a user predicate: evaluate it once on the host; the kernel takes an index box
+        int32_t l[3] = {dims[0], dims[1], dims[2]}, h[3] = {-1, -1, -1};
+        long long count = 0;
+        for (int x = 0; x < dims[0]; ++x)
+            for (int y = 0; y < dims[1]; ++y)
+                for (int z = 0; z < dims[2]; ++z)
+                    if (flowData->pointCriterion(x, y, z)) {
+                        const int c[3] = {x, y, z};
+                        for (int a = 0; a < 3; ++a) { if (c[a] < l[a]) l[a] = c[a]; if (c[a] > h[a]) h[a] = c[a]; }
+                        ++count;
+                    }
+        if (count == 0) { check(lbm_set_source(m_handle, LBM_SOURCE_NONE, nullptr, nullptr, nullptr), "setFlowData"); return; }
+        if (count != (long long)(h[0] - l[0] + 1) * (h[1] - l[1] + 1) * (h[2] - l[2] + 1)) {
+            m_lastError = "setFlowData: the criterion does not select an index box";
+            printf("Lattice::setFlowData failed: the criterion does not select an index box\n");
+            return;
+        }
+        for (int a = 0; a < 3; ++a) { lo[a] = l[a]; hi[a] = h[a]; }
+    }
+    check(lbm_set_source(m_handle, LBM_SOURCE_BOX, lo, hi, flowData->inducedFlow.particle_distribution), "setFlowData");
+}
+
+void Lattice::insertModel(std::string filename)
+{
+    flush();
+    delete m_simModel;
+    m_simModel = new Model();
+    m_simModel->importModel(filename);
+    if (!m_handle || !m_simModel->handle()) return;
+    int accepted = 0;
+    check(lbm_insert_model(m_handle, m_simModel->handle(), m_latticeSpacing, &accepted), "insertModel");
+}
+
+void Lattice::preProcessModel()
+{
+    flush();
+    if (m_simModel == nullptr || !m_handle || !m_simModel->handle()) return;
+    if (!check(lbm_preprocess_model(m_handle, m_simModel->handle(), m_latticeSpacing), "preProcessModel")) return;
+    int n = 0;
+    lbm_get_reflection_tables(m_handle, nullptr, nullptr, 0, &n);
+    m_reflections.assign((size_t)n, ReflectionValues());
+    std::vector<int64_t> cells((size_t)n);
+    if (n) lbm_get_reflection_tables(m_handle, m_reflections.data(), cells.data(), n, &n);
+    m_reflectionCells.assign(cells.begin(), cells.end());
+}
+
+std::array<std::pair<float, int>, 27> Lattice::distributeVector(Point_3 vector)
+{
+    const float v[3] = {vector.x, vector.y, vector.z};
+    float scores[27];
+    int32_t dirs[27];
+    lbm_distribute_vector(v, scores, dirs);
+    std::array<std::pair<float, int>, 27> out;
+    for (int i = 0; i < 27; ++i) out[i] = {scores[i], dirs[i]};
+    return out;
+}
+
+void Lattice::setReflectionDirection(LatticePoint* point, const int index, const unsigned int value)
+{
+    const unsigned shift = 5u * (unsigned)(index % 6);
+    unsigned word = (unsigned)point->reflections->reflection_directions[index / 6];
+    word = (word & ~(0x1Fu << shift)) | (value << shift);
+    point->reflections->reflection_directions[index / 6] = (int)word;
+}
+
+int Lattice::getReflectionDirection(LatticePoint* point, const int index)
+{
+    const unsigned word = (unsigned)point->reflections->reflection_directions[index / 6];
+    return (int)((word >> (5u * (unsigned)(index % 6))) & 0x1Fu);
+}
+
+// ---- RunCudaFunctions ------------------------------------------------------------------------------------------
+
+namespace RunCudaFunctions
+{
+    static lbm_handle of(const LatticeData& d) { return (lbm_handle)d.latticePtr.ptr; }
+    static void report(int rc, const char* what)
+    {
+        if (rc != LBM_OK) printf("RunCudaFunctions::%s failed: %s\n", what, lbm_last_error());
+    }
+
+    void run_calculate_streaming(dim3, dim3, LatticeData lattice, LatticeData) { report(lbm_stream(of(lattice)), "run_calculate_streaming"); }
+
+    void run_calculate_collision(dim3, dim3, LatticeData lattice, float) { report(lbm_collide(of(lattice)), "run_calculate_collision"); }
+
+    void run_calculate_reflections(dim3, dim3, LatticeData lattice, LatticeData) { report(lbm_reflect(of(lattice)), "run_calculate_reflections"); }
+
+    void run_calculate_reflections_data(dim3, dim3, LatticeData lattice, LatticeData, ReflectionData*)
+    {
+        report(lbm_reflect(of(lattice)), "run_calculate_reflections_data");
+    }
+
+    void run_prime_points(dim3, dim3, LatticeData lattice) { report(lbm_prime_points(of(lattice)), "run_prime_points"); }
+
+    void run_generate_flow(dim3, dim3, LatticeData lattice, FlowData*) { report(lbm_source(of(lattice)), "run_generate_flow"); }
+}
