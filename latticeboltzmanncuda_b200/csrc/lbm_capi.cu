@@ -116,6 +116,14 @@ int rebuild_special(lbm_handle h)
     CK(cudaMemcpyAsync(&n, h->flag, sizeof n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->n_special = n;
+    if (n > 1) {
+        // the list is filled in atomic order; sorting it puts the z-words of a row and the rows of a plane next
+        // to each other again, so neighbouring warps share sectors and DRAM pages like in the dense kernels
+        std::vector<uint32_t> list(n);
+        CK(cudaMemcpy(list.data(), h->special_list, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        std::sort(list.begin(), list.end());
+        CK(cudaMemcpy(h->special_list, list.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
     h->dead_dirty = 2;
     return LBM_OK;
 }
@@ -193,7 +201,20 @@ int launch_range(lbm_handle h, unsigned phases, int x0, int x1, cudaStream_t s)
     c.moment_mode = h->cfg.moment_mode;
     c.eq64 = h->cfg.eq_precision == LBM_EQ_FP64;
     c.general = fast_path_ok(h, phases) ? 0 : 1;
-    CK(launch_step(c, p, s));
+    // On the handle's main stream the special-word kernel runs next to the general kernel on the side stream:
+    // the two touch disjoint cells of the output and only read the input, and the latency-bound special
+    // kernel fills bandwidth the general kernel leaves.
+    static const bool concurrent = [] { const char* e = getenv("LBM_SPECIAL_CONCURRENT"); return e ? atoi(e) != 0 : true; }();
+    const bool split = concurrent && c.general && h->n_special && s == h->stream;
+    if (split) {
+        CK(cudaEventRecord(h->ev_main, h->stream));
+        CK(cudaStreamWaitEvent(h->side, h->ev_main, 0));
+    }
+    CK(launch_step(c, p, s, split ? h->side : nullptr));
+    if (split) {
+        CK(cudaEventRecord(h->ev_side, h->side));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_side, 0));
+    }
     h->launches += 1 + ((c.general && h->n_special) ? 1 : 0);
     return LBM_OK;
 }
@@ -294,7 +315,13 @@ LBM_API int lbm_create(const lbm_config* cfg, lbm_handle* out)
     } while (0)
     CKB(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
-    CKB(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    {
+        // the side stream outranks the main one: its (smaller) kernels get SM slots as soon as blocks of the
+        // main kernel retire, instead of waiting for the main grid to drain
+        int lo_prio = 0, hi_prio = 0;
+        CKB(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        CKB(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi_prio));
+    }
     CKB(cudaEventCreate(&h->ev0));
     CKB(cudaEventCreate(&h->ev1));
     CKB(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));

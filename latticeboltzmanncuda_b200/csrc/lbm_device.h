@@ -99,7 +99,8 @@ struct LaunchCfg {
 };
 
 // launches (all asynchronous on `stream`)
-cudaError_t launch_step(const LaunchCfg& cfg, const StepParams& p, cudaStream_t stream);
+// stream_special (optional): the special-word kernel of the general path runs there, concurrently with the rest
+cudaError_t launch_step(const LaunchCfg& cfg, const StepParams& p, cudaStream_t stream, cudaStream_t stream_special);
 
 cudaError_t launch_fill_ghosts(float* f, const Geom& g, int q, const int bc[3], const float wall_u[6][3], bool include_x,
                                cudaStream_t stream, int* launches);

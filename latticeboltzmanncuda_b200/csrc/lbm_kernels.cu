@@ -371,8 +371,8 @@ __global__ void __launch_bounds__(128, MINB) step_general_kernel(const __grid_co
 
 // Special words (touching a solid cell, a wall ghost or a reflection target): one warp per entry of the
 // compact list built with the classification.  Same step as everywhere else plus boundary_path().
-template <int Q, int MOMENT, bool EQ64>
-__global__ void __launch_bounds__(128) step_special_kernel(const __grid_constant__ StepParams p)
+template <int Q, int MOMENT, bool EQ64, int MINB>
+__global__ void __launch_bounds__(128, MINB) step_special_kernel(const __grid_constant__ StepParams p)
 {
     const Geom& g = p.g;
     const unsigned lane = threadIdx.x & 31u;
@@ -458,7 +458,7 @@ cudaError_t launch_step_general_r(const StepParams& p, cudaStream_t stream)
 }
 
 template <int Q, int MOMENT, bool EQ64>
-cudaError_t launch_step_tasks(const StepParams& p, cudaStream_t stream)
+cudaError_t launch_step_tasks(const StepParams& p, cudaStream_t stream, cudaStream_t stream_special)
 {
     if (p.x1 <= p.x0) return cudaSuccess;
     static int rows = [] { const char* e = getenv("LBM_GENERAL_ROWS"); return e ? atoi(e) : 8; }();   // tuning knob
@@ -469,24 +469,28 @@ cudaError_t launch_step_tasks(const StepParams& p, cudaStream_t stream)
     if (e != cudaSuccess) return e;
     if (p.n_special > 0) {
         const long long blocks = (p.n_special + 3) / 4;
-        step_special_kernel<Q, MOMENT, EQ64><<<(unsigned)blocks, 128, 0, stream>>>(p);
+        static int minb = [] { const char* e = getenv("LBM_SPECIAL_MINB"); return e ? atoi(e) : 10; }();   // tuning knob
+        cudaStream_t ss = stream_special ? stream_special : stream;
+        if (minb >= 12)      step_special_kernel<Q, MOMENT, EQ64, 12><<<(unsigned)blocks, 128, 0, ss>>>(p);
+        else if (minb >= 10) step_special_kernel<Q, MOMENT, EQ64, 10><<<(unsigned)blocks, 128, 0, ss>>>(p);
+        else                 step_special_kernel<Q, MOMENT, EQ64, 8><<<(unsigned)blocks, 128, 0, ss>>>(p);
     }
     return cudaGetLastError();
 }
 
 template <int Q>
-cudaError_t launch_step_q(const LaunchCfg& c, const StepParams& p, cudaStream_t s)
+cudaError_t launch_step_q(const LaunchCfg& c, const StepParams& p, cudaStream_t s, cudaStream_t s2)
 {
     const int key = (c.moment_mode ? 4 : 0) | (c.eq64 ? 2 : 0) | (c.general ? 1 : 0);
     switch (key) {
         case 0: return launch_step_dense<Q, 0, false>(p, s);
-        case 1: return launch_step_tasks<Q, 0, false>(p, s);
+        case 1: return launch_step_tasks<Q, 0, false>(p, s, s2);
         case 2: return launch_step_dense<Q, 0, true>(p, s);
-        case 3: return launch_step_tasks<Q, 0, true>(p, s);
+        case 3: return launch_step_tasks<Q, 0, true>(p, s, s2);
         case 4: return launch_step_dense<Q, 1, false>(p, s);
-        case 5: return launch_step_tasks<Q, 1, false>(p, s);
+        case 5: return launch_step_tasks<Q, 1, false>(p, s, s2);
         case 6: return launch_step_dense<Q, 1, true>(p, s);
-        default: return launch_step_tasks<Q, 1, true>(p, s);
+        default: return launch_step_tasks<Q, 1, true>(p, s, s2);
     }
 }
 
@@ -783,10 +787,10 @@ __global__ void __launch_bounds__(256) mass_momentum_kernel(const float* __restr
 
 // ---- launch wrappers ---------------------------------------------------------------------------
 
-cudaError_t launch_step(const LaunchCfg& cfg, const StepParams& p, cudaStream_t stream)
+cudaError_t launch_step(const LaunchCfg& cfg, const StepParams& p, cudaStream_t stream, cudaStream_t stream_special)
 {
-    if (cfg.q == 27) return launch_step_q<27>(cfg, p, stream);
-    if (cfg.q == 19) return launch_step_q<19>(cfg, p, stream);
+    if (cfg.q == 27) return launch_step_q<27>(cfg, p, stream, stream_special);
+    if (cfg.q == 19) return launch_step_q<19>(cfg, p, stream, stream_special);
     return cudaErrorInvalidValue;
 }
 
