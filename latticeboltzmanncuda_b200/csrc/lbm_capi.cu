@@ -173,11 +173,11 @@ void fill_params(lbm_handle h, StepParams& p, unsigned phases, int x0, int x1)
     p.force_mode = h->cfg.force_mode;
     p.src_on = h->src_on;
     for (int a = 0; a < 3; ++a) { p.src_lo[a] = h->src_lo[a]; p.src_hi[a] = h->src_hi[a]; p.bc[a] = h->cfg.bc[a]; }
-    std::memcpy(p.wall_z, h->cfg.wall_u[4], sizeof p.wall_z);
-    p.wall_z_moving = 0;
-    for (int k = 4; k < 6; ++k)
+    std::memcpy(p.wall_u, h->cfg.wall_u, sizeof p.wall_u);
+    p.wall_moving = 0;
+    for (int k = 0; k < 6; ++k)
         for (int a = 0; a < 3; ++a)
-            if (h->cfg.wall_u[k][a] != 0.0f) p.wall_z_moving = 1;
+            if (h->cfg.wall_u[k][a] != 0.0f) p.wall_moving = 1;
     std::memcpy(p.src_f, h->src_f, sizeof p.src_f);
 }
 
@@ -235,8 +235,36 @@ int fill_ghosts(lbm_handle h, bool include_x)
     return LBM_OK;
 }
 
+void fill_inplace(lbm_handle h, InplaceParams& ip)
+{
+    ip.f = h->buf[0];
+    ip.g = h->g;
+    ip.tau = h->cfg.tau;
+    ip.inv_tau = 1.0f / h->cfg.tau;
+    ip.parity = h->aa_parity;
+    for (int a = 0; a < 3; ++a) ip.bc[a] = h->cfg.bc[a];
+    std::memcpy(ip.wall_u, h->cfg.wall_u, sizeof ip.wall_u);
+}
+
+int inplace_only(lbm_handle h, const char* what)
+{
+    if (h->inplace) return fail(LBM_ERR_UNSUPPORTED, "%s is not available on the in-place engine (all-fluid lattices, fused steps, SoA transfers)", what);
+    return LBM_OK;
+}
+
 int one_step(lbm_handle h, unsigned phases)
 {
+    if (h->inplace) {
+        const bool source_noop = !(phases & PH_SOURCE) || !h->src_on;
+        if (!(phases & PH_STREAM) || !(phases & PH_COLLIDE) || !source_noop)
+            return fail(LBM_ERR_UNSUPPORTED, "the in-place engine runs fused stream + collide steps only");
+        InplaceParams ip;
+        fill_inplace(h, ip);
+        CK(launch_inplace_step(ip, h->cfg.q, h->cfg.moment_mode, h->cfg.eq_precision == LBM_EQ_FP64, h->stream));
+        h->launches += (h->aa_parity == 0) ? 2 : 1;
+        h->aa_parity ^= 1;
+        return LBM_OK;
+    }
     if (h->pending_commit) return fail(LBM_ERR_STATE, "lbm_step_range in flight: call lbm_step_commit first");
     if (phases & PH_STREAM) {
         int rc = fill_ghosts(h, true);
@@ -291,8 +319,12 @@ LBM_API int lbm_create(const lbm_config* cfg, lbm_handle* out)
         if (cfg->bc[a] < 0 || cfg->bc[a] > 3) return fail(LBM_ERR_INVALID, "bad bc");
         if (cfg->bc[a] == LBM_BC_HALO && a != 0) return fail(LBM_ERR_INVALID, "LBM_BC_HALO is for the x axis only");
     }
-    if (cfg->engine != LBM_ENGINE_AUTO && cfg->engine != LBM_ENGINE_PULL2)
+    if (cfg->engine != LBM_ENGINE_AUTO && cfg->engine != LBM_ENGINE_PULL2 && cfg->engine != LBM_ENGINE_INPLACE)
         return fail(LBM_ERR_UNSUPPORTED, "engine %d is not built in this version", cfg->engine);
+    if (cfg->engine == LBM_ENGINE_INPLACE)
+        for (int a = 0; a < 3; ++a)
+            if (cfg->bc[a] != LBM_BC_PERIODIC && cfg->bc[a] != LBM_BC_WALL)
+                return fail(LBM_ERR_UNSUPPORTED, "the in-place engine takes periodic or wall edges only");
     const Geom g = make_geom(cfg->nx, cfg->ny, cfg->nz);
     if (g.np >= (1ll << 32)) return fail(LBM_ERR_INVALID, "more than 2^32 padded cells per slab");
 
@@ -306,6 +338,7 @@ LBM_API int lbm_create(const lbm_config* cfg, lbm_handle* out)
     h->cfg.device = dev;
     h->g = g;
     h->device = dev;
+    h->inplace = cfg->engine == LBM_ENGINE_INPLACE;
     auto bail = [&](int rc) { lbm_destroy(h); return rc; };
 #define CKB(call)                                                                          \
     do {                                                                                   \
@@ -326,7 +359,7 @@ LBM_API int lbm_create(const lbm_config* cfg, lbm_handle* out)
     CKB(cudaEventCreate(&h->ev1));
     CKB(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
     CKB(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < (h->inplace ? 1 : 2); ++b) {
         CKB(cudaMalloc(&h->buf[b], h->state_bytes()));
         CKB(cudaMemsetAsync(h->buf[b], 0, h->state_bytes(), h->stream));
     }
@@ -404,7 +437,7 @@ LBM_API int lbm_get_layout(lbm_handle h, lbm_layout* o)
     o->xp = h->g.xp; o->yp = h->g.yp; o->zp = h->g.zp; o->pad_z = PAD_Z;
     o->plane = h->g.plane; o->pop_stride = h->g.np;
     o->state_bytes = (int64_t)h->state_bytes();
-    o->n_buffers = 2;
+    o->n_buffers = h->inplace ? 1 : 2;
     return LBM_OK;
 }
 
@@ -414,6 +447,7 @@ LBM_API int lbm_upload_aos(lbm_handle h, const void* cells, size_t count)
 {
     int rc = use(h);
     if (rc) return rc;
+    if ((rc = inplace_only(h, "lbm_upload_aos"))) return rc;
     const Geom& g = h->g;
     const size_t n = (size_t)g.nx * g.ny * g.nz;
     if (!cells || count != n) return fail(LBM_ERR_INVALID, "upload_aos: expected %zu records, got %zu", n, count);
@@ -437,6 +471,7 @@ LBM_API int lbm_download_aos(lbm_handle h, void* cells, size_t count)
 {
     int rc = use(h);
     if (rc) return rc;
+    if ((rc = inplace_only(h, "lbm_download_aos"))) return rc;
     const Geom& g = h->g;
     const size_t n = (size_t)g.nx * g.ny * g.nz;
     if (!cells || count != n) return fail(LBM_ERR_INVALID, "download_aos: expected %zu records, got %zu", n, count);
@@ -474,7 +509,8 @@ LBM_API int lbm_upload_f_soa(lbm_handle h, const float* f)
             float* st = (float*)((char*)h->staging + (size_t)slot * (STAGING_BYTES / 2));
             cudaStream_t s = slot ? h->side : h->stream;
             CK(cudaMemcpyAsync(st, src + (size_t)x0 * g.ny * g.nz, (size_t)nxc * per_plane, cudaMemcpyHostToDevice, s));
-            CK(launch_scatter_dense(st, h->buf[h->cur] + (size_t)q * g.np, g, x0, nxc, s));
+            if (h->inplace) CK(launch_inplace_scatter(st, h->buf[0], g, q, x0, nxc, s));
+            else CK(launch_scatter_dense(st, h->buf[h->cur] + (size_t)q * g.np, g, x0, nxc, s));
             slot ^= 1;
             if (slot == 0) { CK(cudaStreamSynchronize(h->stream)); CK(cudaStreamSynchronize(h->side)); }
         }
@@ -482,6 +518,7 @@ LBM_API int lbm_upload_f_soa(lbm_handle h, const float* f)
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaStreamSynchronize(h->side));
     h->dead_dirty = 2;
+    h->aa_parity = 0;
     return LBM_OK;
 }
 
@@ -500,7 +537,13 @@ LBM_API int lbm_download_f_soa(lbm_handle h, float* f)
         float* dst = f + (size_t)q * g.nx * g.ny * g.nz;
         for (int x0 = 0; x0 < g.nx; x0 += chunk) {
             const int nxc = std::min(chunk, g.nx - x0);
-            CK(launch_gather_dense((float*)h->staging, h->buf[h->cur] + (size_t)q * g.np, g, x0, nxc, h->stream));
+            if (h->inplace) {
+                InplaceParams ip;
+                fill_inplace(h, ip);
+                CK(launch_inplace_gather(ip, h->cfg.q, (float*)h->staging, q, x0, nxc, h->stream));
+            } else {
+                CK(launch_gather_dense((float*)h->staging, h->buf[h->cur] + (size_t)q * g.np, g, x0, nxc, h->stream));
+            }
             CK(cudaMemcpyAsync(dst + (size_t)x0 * g.ny * g.nz, h->staging, (size_t)nxc * per_plane, cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
         }
@@ -512,6 +555,8 @@ LBM_API int lbm_set_solid_mask(lbm_handle h, const uint8_t* solid, int x_ghost_p
 {
     int rc = use(h);
     if (rc) return rc;
+    if (solid && (rc = inplace_only(h, "lbm_set_solid_mask"))) return rc;
+    if (h->inplace) return LBM_OK;
     const Geom& g = h->g;
     const size_t per = (size_t)g.ny * g.nz;
     const size_t n = per * (size_t)g.nx;
@@ -545,6 +590,7 @@ LBM_API int lbm_set_reflection_table(lbm_handle h, const void* tables, const int
 {
     int rc = use(h);
     if (rc) return rc;
+    if ((rc = inplace_only(h, "lbm_set_reflection_table"))) return rc;
     if (n < 0 || (n > 0 && (!tables || !cell_index))) return fail(LBM_ERR_INVALID, "bad reflection table arguments");
     if (h->cfg.bc[0] == LBM_BC_HALO && n > 0)
         return fail(LBM_ERR_UNSUPPORTED, "table reflection is not available on halo (slab) handles yet");
@@ -630,6 +676,7 @@ LBM_API int lbm_set_source(lbm_handle h, int kind, const int32_t lo[3], const in
     if (!h) return fail(LBM_ERR_INVALID, "null handle");
     if (kind == LBM_SOURCE_NONE) { h->src_on = 0; return LBM_OK; }
     if (kind != LBM_SOURCE_BOX || !lo || !hi || !f) return fail(LBM_ERR_INVALID, "bad source arguments");
+    if (h->inplace) return inplace_only(h, "lbm_set_source");
     h->src_on = 1;
     for (int a = 0; a < 3; ++a) { h->src_lo[a] = lo[a]; h->src_hi[a] = hi[a]; }
     for (int i = 0; i < 27; ++i) h->src_f[i] = (i < h->cfg.q) ? f[i] : 0.0f;
@@ -711,7 +758,14 @@ LBM_API int lbm_moments(lbm_handle h, float* rho, float* ux, float* uy, float* u
     const size_t n = (size_t)g.nx * g.ny * g.nz;
     float* dev = nullptr;
     CK(cudaMalloc(&dev, 4 * n * sizeof(float)));
-    cudaError_t e = launch_moments(h->buf[h->cur], g, h->cfg.q, h->cfg.moment_mode, dev, dev + n, dev + 2 * n, dev + 3 * n, h->stream);
+    cudaError_t e;
+    if (h->inplace) {
+        InplaceParams ip;
+        fill_inplace(h, ip);
+        e = launch_inplace_moments(ip, h->cfg.q, h->cfg.moment_mode, dev, dev + n, dev + 2 * n, dev + 3 * n, h->stream);
+    } else {
+        e = launch_moments(h->buf[h->cur], g, h->cfg.q, h->cfg.moment_mode, dev, dev + n, dev + 2 * n, dev + 3 * n, h->stream);
+    }
     float* outs[4] = {rho, ux, uy, uz};
     for (int k = 0; k < 4 && e == cudaSuccess; ++k)
         if (outs[k]) e = cudaMemcpyAsync(outs[k], dev + (size_t)k * n, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
@@ -726,7 +780,13 @@ static int mass_momentum(lbm_handle h, double out4[4])
     int rc = use(h);
     if (rc) return rc;
     CK(cudaMemsetAsync(h->diag, 0, 4 * sizeof(double), h->stream));
-    CK(launch_mass_momentum(h->buf[h->cur], h->g, h->cfg.q, h->diag, h->stream));
+    if (h->inplace) {
+        InplaceParams ip;
+        fill_inplace(h, ip);
+        CK(launch_inplace_mass(ip, h->cfg.q, h->diag, h->stream));
+    } else {
+        CK(launch_mass_momentum(h->buf[h->cur], h->g, h->cfg.q, h->diag, h->stream));
+    }
     CK(cudaMemcpyAsync(out4, h->diag, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return LBM_OK;
@@ -766,12 +826,14 @@ static int plane_ptr(lbm_handle h, float* base, int q, int xp, void** dev_ptr, s
 LBM_API int lbm_plane_ptr(lbm_handle h, int q, int xp, void** dev_ptr, size_t* bytes)
 {
     if (!h) return fail(LBM_ERR_INVALID, "null handle");
+    if (h->inplace) return inplace_only(h, "lbm_plane_ptr");
     return plane_ptr(h, h->buf[h->cur], q, xp, dev_ptr, bytes);
 }
 
 LBM_API int lbm_next_plane_ptr(lbm_handle h, int q, int xp, void** dev_ptr, size_t* bytes)
 {
     if (!h) return fail(LBM_ERR_INVALID, "null handle");
+    if (h->inplace) return inplace_only(h, "lbm_next_plane_ptr");
     return plane_ptr(h, h->buf[h->cur ^ 1], q, xp, dev_ptr, bytes);
 }
 
@@ -813,6 +875,7 @@ LBM_API int lbm_step_range(lbm_handle h, unsigned phases, int x0, int x1, int on
 {
     int rc = use(h);
     if (rc) return rc;
+    if ((rc = inplace_only(h, "lbm_step_range"))) return rc;
     if (x0 < 0 || x1 > h->g.nx || x0 > x1 || (phases & ~15u) || phases == 0) return fail(LBM_ERR_INVALID, "bad range");
     if (on_side_stream) {
         // the side stream starts after everything queued so far on the main stream

@@ -87,9 +87,25 @@ struct StepParams {
     int   src_lo[3], src_hi[3];
     float src_f[27];
     int   bc[3];
-    float wall_z[2][3];       // velocity of the z walls (x and y walls are ghost fills)
-    int   wall_z_moving;
+    float wall_u[6][3];       // wall velocities (the z walls are applied at pull time, x and y walls by ghost fills)
+    int   wall_moving;
 };
+
+// single-buffer (AA pattern) engine, lbm_inplace.cu
+struct InplaceParams {
+    float* f;
+    Geom  g;
+    float tau, inv_tau;
+    int   parity;             // 0: f*_i(x) parked in A[inv(i)][x] (next step pulls and pushes); 1: pushed to A[i][x + c_i]
+    int   bc[3];              // 1 periodic, 2 wall
+    float wall_u[6][3];
+};
+
+cudaError_t launch_inplace_step(const InplaceParams& p, int q, int moment, int eq64, cudaStream_t stream);
+cudaError_t launch_inplace_scatter(const float* dense, float* f, const Geom& g, int q_index, int x0, int nxc, cudaStream_t stream);
+cudaError_t launch_inplace_gather(const InplaceParams& p, int q, float* dense, int q_index, int x0, int nxc, cudaStream_t stream);
+cudaError_t launch_inplace_moments(const InplaceParams& p, int q, int moment_mode, float* rho, float* ux, float* uy, float* uz, cudaStream_t stream);
+cudaError_t launch_inplace_mass(const InplaceParams& p, int q, double* out4, cudaStream_t stream);
 
 struct LaunchCfg {
     int q;

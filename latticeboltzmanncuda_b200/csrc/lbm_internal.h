@@ -15,6 +15,8 @@ struct lbm_lattice_s {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_side = nullptr, ev_main = nullptr;
     float* buf[2] = {nullptr, nullptr};
     int cur = 0;
+    bool inplace = false;            // single-buffer AA engine: only buf[0] exists
+    int aa_parity = 0;
     bool pending_commit = false;
     unsigned pending_phases = 0;
     uint32_t* solid = nullptr;       // padded bit mask

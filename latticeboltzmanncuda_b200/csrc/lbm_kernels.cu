@@ -18,70 +18,7 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-// ---- collision ---------------------------------------------------------------------------
-
-// Reference arithmetic (SimCalcFuncs.cu:100-155): fp32 moments accumulated in index order,
-// equilibrium promoted to double by the double literals, narrowed to float, float subtract,
-// float divide by the timescale.  Expression shapes are kept so that nvcc contracts them the
-// way it contracts the reference's.
-template <int Q, int MOMENT>
-__device__ __forceinline__ void collide_fp64(float (&f)[Q], float timescale)
-{
-    float density = 0.0f, ux = 0.0f, uy = 0.0f, uz = 0.0f;
-#pragma unroll
-    for (int i = 0; i < Q; ++i) {
-        const float s = (MOMENT == 0) ? dir_split(i) : 1.0f;
-        density += f[i];
-        if (dir_c(i, 0) != 0) ux += f[i] * (float)dir_c(i, 0) * s;
-        if (dir_c(i, 1) != 0) uy += f[i] * (float)dir_c(i, 1) * s;
-        if (dir_c(i, 2) != 0) uz += f[i] * (float)dir_c(i, 2) * s;
-    }
-    if (density != 0.0) {
-        ux /= density; uy /= density; uz /= density;
-    }
-#pragma unroll
-    for (int i = 0; i < Q; ++i) {
-        float common_term = (((float)dir_c(i, 0) * ux) + ((float)dir_c(i, 1) * uy) + ((float)dir_c(i, 2) * uz));
-        float eq = dir_weight<Q>(i) * density *
-                   (1 + (3.0 * common_term) + (4.5 * common_term * common_term) - (1.5 * ((ux * ux) + (uy * uy) + (uz * uz))));
-        f[i] = f[i] + (eq - f[i]) / timescale;
-    }
-}
-
-// Throughput arithmetic: all fp32, opposite directions share the even part of the
-// equilibrium, relaxation by multiplication with 1/tau.
-template <int Q, int MOMENT>
-__device__ __forceinline__ void collide_fp32(float (&f)[Q], float inv_tau)
-{
-    float rho = f[0], mx = 0.0f, my = 0.0f, mz = 0.0f;
-#pragma unroll
-    for (int i = 1; i < Q; ++i) {
-        const float s = (MOMENT == 0) ? dir_split(i) : 1.0f;
-        rho += f[i];
-        if (dir_c(i, 0) != 0) mx = fmaf(f[i], (float)dir_c(i, 0) * s, mx);
-        if (dir_c(i, 1) != 0) my = fmaf(f[i], (float)dir_c(i, 1) * s, my);
-        if (dir_c(i, 2) != 0) mz = fmaf(f[i], (float)dir_c(i, 2) * s, mz);
-    }
-    const float inv_rho = (rho != 0.0f) ? 1.0f / rho : 1.0f;
-    const float ux = mx * inv_rho, uy = my * inv_rho, uz = mz * inv_rho;
-    const float base = fmaf(-1.5f, fmaf(ux, ux, fmaf(uy, uy, uz * uz)), 1.0f);
-    float moving = 0.0f;                               // sum of the equilibria of all moving populations
-#pragma unroll
-    for (int i = 1; i < Q; ++i) {
-        if (dir_inv(i) < i) continue;                  // handle each +/- pair once
-        const int j = dir_inv(i);
-        const float cu = (float)dir_c(i, 0) * ux + (float)dir_c(i, 1) * uy + (float)dir_c(i, 2) * uz;
-        const float wr = (float)dir_weight<Q>(i) * rho;
-        const float even = wr * fmaf(4.5f * cu, cu, base);
-        const float odd = wr * 3.0f * cu;
-        moving = fmaf(2.0f, even, moving);
-        f[i] = fmaf(inv_tau, (even + odd) - f[i], f[i]);
-        f[j] = fmaf(inv_tau, (even - odd) - f[j], f[j]);
-    }
-    // the rest equilibrium is what is left of rho: sum_i feq_i == rho holds to round-off instead of
-    // drifting with the rounding of the fp32 weights (their sum is not exactly 1)
-    f[0] = fmaf(inv_tau, (rho - moving) - f[0], f[0]);
-}
+#include "lbm_collide.inl"
 
 // velocity set for run-time indices (link lists); compile-time indices use dir_c()
 __constant__ int8_t c_dir[27][3] = {
@@ -236,8 +173,8 @@ __device__ __forceinline__ bool boundary_path(const StepParams& p, float (&f)[Q]
 //                6 w_i (c_i . u_wall) for a moving wall (rho_wall = 1).
 // edge_word is warp-uniform: only the first and last word of a row take the second branch.
 template <int Q>
-__device__ __forceinline__ void pull_populations(const StepParams& p, const float* __restrict__ fin, int z, bool edge_word,
-                                                 float (&f)[Q])
+__device__ __forceinline__ void pull_populations(const StepParams& p, const float* __restrict__ fin, int x, int y, int z,
+                                                 bool edge_word, float (&f)[Q])
 {
     const Geom& g = p.g;
     if (!edge_word || p.bc[2] == 0) {
@@ -256,8 +193,12 @@ __device__ __forceinline__ void pull_populations(const StepParams& p, const floa
         long long a = off;
         if (outside) a = wall ? (long long)dir_inv(i) * g.np : off + (dir_c(i, 2) > 0 ? g.nz : -g.nz);
         float v = fin[a];
-        if (outside && wall && p.wall_z_moving) {
-            const float* u = p.wall_z[dir_c(i, 2) > 0 ? 0 : 1];
+        if (outside && wall && p.wall_moving) {
+            // where walls meet, the one named first in x, y, z order supplies the velocity
+            const int sx = x - dir_c(i, 0), sy = y - dir_c(i, 1);
+            const float* u = p.wall_u[4 + (dir_c(i, 2) > 0 ? 0 : 1)];
+            if (p.bc[0] == 2 && (sx < 0 || sx >= g.nx)) u = p.wall_u[sx < 0 ? 0 : 1];
+            else if (p.bc[1] == 2 && (sy < 0 || sy >= g.ny)) u = p.wall_u[2 + (sy < 0 ? 0 : 1)];
             v += 6.0f * (float)dir_weight<Q>(i) * ((float)dir_c(i, 0) * u[0] + (float)dir_c(i, 1) * u[1] + (float)dir_c(i, 2) * u[2]);
         }
         f[i] = v;
@@ -279,7 +220,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
     const long long idx = ((long long)(x + 1) * g.yp + (y + 1)) * g.zp + (z + PAD_Z);
     const float* __restrict__ fin = p.fin + idx;
     float f[Q];
-    pull_populations<Q>(p, fin, z, false, f);      // open z edge: the ghost columns hold zeros
+    pull_populations<Q>(p, fin, x, y, z, false, f);      // open z edge: the ghost columns hold zeros
     // ---- BGK relaxation (SimCalcFuncs.cu:98-156)
     if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
     else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
@@ -342,7 +283,7 @@ __global__ void __launch_bounds__(128, MINB) step_general_kernel(const __grid_co
         } else {
             const float* __restrict__ fin = p.fin + idx;
             if (do_stream) {
-                pull_populations<Q>(p, fin, z, wi == 0 || wi == wcount - 1, f);
+                pull_populations<Q>(p, fin, x, y, z, wi == 0 || wi == wcount - 1, f);
             } else {
 #pragma unroll
                 for (int i = 0; i < Q; ++i) f[i] = fin[(long long)i * g.np];
@@ -390,7 +331,7 @@ __global__ void __launch_bounds__(128, MINB) step_special_kernel(const __grid_co
     const float* __restrict__ fin = p.fin + idx;
     float f[Q];
     if (do_stream) {
-        pull_populations<Q>(p, fin, z, w == PAD_Z / 32 || w == PAD_Z / 32 + ((g.nz + 31) >> 5) - 1, f);
+        pull_populations<Q>(p, fin, x, y, z, w == PAD_Z / 32 || w == PAD_Z / 32 + ((g.nz + 31) >> 5) - 1, f);
     } else {
 #pragma unroll
         for (int i = 0; i < Q; ++i) f[i] = fin[(long long)i * g.np];

@@ -422,3 +422,72 @@ def test_bad_arguments_are_reported():
         lat.load_data(O.new_cells(2, 2, 2))
     with pytest.raises(lb.LbmError):
         lat.set_reflection_tables(np.zeros(1, O.REFLECTION_VALUES), [4 * 4 * 4 + 1])
+
+
+# ---- single-buffer (AA pattern) engine ----------------------------------------------------------------------
+
+@pytest.mark.parametrize("q", [19, 27])
+@pytest.mark.parametrize("eq", [lb.EQ_FP32, lb.EQ_FP64])
+@pytest.mark.parametrize("bc", [(1, 1, 1), (2, 2, 2), (1, 2, 1), (2, 1, 2)])
+@pytest.mark.parametrize("steps", [1, 2, 7, 12])
+def test_inplace_engine_equals_two_buffer_engine(q, eq, bc, steps):
+    """the in-place engine holds one copy of the populations; after any number of steps (odd or even, i.e. in
+    either of its two storage forms) the state it reports is the two-buffer engine's, and the oracle's"""
+    X, Y, Z = 9, 6, 37
+    f = soa_state(q, X, Y, Z, 53)
+    wall_u = np.zeros((6, 3), np.float32)
+    wall_u[3] = (0.03, 0.0, 0.01)          # moving y-high wall (used when y is a wall axis)
+    wall_u[4] = (0.0, 0.02, 0.0)           # moving z-low wall
+    kw = dict(tau=0.7, q=q, bc=bc, wall_u=wall_u, moment_mode=lb.MOMENT_STANDARD, eq_precision=eq,
+              boundary_mode=lb.BOUNDARY_BOUNCE_BACK)
+    ref = make(X, Y, Z, **kw)
+    ref.load_populations(f)
+    ref.step(steps)
+    want = ref.retrieve_populations()
+    lat = make(X, Y, Z, engine=lb.ENGINE_INPLACE, **kw)
+    assert lat.layout().n_buffers == 1
+    lat.load_populations(f)
+    lat.step(steps)
+    got = lat.retrieve_populations()
+    assert rel_err(got, want) <= 2e-6
+    orc = O.step_soa(f, X, Y, Z, q, 0.7, bc=bc, wall_u=wall_u, moment=O.MOMENT_STANDARD, eq64=(eq == lb.EQ_FP64), steps=steps)
+    assert rel_err(got, orc) <= REL
+    assert lat.mass() == pytest.approx(ref.mass(), rel=1e-6)
+    assert np.allclose(lat.momentum(), ref.momentum(), atol=1e-4)
+    for a, b in zip(lat.moments(), ref.moments()):
+        assert np.allclose(a, b, rtol=1e-4, atol=1e-6)
+
+
+def test_inplace_engine_refuses_what_it_cannot_do():
+    with pytest.raises(lb.LbmError):
+        make(8, 8, 8, engine=lb.ENGINE_INPLACE)                          # zero-inflow edges (the default)
+    lat = make(8, 8, 8, engine=lb.ENGINE_INPLACE, bc=(1, 1, 1))
+    with pytest.raises(lb.LbmError):
+        lat.set_solid_mask(np.ones((8, 8, 8), np.uint8))
+    with pytest.raises(lb.LbmError):
+        lat.simulateStreaming()                                          # fused steps only
+    with pytest.raises(lb.LbmError):
+        lat.load_data(O.new_cells(8, 8, 8))
+
+
+def test_inplace_taylor_green_half_the_memory():
+    n = 128
+    tau, u0 = 0.6, 0.04
+    k = 2 * np.pi / n
+    x = np.arange(n)[:, None, None]; y = np.arange(n)[None, :, None]
+    ux = (u0 * np.sin(k * x) * np.cos(k * y) * np.ones((1, 1, n))); uy = (-u0 * np.cos(k * x) * np.sin(k * y) * np.ones((1, 1, n)))
+    c = O.DIRECTIONS[:19].astype(np.float64); w = O.weights(19)
+    cu = c[:, 0, None, None, None] * ux + c[:, 1, None, None, None] * uy
+    f = (w[:, None, None, None] * (1 + 3 * cu + 4.5 * cu ** 2 - 1.5 * (ux ** 2 + uy ** 2))).astype(np.float32)
+    kw = dict(tau=tau, q=19, bc=(1, 1, 1), moment_mode=lb.MOMENT_STANDARD, eq_precision=lb.EQ_FP32, boundary_mode=lb.BOUNDARY_BOUNCE_BACK)
+    two = make(n, n, n, **kw)
+    one = make(n, n, n, engine=lb.ENGINE_INPLACE, **kw)
+    assert one.layout().n_buffers * one.layout().state_bytes * 2 == two.layout().n_buffers * two.layout().state_bytes
+    one.load_populations(f)
+    m0 = one.mass()
+    one.step(201)
+    r, a, b, _ = one.moments()
+    e1 = float((r.astype(np.float64) * (a.astype(np.float64) ** 2 + b.astype(np.float64) ** 2)).sum())
+    e0 = float((ux ** 2 + uy ** 2).sum())
+    assert e1 / e0 == pytest.approx(np.exp(-2.0 * (tau - 0.5) / 3.0 * 2 * k * k * 201), rel=0.02)
+    assert one.mass() == pytest.approx(m0, rel=1e-6)

@@ -55,6 +55,10 @@ if which in ("parts",):
     run("q19 general, walls y/z only", 19, lb.EQ_FP32, (Z, W, W), BB, False, False)
     run("q19 general, walls y only", 19, lb.EQ_FP32, (Z, W, Z), BB, False, False)
     run("q19 general, obstacle only", 19, lb.EQ_FP32, (Z, Z, Z), BB, True, False)
+if which in ("all", "inplace"):
+    run("q19 fp32 IN-PLACE periodic xyz (1 buffer)", 19, lb.EQ_FP32, (P, P, P), BB, False, False, engine=lb.ENGINE_INPLACE)
+    run("q19 fp32 IN-PLACE walls xyz (1 buffer)", 19, lb.EQ_FP32, (W, W, W), BB, False, False, engine=lb.ENGINE_INPLACE)
+    run("q27 fp32 IN-PLACE periodic xyz (1 buffer)", 27, lb.EQ_FP32, (P, P, P), BB, False, False, engine=lb.ENGINE_INPLACE)
 if which in ("all",):
     run("q19 fp32 periodic xyz (3 ghost fills)", 19, lb.EQ_FP32, (P, P, P), BB, False, False)
     run("q27 fp32 fast", 27, lb.EQ_FP32, (Z, Z, Z), BB, False, False)
