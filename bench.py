@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--q", type=int, default=19, choices=[19, 27])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the all-fluid dense / in-place side measurements")
     ap.add_argument("--ref-size", type=int, default=int(os.environ.get("LBM_REF_SIZE", "256")))
     return ap.parse_args()
 
@@ -250,6 +251,7 @@ def run_ours(args):
     per_gpu_gbs = (live_total / world) * args.steps * b_alg / (ms * 1e-3) / 1e9
     mass = lat.mass()
     finite = bool(np.isfinite(mass))
+    state_gb = lat.layout().state_bytes / 1e9
 
     # ---- end to end through the host API: upload (pinned) + K x (step + force read-back) + moments download
     e2e = None
@@ -280,6 +282,26 @@ def run_ours(args):
                "what": "lbm_upload_f_soa from pinned host + %d x (lbm_set_source, lbm_step, lbm_get_force) + lbm_moments to pinned host" % args.steps,
                "seconds": dt}
 
+    # ---- the two dense engines on an all-fluid lattice of the same size (context for the roofline; N = 1 only)
+    extra = None
+    if world == 1 and not args.no_extra:
+        extra = {}
+        lat.close()
+        for name, engine, bc in (("dense_two_buffer", lb.ENGINE_PULL2, (lb.BC_PERIODIC, lb.BC_PERIODIC, lb.BC_ZERO_INFLOW)),
+                                 ("in_place_single_buffer", lb.ENGINE_INPLACE, (lb.BC_PERIODIC,) * 3)):
+            l2 = lb.Lattice(nx, gy, gz, None, None, lb.FluidData(1.0, tau), 1.0 / gx, q=q, bc=bc, moment_mode=lb.MOMENT_STANDARD,
+                            eq_precision=lb.EQ_FP32, boundary_mode=lb.BOUNDARY_BOUNCE_BACK, device=local, engine=engine)
+            for i in range(q):
+                hf[i] = w[i]
+            l2.load_populations(hf)
+            l2.step(4)
+            l2.sync()
+            ms2, _ = l2.step_timed(40)
+            gbs2 = cells_total * 40 * b_alg / (ms2 * 1e-3) / 1e9
+            extra[name] = {"mlups": cells_total * 40 / (ms2 * 1e-3) / 1e6, "gbs": gbs2, "frac": gbs2 / peak,
+                           "state_gb": l2.layout().state_bytes * l2.layout().n_buffers / 1e9}
+            l2.close()
+
     out = None
     if rank == 0:
         traffic = None
@@ -297,7 +319,7 @@ def run_ours(args):
                                    "half-way bounce-back, periodic in x, walls in y/z, initial u=(0.04,0,0), plane source at x=0; "
                                    "%d x-slab(s) of %dx%dx%d" % (gx, gy, gz, q, world, nx, gy, gz),
                        "cells_per_gpu": nx * gy * gz, "tau": tau, "engine": "two-buffer fused pull, classified 32-cell words",
-                       "l2": "state per GPU %.1f GB >> 126 MB L2, no flush needed" % (lat.layout().state_bytes / 1e9)},
+                       "l2": "state per GPU %.1f GB >> 126 MB L2, no flush needed" % state_gb},
             "gpu_launches": int(launches),
             "live_cells": live_total, "mflups": live_total * args.steps / (ms * 1e-3) / 1e6,
             "hbm_gbs_per_gpu": per_gpu_gbs,
@@ -313,6 +335,8 @@ def run_ours(args):
         }
         if e2e:
             out["e2e"] = e2e
+        if extra:
+            out["all_fluid_engines"] = extra
     if world > 1:
         dist.barrier()
     if rank == 0 and not args.no_cpu and world == 1:
