@@ -490,33 +490,39 @@ LBM_API int lbm_download_aos(lbm_handle h, void* cells, size_t count)
     return LBM_OK;
 }
 
+// dense [nx][ny][nz] block of one population <-> its padded device array, as one strided DMA transfer
+static cudaError_t copy_population(lbm_handle h, float* dev_pop, float* host_pop, bool to_device, cudaStream_t s)
+{
+    const Geom& g = h->g;
+    cudaMemcpy3DParms p;
+    std::memset(&p, 0, sizeof p);
+    cudaPitchedPtr host = make_cudaPitchedPtr(host_pop, (size_t)g.nz * sizeof(float), (size_t)g.nz * sizeof(float), (size_t)g.ny);
+    cudaPitchedPtr dev = make_cudaPitchedPtr(dev_pop, (size_t)g.zp * sizeof(float), (size_t)g.zp * sizeof(float), (size_t)g.yp);
+    const cudaPos interior = make_cudaPos((size_t)PAD_Z * sizeof(float), 1, 1);
+    p.srcPtr = to_device ? host : dev;
+    p.dstPtr = to_device ? dev : host;
+    p.srcPos = to_device ? make_cudaPos(0, 0, 0) : interior;
+    p.dstPos = to_device ? interior : make_cudaPos(0, 0, 0);
+    p.extent = make_cudaExtent((size_t)g.nz * sizeof(float), (size_t)g.ny, (size_t)g.nx);
+    p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    return cudaMemcpy3DAsync(&p, s);
+}
+
 LBM_API int lbm_upload_f_soa(lbm_handle h, const float* f)
 {
     int rc = use(h);
     if (rc) return rc;
     if (!f) return fail(LBM_ERR_INVALID, "null buffer");
-    if ((rc = ensure_staging(h))) return rc;
     const Geom& g = h->g;
-    const size_t per_plane = (size_t)g.ny * g.nz * sizeof(float);
-    if (per_plane > STAGING_BYTES) return fail(LBM_ERR_UNSUPPORTED, "one x-plane exceeds the staging buffer");
-    const int chunk = (int)std::max<size_t>(1, STAGING_BYTES / 2 / per_plane);
-    // two half-buffers alternate so that the H2D copy of a chunk overlaps the scatter of the previous one
-    int slot = 0;
+    CK(cudaStreamSynchronize(h->side));
+    // one strided host-to-device transfer per population, straight into the padded layout (no staging, no
+    // scatter kernel); the in-place engine parks population i in the slot of its opposite (lbm_inplace.cu)
     for (int q = 0; q < h->cfg.q; ++q) {
-        const float* src = f + (size_t)q * g.nx * g.ny * g.nz;
-        for (int x0 = 0; x0 < g.nx; x0 += chunk) {
-            const int nxc = std::min(chunk, g.nx - x0);
-            float* st = (float*)((char*)h->staging + (size_t)slot * (STAGING_BYTES / 2));
-            cudaStream_t s = slot ? h->side : h->stream;
-            CK(cudaMemcpyAsync(st, src + (size_t)x0 * g.ny * g.nz, (size_t)nxc * per_plane, cudaMemcpyHostToDevice, s));
-            if (h->inplace) CK(launch_inplace_scatter(st, h->buf[0], g, q, x0, nxc, s));
-            else CK(launch_scatter_dense(st, h->buf[h->cur] + (size_t)q * g.np, g, x0, nxc, s));
-            slot ^= 1;
-            if (slot == 0) { CK(cudaStreamSynchronize(h->stream)); CK(cudaStreamSynchronize(h->side)); }
-        }
+        float* src = const_cast<float*>(f) + (size_t)q * g.nx * g.ny * g.nz;
+        float* dst = h->inplace ? h->buf[0] + (size_t)dir_inv(q) * g.np : h->buf[h->cur] + (size_t)q * g.np;
+        CK(copy_population(h, dst, src, true, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaStreamSynchronize(h->side));
     h->dead_dirty = 2;
     h->aa_parity = 0;
     return LBM_OK;
@@ -533,6 +539,12 @@ LBM_API int lbm_download_f_soa(lbm_handle h, float* f)
     if (per_plane > STAGING_BYTES) return fail(LBM_ERR_UNSUPPORTED, "one x-plane exceeds the staging buffer");
     const int chunk = (int)std::max<size_t>(1, STAGING_BYTES / per_plane);
     CK(cudaStreamSynchronize(h->side));
+    if (!h->inplace) {
+        for (int q = 0; q < h->cfg.q; ++q)
+            CK(copy_population(h, h->buf[h->cur] + (size_t)q * g.np, f + (size_t)q * g.nx * g.ny * g.nz, false, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return LBM_OK;
+    }
     for (int q = 0; q < h->cfg.q; ++q) {
         float* dst = f + (size_t)q * g.nx * g.ny * g.nz;
         for (int x0 = 0; x0 < g.nx; x0 += chunk) {

@@ -163,6 +163,22 @@ __device__ __forceinline__ bool boundary_path(const StepParams& p, float (&f)[Q]
     return dead;
 }
 
+// moving-wall term 6 w_i (c_i . u_wall), rho_wall = 1, for a population that bounced off the z edge; where walls
+// meet, the one named first in x, y, z order supplies the velocity.  Kept out of line: it runs on the edge
+// lanes of moving-wall set-ups only and must not cost the pull loop registers.
+template <int Q>
+__device__ __noinline__ float moving_wall_term(const StepParams& p, int i, int x, int y)
+{
+    const Geom& g = p.g;
+    const int sx = x - c_dir[i][0], sy = y - c_dir[i][1];
+    const float* u = p.wall_u[4 + (c_dir[i][2] > 0 ? 0 : 1)];
+    if (p.bc[0] == 2 && (sx < 0 || sx >= g.nx)) u = p.wall_u[sx < 0 ? 0 : 1];
+    else if (p.bc[1] == 2 && (sy < 0 || sy >= g.ny)) u = p.wall_u[2 + (sy < 0 ? 0 : 1)];
+    const float w = (Q == 27) ? (i < 7 ? (float)(2.0 / 27.0) : (i < 19 ? (float)(1.0 / 54.0) : (float)(1.0 / 216.0)))
+                              : (i < 7 ? (float)(1.0 / 18.0) : (float)(1.0 / 36.0));
+    return 6.0f * w * ((float)c_dir[i][0] * u[0] + (float)c_dir[i][1] * u[1] + (float)c_dir[i][2] * u[2]);
+}
+
 // Pull f_i(x) <- f_i(x - c_i)  (SimCalcFuncs.cu:83-94, j = INVERSE[i] relabelled).
 // x and y edges are ghost planes / rows (filled by launch_fill_ghosts or left at zero); the z edge is
 // resolved here, by choosing the address the edge lane reads from, because a z ghost shares its row with
@@ -193,14 +209,7 @@ __device__ __forceinline__ void pull_populations(const StepParams& p, const floa
         long long a = off;
         if (outside) a = wall ? (long long)dir_inv(i) * g.np : off + (dir_c(i, 2) > 0 ? g.nz : -g.nz);
         float v = fin[a];
-        if (outside && wall && p.wall_moving) {
-            // where walls meet, the one named first in x, y, z order supplies the velocity
-            const int sx = x - dir_c(i, 0), sy = y - dir_c(i, 1);
-            const float* u = p.wall_u[4 + (dir_c(i, 2) > 0 ? 0 : 1)];
-            if (p.bc[0] == 2 && (sx < 0 || sx >= g.nx)) u = p.wall_u[sx < 0 ? 0 : 1];
-            else if (p.bc[1] == 2 && (sy < 0 || sy >= g.ny)) u = p.wall_u[2 + (sy < 0 ? 0 : 1)];
-            v += 6.0f * (float)dir_weight<Q>(i) * ((float)dir_c(i, 0) * u[0] + (float)dir_c(i, 1) * u[1] + (float)dir_c(i, 2) * u[2]);
-        }
+        if (outside && wall && p.wall_moving) v += moving_wall_term<Q>(p, i, x, y);
         f[i] = v;
     }
 }
