@@ -354,11 +354,15 @@ LBM_API int lbm_create(const lbm_config* cfg, lbm_handle* out)
         int lo_prio = 0, hi_prio = 0;
         CKB(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
         CKB(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi_prio));
+        // the bulk stream carries the interior planes of a slab at the lowest priority, so that the halo
+        // transfer posted meanwhile (NCCL or copies) is not starved of SM slots by that large grid
+        CKB(cudaStreamCreateWithPriority(&h->bulk, cudaStreamNonBlocking, lo_prio));
     }
     CKB(cudaEventCreate(&h->ev0));
     CKB(cudaEventCreate(&h->ev1));
     CKB(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
     CKB(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+    CKB(cudaEventCreateWithFlags(&h->ev_bulk, cudaEventDisableTiming));
     for (int b = 0; b < (h->inplace ? 1 : 2); ++b) {
         CKB(cudaMalloc(&h->buf[b], h->state_bytes()));
         CKB(cudaMemsetAsync(h->buf[b], 0, h->state_bytes(), h->stream));
@@ -391,6 +395,8 @@ LBM_API int lbm_destroy(lbm_handle h)
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_side) cudaEventDestroy(h->ev_side);
     if (h->ev_main) cudaEventDestroy(h->ev_main);
+    if (h->ev_bulk) cudaEventDestroy(h->ev_bulk);
+    if (h->bulk) { cudaStreamSynchronize(h->bulk); cudaStreamDestroy(h->bulk); }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->side) cudaStreamDestroy(h->side);
     delete h;
@@ -402,6 +408,7 @@ LBM_API int lbm_sync(lbm_handle h)
     int rc = use(h);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->side));
+    CK(cudaStreamSynchronize(h->bulk));
     CK(cudaStreamSynchronize(h->stream));
     return LBM_OK;
 }
@@ -890,12 +897,11 @@ LBM_API int lbm_step_range(lbm_handle h, unsigned phases, int x0, int x1, int on
     if ((rc = inplace_only(h, "lbm_step_range"))) return rc;
     if (x0 < 0 || x1 > h->g.nx || x0 > x1 || (phases & ~15u) || phases == 0) return fail(LBM_ERR_INVALID, "bad range");
     if (on_side_stream) {
-        // the side stream starts after everything queued so far on the main stream
-        if (!h->pending_commit || true) {
-            CK(cudaEventRecord(h->ev_main, h->stream));
-            CK(cudaStreamWaitEvent(h->side, h->ev_main, 0));
-        }
-        rc = launch_range(h, phases, x0, x1, h->side);
+        // the bulk stream starts after everything queued so far on the main stream
+        CK(cudaEventRecord(h->ev_main, h->stream));
+        CK(cudaStreamWaitEvent(h->bulk, h->ev_main, 0));
+        rc = launch_range(h, phases, x0, x1, h->bulk);
+        h->bulk_used = true;
     } else {
         rc = launch_range(h, phases, x0, x1, h->stream);
     }
@@ -910,9 +916,12 @@ LBM_API int lbm_step_commit(lbm_handle h)
     int rc = use(h);
     if (rc) return rc;
     if (!h->pending_commit) return fail(LBM_ERR_STATE, "nothing to commit");
-    // the main stream continues only after the side stream's share of this step
-    CK(cudaEventRecord(h->ev_side, h->side));
-    CK(cudaStreamWaitEvent(h->stream, h->ev_side, 0));
+    // the main stream continues only after the bulk stream's share of this step
+    if (h->bulk_used) {
+        CK(cudaEventRecord(h->ev_bulk, h->bulk));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_bulk, 0));
+        h->bulk_used = false;
+    }
     h->cur ^= 1;
     h->pending_commit = false;
     note_step_done(h, h->pending_phases);

@@ -11,13 +11,14 @@ struct lbm_lattice_s {
     lbm_config cfg;
     lbm::Geom g;
     int device = 0;
-    cudaStream_t stream = nullptr, side = nullptr, own_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_side = nullptr, ev_main = nullptr;
+    cudaStream_t stream = nullptr, side = nullptr, own_stream = nullptr, bulk = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_side = nullptr, ev_main = nullptr, ev_bulk = nullptr;
     float* buf[2] = {nullptr, nullptr};
     int cur = 0;
     bool inplace = false;            // single-buffer AA engine: only buf[0] exists
     int aa_parity = 0;
     bool pending_commit = false;
+    bool bulk_used = false;
     unsigned pending_phases = 0;
     uint32_t* solid = nullptr;       // padded bit mask
     uint8_t* cls = nullptr;          // class of every interior 32-cell word, [x][word][y]

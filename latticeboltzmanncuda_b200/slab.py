@@ -12,6 +12,7 @@ gloo in the CPU tests).  `SlabLattice` drives one `Lattice` handle per rank: edg
 exchange of the new edge planes into the neighbours' ghost planes, overlapped with the interior planes.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -103,7 +104,7 @@ class SlabLattice:
                                device=device, **kw)
         self.q = self.lattice.q
         self.halo = HaloExchange(rank, world, bc_x == capi.BC_PERIODIC, self.q)
-        self.overlap = bool(overlap)
+        self.overlap = bool(overlap) and not os.environ.get("LBM_SLAB_NOOVERLAP")
         self._lib = capi.load()
         self._views = {}
         # everything this handle launches is ordered on a torch stream, which NCCL transfers order against
@@ -125,6 +126,8 @@ class SlabLattice:
 
     def _exchange(self, nxt):
         """edge planes of the (next or current) state -> the neighbours' ghost planes of the same state"""
+        if os.environ.get("LBM_SLAB_NOEXCHANGE"):        # diagnosis only: step without communication (wrong results)
+            return []
         nx = self.nx
         send = lambda q, which: self._plane(q, 1 if which == "lo" else nx, nxt)
         recv = lambda q, which: self._plane(q, 0 if which == "lo" else nx + 1, nxt)
