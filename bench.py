@@ -162,7 +162,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: one JSON line only
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"            # keep NCCL's version banner off stdout: one JSON line only
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # halo transfers must get SM slots next to the interior kernel
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
