@@ -299,6 +299,36 @@ def run_ours(args):
                            "state_gb": l2.layout().state_bytes * l2.layout().n_buffers / 1e9}
             l2.close()
 
+    # ---- the reference arm's own workload in the reference's own mode (N = 1 only): D3Q27, SPLIT moments, fp64
+    # equilibrium, zero-inflow edges, table reflection built from the OBJ fixture on the GPU, plane source, force
+    # accumulator, driven through the four per-phase calls like the CLI -- the like-for-like number for --impl reference
+    refmode = None
+    if world == 1 and not args.no_extra:
+        n = args.ref_size
+        obj = os.path.join(ROOT, "tests", "golden", "obj", "cube_angled.obj")
+        flow27 = source_flow(27)
+        l3 = lb.Lattice(n, n, n, None, None, lb.FluidData(1.0, tau), float(np.float32(1.0 / n)), device=local)   # defaults = reference behaviour
+        start = np.zeros(n * n * n, dtype=lb.LATTICE_POINT)
+        start["f"] = flow27[None, :]
+        l3.load_data(start)
+        del start
+        t_geo = time.perf_counter()
+        l3.insertModel(obj)
+        l3.preProcessModel()
+        l3.sync()
+        t_geo = time.perf_counter() - t_geo
+        l3.setFlowData(lb.FlowData(lb.FlowCriterion.ptestPlaneCriteria, flow27))
+        l3.setReflectionData(lb.ReflectionData())
+        l3.step(3)
+        l3.sync()
+        ms3, _ = l3.step_timed(20)
+        st3 = l3.stats()
+        refmode = {"mlups": n ** 3 * 20 / (ms3 * 1e-3) / 1e6, "ms_per_step": ms3 / 20,
+                   "config": "%d^3 D3Q27, reference arithmetic (fp64 equilibrium, SPLIT moments), zero-inflow edges, table reflection "
+                             "(%d links), plane source, force accumulator" % (n, st3["links"]),
+                   "geometry_seconds": t_geo, "geometry": "lbm_insert_model + lbm_preprocess_model on the GPU (voxelise %d^3 cells, build tables)" % n}
+        l3.close()
+
     out = None
     if rank == 0:
         traffic = None
@@ -334,6 +364,8 @@ def run_ours(args):
             out["e2e"] = e2e
         if extra:
             out["all_fluid_engines"] = extra
+        if refmode:
+            out["reference_mode"] = refmode
     if world > 1:
         dist.barrier()
     if rank == 0 and not args.no_cpu and world == 1:
