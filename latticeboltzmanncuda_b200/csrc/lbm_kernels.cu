@@ -46,7 +46,8 @@ __device__ __forceinline__ uint32_t neighbour_bits(const uint32_t* __restrict__ 
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
             const uint32_t* r = solid + (row + (long long)dx * yp + dy) * wz + w;
-            const uint32_t prev = __ldg(r - 1), c = __ldg(r), next = __ldg(r + 1);
+            // when nz is not a multiple of 32 the last interior word is also the last word of the row
+            const uint32_t prev = __ldg(r - 1), c = __ldg(r), next = (w + 1 < wz) ? __ldg(r + 1) : 0u;
             const uint32_t below = __funnelshift_l(prev, c, 1);   // bit k = solid(z_k - 1)
             const uint32_t above = __funnelshift_r(c, next, 1);   // bit k = solid(z_k + 1)
             nb |= (((below >> lane) & 1u) << nb_bit(dx, dy, -1)) | (((c >> lane) & 1u) << nb_bit(dx, dy, 0)) |
@@ -632,7 +633,7 @@ __global__ void build_cellinfo_kernel(const uint32_t* __restrict__ solid, const 
         // lanes 0..26 each look at one of the 27 surrounding words
         if (lane < 27) {
             const int dx = (int)lane / 9 - 1, dy = ((int)lane / 3) % 3 - 1, dw = (int)lane % 3 - 1;
-            near = solid[(row + (long long)dx * g.yp + dy) * g.wz + w + dw];
+            if (w + dw < g.wz) near = solid[(row + (long long)dx * g.yp + dy) * g.wz + w + dw];
         }
         own = __shfl_sync(FULL, near, 13);
         near = __any_sync(FULL, near != 0u);
