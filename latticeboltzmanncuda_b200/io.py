@@ -1,0 +1,73 @@
+"""State and field I/O around the hot path.
+
+The reference has no writer: `retrieve_data()` / `load_data()` (simulation/source/Lattice.cpp:73-113) are its only
+dump / restore.  Here a checkpoint is the populations (SoA, what the kernels hold), the solid mask, the reflection
+tables and the source / force settings in one `.npz`; `write_vti` dumps the density and velocity moments as VTK
+ImageData for inspection (ParaView etc.).
+"""
+import struct
+
+import numpy as np
+
+from . import capi
+from .lattice import FlowData, ReflectionData
+
+
+def save_checkpoint(lat, path):
+    """everything needed to continue the run bit for bit on a lattice created with the same options"""
+    tables, cells = lat.reflection_tables()
+    flow = lat.m_flowData
+    r = lat.retrieve_reflection_data() if lat.m_reflectionData is not None else None
+    np.savez(path,
+             dims=np.array([lat.nx, lat.ny, lat.nz, lat.q], np.int32),
+             f=lat.retrieve_populations(),
+             solid=lat.get_solid_mask(),
+             tables=tables.view(np.uint8).reshape(-1, 380) if len(tables) else np.zeros((0, 380), np.uint8),
+             table_cells=cells,
+             source_box=np.array([[-1 if v is None else v for v in c] for c in flow.pointCriterion], np.int64) if flow else np.zeros((0, 3), np.int64),
+             source_f=flow.inducedFlow if flow else np.zeros(0, np.float32),
+             force=np.array([r.x, r.y, r.z], np.float32) if r is not None else np.zeros(0, np.float32))
+
+
+def load_checkpoint(lat, path):
+    with np.load(path) as z:
+        dims = tuple(int(v) for v in z["dims"])
+        if dims != (lat.nx, lat.ny, lat.nz, lat.q):
+            raise ValueError("checkpoint is for a %r lattice, this one is %r" % (dims, (lat.nx, lat.ny, lat.nz, lat.q)))
+        if z["solid"].any():
+            lat.set_solid_mask(z["solid"])
+        lat.load_populations(z["f"])
+        if len(z["table_cells"]):
+            lat.set_reflection_tables(z["tables"].reshape(-1).view(capi.REFLECTION_VALUES), z["table_cells"])
+        if len(z["source_f"]):
+            lo, hi = ([None if v < 0 else int(v) for v in row] for row in z["source_box"])
+            lat.setFlowData(FlowData((tuple(lo), tuple(hi)), z["source_f"]))
+        if len(z["force"]):
+            lat.setReflectionData(ReflectionData(*[float(v) for v in z["force"]]))
+
+
+def write_vti(path, rho, ux, uy, uz, spacing=1.0, solid=None):
+    """density + velocity on the lattice points as VTK XML ImageData (appended raw binary, little endian).
+    Arrays are [nx, ny, nz] as `Lattice.moments()` returns them; VTK wants x fastest, so they are transposed."""
+    nx, ny, nz = rho.shape
+    arrays = [("density", np.ascontiguousarray(rho.transpose(2, 1, 0), "<f4"), 1)]
+    vel = np.stack([ux, uy, uz], axis=-1).transpose(2, 1, 0, 3)
+    arrays.append(("velocity", np.ascontiguousarray(vel, "<f4"), 3))
+    if solid is not None:
+        arrays.append(("solid", np.ascontiguousarray(np.asarray(solid, np.uint8).transpose(2, 1, 0)), 1))
+    head, blobs, offset = [], [], 0
+    for name, a, comps in arrays:
+        vt = "Float32" if a.dtype == np.dtype("<f4") else "UInt8"
+        head.append('<DataArray type="%s" Name="%s" NumberOfComponents="%d" format="appended" offset="%d"/>' % (vt, name, comps, offset))
+        raw = a.tobytes()
+        blobs.append(struct.pack("<Q", len(raw)) + raw)
+        offset += 8 + len(raw)
+    ext = "0 %d 0 %d 0 %d" % (nx - 1, ny - 1, nz - 1)
+    xml = ('<?xml version="1.0"?>\n<VTKFile type="ImageData" version="1.0" byte_order="LittleEndian" header_type="UInt64">\n'
+           '<ImageData WholeExtent="%s" Origin="0 0 0" Spacing="%g %g %g">\n<Piece Extent="%s">\n<PointData Scalars="density" Vectors="velocity">\n%s\n'
+           '</PointData>\n</Piece>\n</ImageData>\n<AppendedData encoding="raw">\n_' % (ext, spacing, spacing, spacing, ext, "\n".join(head)))
+    with open(path, "wb") as fh:
+        fh.write(xml.encode())
+        for b in blobs:
+            fh.write(b)
+        fh.write(b"\n</AppendedData>\n</VTKFile>\n")
