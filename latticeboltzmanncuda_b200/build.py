@@ -32,16 +32,20 @@ def is_stale():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build_native(force=False, verbose=False):
-    """nvcc -gencode arch=compute_100a,code=sm_100a -> latticeboltzmanncuda_b200/liblbm_b200.so"""
-    if not force and not is_stale():
+def build_native(force=False, verbose=False, variant=None, defines=()):
+    """nvcc -gencode arch=compute_100a,code=sm_100a -> latticeboltzmanncuda_b200/liblbm_b200.so
+
+    variant / defines: a measurement build `liblbm_b200.<variant>.so` with extra -D macros (the launch-shape
+    knobs at the top of csrc/lbm_kernels.cu); load it with LBM_B200_LIB=<path> (capi.load)."""
+    global_lib = LIB if not variant else os.path.join(HERE, "liblbm_b200.%s.so" % variant)
+    if not variant and not force and not is_stale():
         return LIB
     nvcc = nvcc_path()
     common = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC,-fvisibility=hidden"]
+              "-Xcompiler", "-fPIC,-fvisibility=hidden"] + ["-D" + d for d in defines]
     if verbose:
         common.append("-Xptxas=-v")
-    objdir = os.path.join(CSRC, "_obj")
+    objdir = os.path.join(CSRC, "_obj" if not variant else "_obj_" + variant)
     os.makedirs(objdir, exist_ok=True)
     procs, objs = [], []
     for src in sources():
@@ -51,9 +55,12 @@ def build_native(force=False, verbose=False):
     for pr in procs:
         if pr.wait() != 0:
             raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs, cwd=CSRC)
-    return LIB
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", global_lib] + objs, cwd=CSRC)
+    return global_lib
 
 
 if __name__ == "__main__":
-    print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m latticeboltzmanncuda_b200.build [--force] [-v] [--variant NAME -DMACRO=VALUE ...]
+    name = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=name,
+                       defines=[a[2:] for a in sys.argv if a.startswith("-D")]))

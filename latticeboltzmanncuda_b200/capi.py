@@ -125,7 +125,8 @@ _lib = None
 
 
 def library_path():
-    return _build.LIB
+    # LBM_B200_LIB: a measurement build of the same sources (build.py --variant); never a different implementation
+    return os.environ.get("LBM_B200_LIB") or _build.LIB
 
 
 def load(build_if_missing=True):
@@ -134,7 +135,7 @@ def load(build_if_missing=True):
     if _lib is not None:
         return _lib
     path = library_path()
-    if build_if_missing and _build.is_stale():
+    if build_if_missing and path == _build.LIB and _build.is_stale():
         _build.build_native()
     if not os.path.exists(path):
         raise ImportError("liblbm_b200.so is missing (%s): run `python -m latticeboltzmanncuda_b200.build`; "

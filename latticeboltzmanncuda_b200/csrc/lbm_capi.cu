@@ -68,15 +68,24 @@ __global__ void any_nonzero_kernel(const uint32_t* w, size_t n, unsigned* flag)
     if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
-// keep the class array resident in L2: it is a few MB, read by every warp before anything else, and
-// would otherwise be evicted by the population stream every step
-void pin_classes_in_l2(lbm_handle h)
+// Keep the class array (main stream, read by every warp of the general kernel before anything else) and the
+// neighbourhood words of the special list (side stream, read by every warp of the special kernel before it can
+// issue a single population load) resident in L2: a few MB and a few tens of MB that the population stream
+// would otherwise evict every step.
+void pin_tables_in_l2(lbm_handle h)
 {
+    // measured on B200 (profiles/r01_notes.md): pinning the 45 MB of neighbourhood words of the 512^3 obstacle costs
+    // the general kernel 20 % (it loses that much L2 as a write buffer), so only the class bytes are pinned
+    static const bool pin_info = [] { const char* e = getenv("LBM_PIN_CELLINFO"); return e ? atoi(e) != 0 : false; }();
+    static const bool pin_cls = [] { const char* e = getenv("LBM_PIN_CLS"); return e ? atoi(e) != 0 : true; }();
+    if (!pin_cls) return;
     int dev = h->device, max_persist = 0, max_window = 0;
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-    if (max_persist <= 0 || max_window <= 0) return;
-    size_t want = h->cls_bytes < (size_t)max_persist ? h->cls_bytes : (size_t)max_persist;
+    if (max_persist <= 0 || max_window <= 0) { cudaGetLastError(); return; }
+    const size_t info_bytes = (pin_info && h->cellinfo) ? h->n_special * 32 * sizeof(uint32_t) : 0;
+    size_t want = h->cls_bytes + info_bytes;
+    if (want > (size_t)max_persist) want = (size_t)max_persist;
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
     cudaStreamAttrValue attr;
     std::memset(&attr, 0, sizeof attr);
@@ -86,6 +95,12 @@ void pin_classes_in_l2(lbm_handle h)
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    if (info_bytes) {
+        const size_t room = want > h->cls_bytes ? want - h->cls_bytes : 0;
+        attr.accessPolicyWindow.base_ptr = h->cellinfo;
+        attr.accessPolicyWindow.num_bytes = info_bytes < (size_t)max_window ? info_bytes : (size_t)max_window;
+        attr.accessPolicyWindow.hitRatio = room >= info_bytes ? 1.0f : (float)((double)room / (double)info_bytes);
+    }
     cudaStreamSetAttribute(h->side, cudaStreamAttributeAccessPolicyWindow, &attr);
     cudaGetLastError();   // best effort: an unsupported attribute must not poison later calls
 }
@@ -100,18 +115,15 @@ int rebuild_special(lbm_handle h)
         h->cls_pitch = ((g.ny + 15) / 16) * 16;
         h->cls_bytes = (size_t)g.nx * wcount * h->cls_pitch;
         CK(cudaMalloc(&h->cls, h->cls_bytes));
-        pin_classes_in_l2(h);
     }
     const uint32_t* solid = h->any_solid ? h->solid : nullptr;
     const uint32_t* tmask = h->nlinks ? h->tmask : nullptr;
-    if ((solid || tmask) && !h->cellinfo) {
-        CK(cudaMalloc(&h->cellinfo, (size_t)g.np * sizeof(uint32_t)));
+    if ((solid || tmask) && !h->special_list)
         CK(cudaMalloc(&h->special_list, (size_t)g.nx * g.ny * wcount * sizeof(uint32_t)));
-    }
     if (!h->flag) CK(cudaMalloc(&h->flag, sizeof(unsigned)));
     CK(cudaMemsetAsync(h->flag, 0, sizeof(unsigned), h->stream));
     CK(cudaMemsetAsync(h->cls, 0, h->cls_bytes, h->stream));
-    CK(launch_build_cellinfo(solid, tmask, h->cls, h->cls_pitch, h->cellinfo, h->special_list, h->flag, g, h->stream));
+    CK(launch_build_cellinfo(solid, tmask, h->cls, h->cls_pitch, h->special_list, h->flag, g, h->stream));
     unsigned n = 0;
     CK(cudaMemcpyAsync(&n, h->flag, sizeof n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -124,6 +136,15 @@ int rebuild_special(lbm_handle h)
         std::sort(list.begin(), list.end());
         CK(cudaMemcpy(h->special_list, list.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
+    if (n > h->cellinfo_cap) {
+        cudaFree(h->cellinfo);
+        h->cellinfo = nullptr;
+        h->cellinfo_cap = 0;
+        CK(cudaMalloc(&h->cellinfo, (size_t)n * 32 * sizeof(uint32_t)));
+        h->cellinfo_cap = n;
+    }
+    CK(launch_fill_cellinfo(solid, tmask, h->special_list, (long long)n, h->cellinfo, g, h->stream));
+    pin_tables_in_l2(h);
     h->dead_dirty = 2;
     return LBM_OK;
 }
@@ -210,12 +231,13 @@ int launch_range(lbm_handle h, unsigned phases, int x0, int x1, cudaStream_t s)
         CK(cudaEventRecord(h->ev_main, h->stream));
         CK(cudaStreamWaitEvent(h->side, h->ev_main, 0));
     }
-    CK(launch_step(c, p, s, split ? h->side : nullptr));
+    int launched = 0;
+    CK(launch_step(c, p, s, split ? h->side : nullptr, &launched));
     if (split) {
         CK(cudaEventRecord(h->ev_side, h->side));
         CK(cudaStreamWaitEvent(h->stream, h->ev_side, 0));
     }
-    h->launches += 1 + ((c.general && h->n_special) ? 1 : 0);
+    h->launches += launched;
     return LBM_OK;
 }
 
@@ -260,8 +282,9 @@ int one_step(lbm_handle h, unsigned phases)
             return fail(LBM_ERR_UNSUPPORTED, "the in-place engine runs fused stream + collide steps only");
         InplaceParams ip;
         fill_inplace(h, ip);
-        CK(launch_inplace_step(ip, h->cfg.q, h->cfg.moment_mode, h->cfg.eq_precision == LBM_EQ_FP64, h->stream));
-        h->launches += (h->aa_parity == 0) ? 2 : 1;
+        int launched = 0;
+        CK(launch_inplace_step(ip, h->cfg.q, h->cfg.moment_mode, h->cfg.eq_precision == LBM_EQ_FP64, h->stream, &launched));
+        h->launches += launched;
         h->aa_parity ^= 1;
         return LBM_OK;
     }
@@ -879,7 +902,7 @@ LBM_API int lbm_set_stream(lbm_handle h, void* stream)
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
     h->stream = stream ? (cudaStream_t)stream : h->own_stream;
-    if (h->cls) pin_classes_in_l2(h);
+    if (h->cls) pin_tables_in_l2(h);
     return LBM_OK;
 }
 

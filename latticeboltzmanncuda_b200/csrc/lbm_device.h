@@ -76,7 +76,7 @@ struct StepParams {
     const uint32_t* special_list;   // mask-word indices of the special words
     long long n_special;
     int   dead_mode;          // all-solid words: 0 process like any other, 1 write zeros, 2 skip
-    const uint32_t* cellinfo; // per padded cell of special words: bits 0..26 solid flags of the 3x3x3 neighbourhood, bit 27 reflection target
+    const uint32_t* cellinfo; // [n_special][32], list order: bits 0..26 solid flags of the cell's 3x3x3 neighbourhood, bit 27 reflection target
     const uint32_t* tmask;    // link-target bits or nullptr
     const uint32_t* tprefix;  // exclusive popcount prefix per mask word
     const uint32_t* toff;     // CSR offsets per target cell
@@ -101,7 +101,7 @@ struct InplaceParams {
     float wall_u[6][3];
 };
 
-cudaError_t launch_inplace_step(const InplaceParams& p, int q, int moment, int eq64, cudaStream_t stream);
+cudaError_t launch_inplace_step(const InplaceParams& p, int q, int moment, int eq64, cudaStream_t stream, int* launches);
 cudaError_t launch_inplace_scatter(const float* dense, float* f, const Geom& g, int q_index, int x0, int nxc, cudaStream_t stream);
 cudaError_t launch_inplace_gather(const InplaceParams& p, int q, float* dense, int q_index, int x0, int nxc, cudaStream_t stream);
 cudaError_t launch_inplace_moments(const InplaceParams& p, int q, int moment_mode, float* rho, float* ux, float* uy, float* uz, cudaStream_t stream);
@@ -116,7 +116,8 @@ struct LaunchCfg {
 
 // launches (all asynchronous on `stream`)
 // stream_special (optional): the special-word kernel of the general path runs there, concurrently with the rest
-cudaError_t launch_step(const LaunchCfg& cfg, const StepParams& p, cudaStream_t stream, cudaStream_t stream_special);
+// *launches (optional) is incremented by the number of kernels launched
+cudaError_t launch_step(const LaunchCfg& cfg, const StepParams& p, cudaStream_t stream, cudaStream_t stream_special, int* launches);
 
 cudaError_t launch_fill_ghosts(float* f, const Geom& g, int q, const int bc[3], const float wall_u[6][3], bool include_x,
                                cudaStream_t stream, int* launches);
@@ -130,9 +131,11 @@ cudaError_t launch_gather_dense(float* dense, const float* fq, const Geom& g, in
 
 // solid bytes (host order, optionally with x ghost planes) -> padded bit mask incl. ghost bits
 cudaError_t launch_build_mask(const uint8_t* solid_bytes, int has_x_ghost, uint32_t* mask, const Geom& g, const int bc[3], cudaStream_t stream);
-// classify interior mask words and write the neighbourhood words of the special ones
+// classify interior mask words and list the special ones; then (list sorted) write their neighbourhood words
 cudaError_t launch_build_cellinfo(const uint32_t* solid, const uint32_t* tmask, uint8_t* cls, int cls_pitch,
-                                  uint32_t* cellinfo, uint32_t* special_list, unsigned* counter, const Geom& g, cudaStream_t stream);
+                                  uint32_t* special_list, unsigned* counter, const Geom& g, cudaStream_t stream);
+cudaError_t launch_fill_cellinfo(const uint32_t* solid, const uint32_t* tmask, const uint32_t* special_list, long long n_special,
+                                 uint32_t* cellinfo, const Geom& g, cudaStream_t stream);
 cudaError_t launch_mask_to_bytes(const uint32_t* mask, uint8_t* solid_bytes, const Geom& g, cudaStream_t stream);
 
 // moments / reductions

@@ -34,7 +34,8 @@ struct Edge {          // where population i of cell (x,y,z) comes from / goes t
 // neighbour of (x,y,z) in direction (dx,dy,dz) under the per-axis edge rules; `sign` = +1 for the push target
 // x + c_i, -1 for the pull source x - c_i.  For a wall the returned term is 6 w_i (c_b . u) where c_b is the
 // direction of the population after the bounce.
-template <int Q>
+// AXES: bit a set = the cell may sit on an edge of axis a (the others are known to be interior).
+template <int Q, int AXES = 7>
 __device__ __forceinline__ Edge edge_lookup(const InplaceParams& p, int i, int x, int y, int z, int sign)
 {
     const Geom& g = p.g;
@@ -47,7 +48,7 @@ __device__ __forceinline__ Edge edge_lookup(const InplaceParams& p, int i, int x
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const int t = pos[a] + c[a];
-        if (t >= 0 && t < n[a]) { e.off += (long long)c[a] * stride[a]; continue; }
+        if (!((AXES >> a) & 1) || (t >= 0 && t < n[a])) { e.off += (long long)c[a] * stride[a]; continue; }
         if (p.bc[a] == 2) {
             if (e.kind == 0) {       // the wall named first in x, y, z order supplies the velocity
                 const float* u = p.wall_u[a * 2 + (t < 0 ? 0 : 1)];
@@ -82,45 +83,92 @@ __global__ void __launch_bounds__(256) aa_even_kernel(const __grid_constant__ In
     for (int i = 0; i < Q; ++i) a[(long long)dir_inv(i) * g.np] = f[i];
 }
 
-// EDGE = false: warps whose 32 cells all lie away from every domain edge (plain offsets, lean code);
-// EDGE = true : the remaining warps, with the per-direction edge rules.  Two launches over the same grid; each
-// thread only touches its own slots, so they need no ordering between them.
-template <int Q, int MOMENT, bool EQ64, bool EDGE>
-__global__ void __launch_bounds__(256) aa_odd_kernel(const __grid_constant__ InplaceParams p)
+// pull + collide + push of one cell that may sit on a domain edge of the axes in AXES
+template <int Q, int MOMENT, bool EQ64, int AXES>
+__device__ __forceinline__ void aa_odd_edge_cell(const InplaceParams& p, float* a, int x, int y, int z)
 {
     const Geom& g = p.g;
-    const int z = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int x = blockIdx.z;
-    if (z >= g.nz || y >= g.ny) return;
-    float* __restrict__ a = p.f + g.cell(x, y, z);
     float f[Q];
-    // warp-uniform: does any lane of this warp sit on a domain edge?
-    const bool edge = x == 0 || x == g.nx - 1 || y == 0 || y == g.ny - 1 || (z >> 5) == 0 || (z >> 5) == ((g.nz - 1) >> 5);
-    if (edge != EDGE) return;
-    if constexpr (!EDGE) {
 #pragma unroll
-        for (int i = 0; i < Q; ++i)
-            f[i] = a[(long long)dir_inv(i) * g.np - ((long long)dir_c(i, 0) * g.plane + (long long)(dir_c(i, 1) * g.zp + dir_c(i, 2)))];
-        if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
-        else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
+    for (int i = 0; i < Q; ++i) {
+        const Edge e = edge_lookup<Q, AXES>(p, i, x, y, z, -1);
+        f[i] = (e.kind == 0) ? a[(long long)dir_inv(i) * g.np + e.off] : a[(long long)i * g.np] + e.term;
+    }
+    if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
+    else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
+    asm volatile("" : "+l"(a), "+r"(x), "+r"(y), "+r"(z));      // rebuild the addresses instead of keeping Q of them alive
 #pragma unroll
-        for (int i = 0; i < Q; ++i)
-            a[(long long)i * g.np + ((long long)dir_c(i, 0) * g.plane + (long long)(dir_c(i, 1) * g.zp + dir_c(i, 2)))] = f[i];
+    for (int i = 0; i < Q; ++i) {
+        const Edge e = edge_lookup<Q, AXES>(p, i, x, y, z, +1);
+        if (e.kind == 0) a[(long long)i * g.np + e.off] = f[i];
+        else             a[(long long)dir_inv(i) * g.np] = f[i] + e.term;
+    }
+}
+
+// Two launches cover the lattice, each thread touching only its own slots (no ordering between them):
+//   MODE 0  the interior box, rows 1..ny-2 of planes 1..nx-2: a block owns 4 consecutive z-words of a row.  Words
+//           away from the z edge run plain offsets (lean code); the first and last word of the row take the z rule
+//           (periodic wrap / wall) for the populations with c_z != 0 of their first / last lane -- in the same
+//           launch, next to the rest of their row, so that the row is still one contiguous run in DRAM;
+//   MODE 2  the x and y faces, with the per-direction rules of all three axes.
+template <int Q, int MOMENT, bool EQ64, int MODE>
+__global__ void __launch_bounds__(128, (MODE == 0 && Q == 19 && !EQ64) ? 12 : 8) aa_odd_kernel(const __grid_constant__ InplaceParams p)
+{
+    const Geom& g = p.g;
+    const int wcount = (g.nz + 31) >> 5;
+    int x, y, w;
+    if constexpr (MODE == 0) {
+        w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        if (w >= wcount) return;
+        y = 1 + blockIdx.y;
+        x = 1 + blockIdx.z;
     } else {
-#pragma unroll
-        for (int i = 0; i < Q; ++i) {
-            const Edge e = edge_lookup<Q>(p, i, x, y, z, -1);
-            f[i] = (e.kind == 0) ? a[(long long)dir_inv(i) * g.np + e.off] : a[(long long)i * g.np] + e.term;
+        long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const int x2 = min(g.nx, 2), y2 = min(g.ny, 2);
+        const int xi = g.nx - x2;
+        const long long na = (long long)x2 * g.ny * wcount, nb = (long long)xi * y2 * wcount;
+        if (k < na) {
+            const int plane = (int)(k / ((long long)g.ny * wcount));
+            const int rem = (int)(k - (long long)plane * g.ny * wcount);
+            x = plane == 0 ? 0 : g.nx - 1;
+            y = rem / wcount;
+            w = rem - y * wcount;
+        } else if (k < na + nb) {
+            k -= na;
+            const int xs = (int)(k / (y2 * wcount));
+            const int rem = (int)(k - (long long)xs * (y2 * wcount));
+            x = 1 + xs;
+            y = (rem / wcount) == 0 ? 0 : g.ny - 1;
+            w = rem % wcount;
+        } else {
+            return;
         }
+    }
+    const int z = w * 32 + (int)(threadIdx.x & 31u);
+    if (z >= g.nz) return;
+    float* a = p.f + g.cell(x, y, z);
+    if constexpr (MODE == 0) {
+        if (w == 0 || w == wcount - 1) {           // warp-uniform
+            aa_odd_edge_cell<Q, MOMENT, EQ64, 4>(p, a, x, y, z);
+            return;
+        }
+        float f[Q];
+        long long np = g.np, plane = g.plane;
+        int zp = g.zp;
+#pragma unroll
+        for (int i = 0; i < Q; ++i)
+            f[i] = a[(long long)dir_inv(i) * np - ((long long)dir_c(i, 0) * plane + (long long)(dir_c(i, 1) * zp + dir_c(i, 2)))];
         if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
         else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
+        // The push goes to the very addresses the pull read.  Left alone, the compiler keeps all Q of them in
+        // registers across the collision (78 registers for D3Q19, 126 for D3Q27); making the strides and the
+        // base opaque here makes it rebuild each address next to its store (a multiply-add) instead.
+        asm volatile("" : "+l"(np), "+l"(plane), "+r"(zp), "+l"(a));
 #pragma unroll
-        for (int i = 0; i < Q; ++i) {
-            const Edge e = edge_lookup<Q>(p, i, x, y, z, +1);
-            if (e.kind == 0) a[(long long)i * g.np + e.off] = f[i];
-            else             a[(long long)dir_inv(i) * g.np] = f[i] + e.term;
-        }
+        for (int i = 0; i < Q; ++i)
+            a[(long long)i * np + ((long long)dir_c(i, 0) * plane + (long long)(dir_c(i, 1) * zp + dir_c(i, 2)))] = f[i];
+    } else {
+        aa_odd_edge_cell<Q, MOMENT, EQ64, 7>(p, a, x, y, z);
     }
 }
 
@@ -219,35 +267,48 @@ __global__ void __launch_bounds__(256) aa_mass_kernel(const __grid_constant__ In
 }
 
 template <int Q, int MOMENT, bool EQ64>
-cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream)
+cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, int* launches)
 {
     const Geom& g = p.g;
-    int bz = ((g.nz + 31) / 32) * 32;
-    if (bz > 128) bz = 128;
-    int by = 128 / bz;
-    if (by > g.ny) by = g.ny;
-    dim3 block(bz, by, 1), grid((g.nz + bz - 1) / bz, (g.ny + by - 1) / by, g.nx);
+    int n = 0;
     if (p.parity == 0) {        // parked form -> pull / push
-        aa_odd_kernel<Q, MOMENT, EQ64, false><<<grid, block, 0, stream>>>(p);
-        aa_odd_kernel<Q, MOMENT, EQ64, true><<<grid, block, 0, stream>>>(p);
+        const int wcount = (g.nz + 31) / 32;
+        if (g.nx > 2 && g.ny > 2) {
+            dim3 grid((wcount + 3) / 4, g.ny - 2, g.nx - 2);
+            aa_odd_kernel<Q, MOMENT, EQ64, 0><<<grid, 128, 0, stream>>>(p);
+            ++n;
+        }
+        const long long x2 = g.nx < 2 ? g.nx : 2, y2 = g.ny < 2 ? g.ny : 2;
+        const long long xi = g.nx - x2;
+        // when there is no interior box (nx or ny <= 2) the faces are the whole lattice
+        const long long warps = x2 * g.ny * wcount + xi * y2 * wcount;
+        aa_odd_kernel<Q, MOMENT, EQ64, 2><<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(p);
+        ++n;
     } else {                    // arrived form -> local
+        int bz = ((g.nz + 31) / 32) * 32;
+        if (bz > 128) bz = 128;
+        int by = 128 / bz;
+        if (by > g.ny) by = g.ny;
+        dim3 block(bz, by, 1), grid((g.nz + bz - 1) / bz, (g.ny + by - 1) / by, g.nx);
         aa_even_kernel<Q, MOMENT, EQ64><<<grid, block, 0, stream>>>(p);
+        ++n;
     }
+    if (launches) *launches += n;
     return cudaGetLastError();
 }
 
 template <int Q>
-cudaError_t launch_q(const InplaceParams& p, int moment, int eq64, cudaStream_t s)
+cudaError_t launch_q(const InplaceParams& p, int moment, int eq64, cudaStream_t s, int* n)
 {
-    if (moment == 0) return eq64 ? launch_t<Q, 0, true>(p, s) : launch_t<Q, 0, false>(p, s);
-    return eq64 ? launch_t<Q, 1, true>(p, s) : launch_t<Q, 1, false>(p, s);
+    if (moment == 0) return eq64 ? launch_t<Q, 0, true>(p, s, n) : launch_t<Q, 0, false>(p, s, n);
+    return eq64 ? launch_t<Q, 1, true>(p, s, n) : launch_t<Q, 1, false>(p, s, n);
 }
 
 }  // namespace
 
-cudaError_t launch_inplace_step(const InplaceParams& p, int q, int moment, int eq64, cudaStream_t stream)
+cudaError_t launch_inplace_step(const InplaceParams& p, int q, int moment, int eq64, cudaStream_t stream, int* launches)
 {
-    return q == 27 ? launch_q<27>(p, moment, eq64, stream) : launch_q<19>(p, moment, eq64, stream);
+    return q == 27 ? launch_q<27>(p, moment, eq64, stream, launches) : launch_q<19>(p, moment, eq64, stream, launches);
 }
 
 cudaError_t launch_inplace_scatter(const float* dense, float* f, const Geom& g, int q_index, int x0, int nxc, cudaStream_t stream)

@@ -25,7 +25,8 @@ struct lbm_lattice_s {
     int cls_pitch = 0;
     size_t cls_bytes = 0;
     int dead_dirty = 2;              // steps for which all-solid words must still be written as zeros
-    uint32_t* cellinfo = nullptr;    // neighbourhood word per padded cell (special words only)
+    uint32_t* cellinfo = nullptr;    // neighbourhood words of the special words, [n_special][32] in list order
+    size_t cellinfo_cap = 0;         // entries allocated
     uint32_t* special_list = nullptr;   // mask-word indices of the special words
     size_t n_special = 0;
     bool any_solid = false;          // some bit set (geometry or wall ghosts)

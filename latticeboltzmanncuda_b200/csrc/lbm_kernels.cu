@@ -202,16 +202,21 @@ __device__ __forceinline__ void pull_populations(const StepParams& p, const floa
     }
     const bool lo = (z == 0), hi = (z == g.nz - 1);
     const bool wall = p.bc[2] == 2;
+    // all Q loads first, as one batch (only the address differs on the edge lane) ...
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
-        const long long off = (long long)i * g.np - ((long long)dir_c(i, 0) * g.plane + (long long)(dir_c(i, 1) * g.zp + dir_c(i, 2)));
-        if (dir_c(i, 2) == 0) { f[i] = fin[off]; continue; }
-        const bool outside = dir_c(i, 2) > 0 ? lo : hi;          // the cell this population comes from is beyond the z edge
-        long long a = off;
-        if (outside) a = wall ? (long long)dir_inv(i) * g.np : off + (dir_c(i, 2) > 0 ? g.nz : -g.nz);
-        float v = fin[a];
-        if (outside && wall && p.wall_moving) v += moving_wall_term<Q>(p, i, x, y);
-        f[i] = v;
+        long long a = (long long)i * g.np - ((long long)dir_c(i, 0) * g.plane + (long long)(dir_c(i, 1) * g.zp + dir_c(i, 2)));
+        if (dir_c(i, 2) != 0) {
+            const bool outside = dir_c(i, 2) > 0 ? lo : hi;          // the cell this population comes from is beyond the z edge
+            if (outside) a = wall ? (long long)dir_inv(i) * g.np : a + (dir_c(i, 2) > 0 ? g.nz : -g.nz);
+        }
+        f[i] = fin[a];
+    }
+    // ... then the moving-wall terms of the populations that bounced (edge lanes of moving-wall set-ups only)
+    if (wall && p.wall_moving && (lo || hi)) {
+#pragma unroll
+        for (int i = 1; i < Q; ++i)
+            if (dir_c(i, 2) != 0 && (dir_c(i, 2) > 0 ? lo : hi)) f[i] += moving_wall_term<Q>(p, i, x, y);
     }
 }
 
@@ -251,8 +256,23 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
 //   special   skipped here: step_special_kernel walks the compact list of special words.
 enum : unsigned { CLS_ORDINARY = 0, CLS_DEAD = 1, CLS_SPECIAL = 2 };
 
-template <int Q, int MOMENT, bool EQ64, int MINB, int ROWS_PER_WARP>
-__global__ void __launch_bounds__(128, MINB) step_general_kernel(const __grid_constant__ StepParams p)
+// Launch shape of the general and special kernels; the defaults are the values measured best on B200 at 512^3
+// (profiles/r01_notes.md).  Variants for measurement are built with -D (latticeboltzmanncuda_b200/build.py).
+#ifndef LBM_GEN_WARPS
+#define LBM_GEN_WARPS 4        // z-words (warps) per block
+#endif
+#ifndef LBM_GEN_MINB
+#define LBM_GEN_MINB 10        // resident blocks per SM the register allocation aims at
+#endif
+#ifndef LBM_GEN_ROWS
+#define LBM_GEN_ROWS 8         // rows a warp walks (4, 8 or 16)
+#endif
+#ifndef LBM_SPC_MINB
+#define LBM_SPC_MINB 10
+#endif
+
+template <int Q, int MOMENT, bool EQ64, int ROWS_PER_WARP, bool SRC>
+__global__ void __launch_bounds__(32 * LBM_GEN_WARPS, LBM_GEN_MINB) step_general_kernel(const __grid_constant__ StepParams p)
 {
     const Geom& g = p.g;
     const unsigned lane = threadIdx.x & 31u;
@@ -305,9 +325,9 @@ __global__ void __launch_bounds__(128, MINB) step_general_kernel(const __grid_co
             }
         }
         // ---- additive source on the selected cells (SimCalcFuncs.cu:200-215); bounce-back solids take none
-        if ((p.phases & PH_SOURCE) && p.src_on && !(dead && p.boundary_mode == 1)) {
-            if (x >= p.src_lo[0] && x <= p.src_hi[0] && y >= p.src_lo[1] && y <= p.src_hi[1] &&
-                z >= p.src_lo[2] && z <= p.src_hi[2]) {
+        // (SRC is set for the launch that covers the planes the source box intersects, see launch_step_general_r)
+        if (SRC && !(dead && p.boundary_mode == 1)) {
+            if (y >= p.src_lo[1] && y <= p.src_hi[1] && z >= p.src_lo[2] && z <= p.src_hi[2]) {
 #pragma unroll
                 for (int i = 0; i < Q; ++i) f[i] += p.src_f[i];
             }
@@ -320,16 +340,67 @@ __global__ void __launch_bounds__(128, MINB) step_general_kernel(const __grid_co
     }
 }
 
+// Bounce-back pull of one cell of a special word: exactly one load per population.  A population whose
+// upstream neighbour is solid (bit of nb) or lies beyond a z wall is read from the cell's own opposite slot
+// (half-way bounce-back) instead of from the neighbour, so solid cells are never read; solid and inactive
+// lanes load nothing at all.  Momentum exchange with obstacle cells is summed into (fx, fy, fz).
+// ZEDGE (warp-uniform) = the word holds a z edge that is periodic or a wall; kept out of the common path so
+// that its Q loads stay one uninterrupted batch.
+template <int Q, bool ZEDGE>
+__device__ __forceinline__ void pull_bounce_back(const StepParams& p, const float* __restrict__ fin, int x, int y, int z,
+                                                 uint32_t nb, bool live, float (&f)[Q],
+                                                 float& fx, float& fy, float& fz, bool& has_force)
+{
+    const Geom& g = p.g;
+    const bool lo = ZEDGE && (z == 0), hi = ZEDGE && (z == g.nz - 1);
+    const bool wall = p.bc[2] == 2;
+    uint32_t zwalls = 0;                       // populations that bounced off a z wall (moving-wall term below)
+    f[0] = live ? fin[0] : 0.0f;
+#pragma unroll
+    for (int i = 1; i < Q; ++i) {
+        long long a = (long long)i * g.np - ((long long)dir_c(i, 0) * g.plane + (long long)(dir_c(i, 1) * g.zp + dir_c(i, 2)));
+        bool own = (nb >> nb_bit(-dir_c(i, 0), -dir_c(i, 1), -dir_c(i, 2))) & 1u;
+        if (ZEDGE && dir_c(i, 2) != 0) {
+            const bool outside = dir_c(i, 2) > 0 ? lo : hi;
+            if (outside && !own) {
+                if (wall) { own = true; zwalls |= 1u << i; }
+                else a += (dir_c(i, 2) > 0 ? g.nz : -g.nz);
+            }
+        }
+        if (own) a = (long long)dir_inv(i) * g.np;
+        f[i] = live ? fin[a] : 0.0f;
+    }
+    if (p.force) {
+#pragma unroll
+        for (int i = 1; i < Q; ++i) {
+            if (live && ((nb >> nb_bit(-dir_c(i, 0), -dir_c(i, 1), -dir_c(i, 2))) & 1u)) {
+                const float m = f[i] + f[i];
+                fx -= (float)dir_c(i, 0) * m;
+                fy -= (float)dir_c(i, 1) * m;
+                fz -= (float)dir_c(i, 2) * m;
+                has_force = true;
+            }
+        }
+    }
+    if (ZEDGE && p.wall_moving && live && zwalls) {
+#pragma unroll
+        for (int i = 1; i < Q; ++i)
+            if (dir_c(i, 2) != 0 && ((zwalls >> i) & 1u)) f[i] += moving_wall_term<Q>(p, i, x, y);
+    }
+}
+
 // Special words (touching a solid cell, a wall ghost or a reflection target): one warp per entry of the
-// compact list built with the classification.  Same step as everywhere else plus boundary_path().
-template <int Q, int MOMENT, bool EQ64, int MINB>
-__global__ void __launch_bounds__(128, MINB) step_special_kernel(const __grid_constant__ StepParams p)
+// compact list built with the classification; cellinfo holds one neighbourhood word per cell of each entry,
+// in list order.  Same step as everywhere else plus the boundary treatment.
+template <int Q, int MOMENT, bool EQ64>
+__global__ void __launch_bounds__(128, LBM_SPC_MINB) step_special_kernel(const __grid_constant__ StepParams p)
 {
     const Geom& g = p.g;
     const unsigned lane = threadIdx.x & 31u;
     const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (k >= p.n_special) return;
     const uint32_t widx = __ldg(p.special_list + k);          // mask-word index = padded cell index / 32
+    const uint32_t nb = __ldg(p.cellinfo + k * 32 + lane);
     const int w = (int)(widx % (uint32_t)g.wz);
     const uint32_t row = widx / (uint32_t)g.wz;
     const int x = (int)(row / (uint32_t)g.yp) - 1, y = (int)(row % (uint32_t)g.yp) - 1;
@@ -337,17 +408,46 @@ __global__ void __launch_bounds__(128, MINB) step_special_kernel(const __grid_co
     const int z = w * 32 - PAD_Z + (int)lane;
     const bool active = z < g.nz;
     const bool do_stream = p.phases & PH_STREAM;
+    const bool edge_word = w == PAD_Z / 32 || w == PAD_Z / 32 + ((g.nz + 31) >> 5) - 1;
     const long long idx = (long long)widx * 32 + lane;
     const float* __restrict__ fin = p.fin + idx;
     float f[Q];
-    if (do_stream) {
-        pull_populations<Q>(p, fin, x, y, z, w == PAD_Z / 32 || w == PAD_Z / 32 + ((g.nz + 31) >> 5) - 1, f);
-    } else {
+    bool dead, skip_store = false;
+    if (p.boundary_mode == 1 && do_stream) {
+        // ---- half-way bounce-back, fused with the pull
+        const bool solid_here = (nb >> nb_bit(0, 0, 0)) & 1u;
+        float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+        bool has_force = false;
+        if (edge_word && p.bc[2] != 0) pull_bounce_back<Q, true>(p, fin, x, y, z, nb, active && !solid_here, f, fx, fy, fz, has_force);
+        else                           pull_bounce_back<Q, false>(p, fin, x, y, z, nb, active && !solid_here, f, fx, fy, fz, has_force);
+        dead = solid_here;
+        // both buffers already hold zeros in the solid cells: leave out the 32-byte sectors (8 lanes) that
+        // are solid throughout; a sector with a live cell is written whole, a partial one would cost a read
+        const uint32_t solid_lanes = __ballot_sync(FULL, solid_here || !active);
+        skip_store = p.dead_mode == 2 && ((solid_lanes >> (lane & 24u)) & 0xffu) == 0xffu;
+        if (p.force && __any_sync(FULL, has_force)) {
 #pragma unroll
-        for (int i = 0; i < Q; ++i) f[i] = fin[(long long)i * g.np];
+            for (int o = 16; o > 0; o >>= 1) {
+                fx += __shfl_xor_sync(FULL, fx, o);
+                fy += __shfl_xor_sync(FULL, fy, o);
+                fz += __shfl_xor_sync(FULL, fz, o);
+            }
+            if (lane == 0) {
+                double* slot = p.force + 3 * ((unsigned)(widx >> 2) % FORCE_SLOTS);
+                atomicAdd(slot + 0, (double)fx);
+                atomicAdd(slot + 1, (double)fy);
+                atomicAdd(slot + 2, (double)fz);
+            }
+        }
+    } else {
+        if (do_stream) {
+            pull_populations<Q>(p, fin, x, y, z, edge_word, f);
+        } else {
+#pragma unroll
+            for (int i = 0; i < Q; ++i) f[i] = fin[(long long)i * g.np];
+        }
+        dead = boundary_path<Q>(p, f, fin, (long long)widx, x, y, z, lane, active, do_stream, nb);
     }
-    const uint32_t nb = __ldg(p.cellinfo + idx);
-    const bool dead = boundary_path<Q>(p, f, fin, (long long)widx, x, y, z, lane, active, do_stream, nb);
     if ((p.phases & PH_COLLIDE) && !dead) {
         if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
         else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
@@ -359,7 +459,7 @@ __global__ void __launch_bounds__(128, MINB) step_special_kernel(const __grid_co
             for (int i = 0; i < Q; ++i) f[i] += p.src_f[i];
         }
     }
-    if (active) {
+    if (active && !skip_store) {
         float* __restrict__ fout = p.fout + idx;
 #pragma unroll
         for (int i = 0; i < Q; ++i) fout[(long long)i * g.np] = f[i];
@@ -396,52 +496,70 @@ cudaError_t launch_step_dense(const StepParams& p, cudaStream_t stream)
     return cudaGetLastError();
 }
 
-template <int Q, int MOMENT, bool EQ64, int ROWS>
-cudaError_t launch_step_general_r(const StepParams& p, cudaStream_t stream)
+template <int Q, int MOMENT, bool EQ64, int ROWS, bool SRC>
+cudaError_t launch_step_general_x(const StepParams& p, int xa, int xb, cudaStream_t stream)
 {
+    if (xb <= xa) return cudaSuccess;
     const Geom& g = p.g;
+    StepParams q = p;
+    q.x0 = xa; q.x1 = xb;
     const int wcount = (g.nz + 31) / 32;
-    const int warps = wcount < 4 ? wcount : 4;
+    const int warps = wcount < LBM_GEN_WARPS ? wcount : LBM_GEN_WARPS;
     dim3 block(32 * warps, 1, 1);
-    dim3 grid((wcount + warps - 1) / warps, (g.ny + ROWS - 1) / ROWS, p.x1 - p.x0);
-    step_general_kernel<Q, MOMENT, EQ64, 10, ROWS><<<grid, block, 0, stream>>>(p);
+    dim3 grid((wcount + warps - 1) / warps, (g.ny + ROWS - 1) / ROWS, xb - xa);
+    step_general_kernel<Q, MOMENT, EQ64, ROWS, SRC><<<grid, block, 0, stream>>>(q);
     return cudaGetLastError();
 }
 
+// The additive source touches the planes src_lo[0]..src_hi[0] only (the reference's plane x == 0 or one cell):
+// those planes get their own launch of the variant that carries the source code, every other plane runs the
+// variant without it.
+template <int Q, int MOMENT, bool EQ64, int ROWS>
+cudaError_t launch_step_general_r(const StepParams& p, cudaStream_t stream, int* launches)
+{
+    int sa = p.x0, sb = p.x0;      // [sa, sb) = planes of this launch the source box intersects
+    if ((p.phases & PH_SOURCE) && p.src_on) {
+        sa = p.src_lo[0] > p.x0 ? p.src_lo[0] : p.x0;
+        sb = (p.src_hi[0] + 1) < p.x1 ? (p.src_hi[0] + 1) : p.x1;
+        if (sb <= sa) sa = sb = p.x0;
+    }
+    cudaError_t e = launch_step_general_x<Q, MOMENT, EQ64, ROWS, false>(p, p.x0, sa, stream);
+    if (e == cudaSuccess) e = launch_step_general_x<Q, MOMENT, EQ64, ROWS, true>(p, sa, sb, stream);
+    if (e == cudaSuccess) e = launch_step_general_x<Q, MOMENT, EQ64, ROWS, false>(p, sb, p.x1, stream);
+    if (launches) *launches += (sa > p.x0) + (sb > sa) + (p.x1 > sb);
+    return e;
+}
+
 template <int Q, int MOMENT, bool EQ64>
-cudaError_t launch_step_tasks(const StepParams& p, cudaStream_t stream, cudaStream_t stream_special)
+cudaError_t launch_step_tasks(const StepParams& p, cudaStream_t stream, cudaStream_t stream_special, int* launches)
 {
     if (p.x1 <= p.x0) return cudaSuccess;
-    static int rows = [] { const char* e = getenv("LBM_GENERAL_ROWS"); return e ? atoi(e) : 8; }();   // tuning knob
-    cudaError_t e;
-    if (rows >= 16 && p.cls_pitch % 16 == 0) e = launch_step_general_r<Q, MOMENT, EQ64, 16>(p, stream);
-    else if (rows >= 8 && p.cls_pitch % 8 == 0) e = launch_step_general_r<Q, MOMENT, EQ64, 8>(p, stream);
-    else e = launch_step_general_r<Q, MOMENT, EQ64, 4>(p, stream);
+    static_assert(LBM_GEN_ROWS == 4 || LBM_GEN_ROWS == 8 || LBM_GEN_ROWS == 16, "rows per warp");
+    cudaError_t e = launch_step_general_r<Q, MOMENT, EQ64, LBM_GEN_ROWS>(p, stream, launches);   // cls_pitch is a multiple of 16
     if (e != cudaSuccess) return e;
     if (p.n_special > 0) {
         const long long blocks = (p.n_special + 3) / 4;
-        static int minb = [] { const char* e = getenv("LBM_SPECIAL_MINB"); return e ? atoi(e) : 10; }();   // tuning knob
         cudaStream_t ss = stream_special ? stream_special : stream;
-        if (minb >= 12)      step_special_kernel<Q, MOMENT, EQ64, 12><<<(unsigned)blocks, 128, 0, ss>>>(p);
-        else if (minb >= 10) step_special_kernel<Q, MOMENT, EQ64, 10><<<(unsigned)blocks, 128, 0, ss>>>(p);
-        else                 step_special_kernel<Q, MOMENT, EQ64, 8><<<(unsigned)blocks, 128, 0, ss>>>(p);
+        step_special_kernel<Q, MOMENT, EQ64><<<(unsigned)blocks, 128, 0, ss>>>(p);
+        if (launches) *launches += 1;
     }
     return cudaGetLastError();
 }
 
 template <int Q>
-cudaError_t launch_step_q(const LaunchCfg& c, const StepParams& p, cudaStream_t s, cudaStream_t s2)
+cudaError_t launch_step_q(const LaunchCfg& c, const StepParams& p, cudaStream_t s, cudaStream_t s2, int* n)
 {
     const int key = (c.moment_mode ? 4 : 0) | (c.eq64 ? 2 : 0) | (c.general ? 1 : 0);
+    if (!c.general && n) *n += 1;
     switch (key) {
         case 0: return launch_step_dense<Q, 0, false>(p, s);
-        case 1: return launch_step_tasks<Q, 0, false>(p, s, s2);
+        case 1: return launch_step_tasks<Q, 0, false>(p, s, s2, n);
         case 2: return launch_step_dense<Q, 0, true>(p, s);
-        case 3: return launch_step_tasks<Q, 0, true>(p, s, s2);
+        case 3: return launch_step_tasks<Q, 0, true>(p, s, s2, n);
         case 4: return launch_step_dense<Q, 1, false>(p, s);
-        case 5: return launch_step_tasks<Q, 1, false>(p, s, s2);
+        case 5: return launch_step_tasks<Q, 1, false>(p, s, s2, n);
         case 6: return launch_step_dense<Q, 1, true>(p, s);
-        default: return launch_step_tasks<Q, 1, true>(p, s, s2);
+        default: return launch_step_tasks<Q, 1, true>(p, s, s2, n);
     }
 }
 
@@ -612,10 +730,10 @@ __global__ void build_mask_kernel(const uint8_t* __restrict__ sb, int has_x_ghos
 // One warp per interior (row, word).  A word is special if any of the 27 mask words around it has a
 // solid bit or it holds a reflection target; it is dead if every one of its interior cells is solid.
 // cls is laid out [x][word][y] (y fastest, pitch cls_pitch) so that the classes of consecutive rows of
-// one z-word are adjacent bytes; cellinfo is indexed like the populations (one word per padded cell,
-// only the cells of special words are ever written or read; bit 27 = reflection target).
+// one z-word are adjacent bytes.  The neighbourhood words of the special words are written afterwards, in
+// the order of the sorted list (fill_cellinfo_kernel).
 __global__ void build_cellinfo_kernel(const uint32_t* __restrict__ solid, const uint32_t* __restrict__ tmask,
-                                      uint8_t* __restrict__ cls, int cls_pitch, uint32_t* __restrict__ cellinfo,
+                                      uint8_t* __restrict__ cls, int cls_pitch,
                                       uint32_t* __restrict__ special_list, unsigned* counter, Geom g)
 {
     const int wlo = PAD_Z / 32, wcount = (g.nz + 31) / 32;            // words that hold interior cells
@@ -648,10 +766,27 @@ __global__ void build_cellinfo_kernel(const uint32_t* __restrict__ solid, const 
     if ((own & live_lanes) == live_lanes) c = CLS_DEAD;
     else if (touches || (tw & live_lanes)) {
         c = CLS_SPECIAL;
-        cellinfo[widx * 32 + lane] = nb | (((tw >> lane) & 1u) << 27);
         if (lane == 0) special_list[atomicAdd(counter, 1u)] = (uint32_t)widx;
     }
     if (lane == 0) cls[((long long)x * wcount + wi) * cls_pitch + y] = (uint8_t)c;
+}
+
+// cellinfo[k * 32 + lane] for the k-th entry of the (sorted) special list: bits 0..26 = solid flags of the
+// 3x3x3 neighbourhood of the cell (bit 13 the cell itself), bit 27 = reflection target.  One warp per entry;
+// 128 bytes per special word, contiguous in the order the step kernel walks them.
+__global__ void fill_cellinfo_kernel(const uint32_t* __restrict__ solid, const uint32_t* __restrict__ tmask,
+                                     const uint32_t* __restrict__ special_list, long long n_special,
+                                     uint32_t* __restrict__ cellinfo, Geom g)
+{
+    const long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    if (k >= n_special) return;
+    const uint32_t widx = special_list[k];
+    const int w = (int)(widx % (uint32_t)g.wz);
+    const long long row = widx / (uint32_t)g.wz;
+    const uint32_t nb = solid ? neighbour_bits(solid, row, g.yp, g.wz, w, lane) : 0u;
+    const uint32_t tw = tmask ? tmask[widx] : 0u;
+    cellinfo[k * 32 + lane] = nb | (((tw >> lane) & 1u) << 27);
 }
 
 __global__ void mask_to_bytes_kernel(const uint32_t* __restrict__ mask, uint8_t* __restrict__ sb, Geom g)
@@ -738,10 +873,10 @@ __global__ void __launch_bounds__(256) mass_momentum_kernel(const float* __restr
 
 // ---- launch wrappers ---------------------------------------------------------------------------
 
-cudaError_t launch_step(const LaunchCfg& cfg, const StepParams& p, cudaStream_t stream, cudaStream_t stream_special)
+cudaError_t launch_step(const LaunchCfg& cfg, const StepParams& p, cudaStream_t stream, cudaStream_t stream_special, int* launches)
 {
-    if (cfg.q == 27) return launch_step_q<27>(cfg, p, stream, stream_special);
-    if (cfg.q == 19) return launch_step_q<19>(cfg, p, stream, stream_special);
+    if (cfg.q == 27) return launch_step_q<27>(cfg, p, stream, stream_special, launches);
+    if (cfg.q == 19) return launch_step_q<19>(cfg, p, stream, stream_special, launches);
     return cudaErrorInvalidValue;
 }
 
@@ -823,11 +958,20 @@ cudaError_t launch_build_mask(const uint8_t* solid_bytes, int has_x_ghost, uint3
 }
 
 cudaError_t launch_build_cellinfo(const uint32_t* solid, const uint32_t* tmask, uint8_t* cls, int cls_pitch,
-                                  uint32_t* cellinfo, uint32_t* special_list, unsigned* counter, const Geom& g, cudaStream_t stream)
+                                  uint32_t* special_list, unsigned* counter, const Geom& g, cudaStream_t stream)
 {
     const long long nwarps = (long long)g.nx * g.ny * ((g.nz + 31) / 32);
     const long long threads = nwarps * 32;
-    build_cellinfo_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(solid, tmask, cls, cls_pitch, cellinfo, special_list, counter, g);
+    build_cellinfo_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(solid, tmask, cls, cls_pitch, special_list, counter, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_cellinfo(const uint32_t* solid, const uint32_t* tmask, const uint32_t* special_list, long long n_special,
+                                 uint32_t* cellinfo, const Geom& g, cudaStream_t stream)
+{
+    if (n_special <= 0) return cudaSuccess;
+    const long long threads = n_special * 32;
+    fill_cellinfo_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(solid, tmask, special_list, n_special, cellinfo, g);
     return cudaGetLastError();
 }
 

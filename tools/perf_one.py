@@ -11,3 +11,7 @@ elif name == "tasks_obst":
     run("tasks, obstacle", 19, lb.EQ_FP32, (Z, Z, Z), BB, True, False)
 elif name == "headline":
     run("headline", 19, lb.EQ_FP32, (Z, W, W), BB, True, True)
+elif name == "inplace":
+    run("in-place periodic", 19, lb.EQ_FP32, (P, P, P), BB, False, False, engine=lb.ENGINE_INPLACE)
+elif name == "inplace_walls":
+    run("in-place walls", 19, lb.EQ_FP32, (W, W, W), BB, False, False, engine=lb.ENGINE_INPLACE)
