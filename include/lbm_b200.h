@@ -119,7 +119,7 @@ LBM_API int lbm_destroy(lbm_handle h);
 LBM_API int lbm_upload_aos(lbm_handle h, const void *cells, size_t count);
 LBM_API int lbm_download_aos(lbm_handle h, void *cells, size_t count);
 
-/* populations only, dense float[q][nx][ny][nz] */
+/* populations only, dense float[q][nx][ny][nz]; f may point to host (pageable or pinned) or device memory */
 LBM_API int lbm_upload_f_soa(lbm_handle h, const float *f);
 LBM_API int lbm_download_f_soa(lbm_handle h, float *f);
 
@@ -165,7 +165,7 @@ LBM_API int lbm_step_phases(lbm_handle h, int n, unsigned phases);
 LBM_API int lbm_step_timed(lbm_handle h, int n, unsigned phases, float *ms, int *launches);
 
 /* density and velocity moments of the current state, dense float[nx*ny*nz] each (any may
- * be NULL), computed with the handle's moment_mode */
+ * be NULL), computed with the handle's moment_mode; the outputs may be host or device memory */
 LBM_API int lbm_moments(lbm_handle h, float *rho, float *ux, float *uy, float *uz);
 /* sum over all cells of sum_i f_i, and of sum_i f_i c_i, accumulated in double */
 LBM_API int lbm_mass(lbm_handle h, double *mass);

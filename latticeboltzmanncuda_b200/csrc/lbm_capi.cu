@@ -534,7 +534,7 @@ static cudaError_t copy_population(lbm_handle h, float* dev_pop, float* host_pop
     p.srcPos = to_device ? make_cudaPos(0, 0, 0) : interior;
     p.dstPos = to_device ? interior : make_cudaPos(0, 0, 0);
     p.extent = make_cudaExtent((size_t)g.nz * sizeof(float), (size_t)g.ny, (size_t)g.nx);
-    p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    p.kind = cudaMemcpyDefault;      // the caller's buffer may be host (pageable or pinned) or device memory
     return cudaMemcpy3DAsync(&p, s);
 }
 
@@ -586,7 +586,7 @@ LBM_API int lbm_download_f_soa(lbm_handle h, float* f)
             } else {
                 CK(launch_gather_dense((float*)h->staging, h->buf[h->cur] + (size_t)q * g.np, g, x0, nxc, h->stream));
             }
-            CK(cudaMemcpyAsync(dst + (size_t)x0 * g.ny * g.nz, h->staging, (size_t)nxc * per_plane, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(dst + (size_t)x0 * g.ny * g.nz, h->staging, (size_t)nxc * per_plane, cudaMemcpyDefault, h->stream));
             CK(cudaStreamSynchronize(h->stream));
         }
     }
@@ -810,7 +810,7 @@ LBM_API int lbm_moments(lbm_handle h, float* rho, float* ux, float* uy, float* u
     }
     float* outs[4] = {rho, ux, uy, uz};
     for (int k = 0; k < 4 && e == cudaSuccess; ++k)
-        if (outs[k]) e = cudaMemcpyAsync(outs[k], dev + (size_t)k * n, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+        if (outs[k]) e = cudaMemcpyAsync(outs[k], dev + (size_t)k * n, n * sizeof(float), cudaMemcpyDefault, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(dev);
     if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "moments: %s", cudaGetErrorString(e));

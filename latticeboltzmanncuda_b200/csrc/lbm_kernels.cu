@@ -262,7 +262,7 @@ enum : unsigned { CLS_ORDINARY = 0, CLS_DEAD = 1, CLS_SPECIAL = 2 };
 #define LBM_GEN_WARPS 4        // z-words (warps) per block
 #endif
 #ifndef LBM_GEN_MINB
-#define LBM_GEN_MINB 10        // resident blocks per SM the register allocation aims at
+#define LBM_GEN_MINB 8         // resident blocks per SM the register allocation aims at (64 registers; 10 and 12 measured slower)
 #endif
 #ifndef LBM_GEN_ROWS
 #define LBM_GEN_ROWS 8         // rows a warp walks (4, 8 or 16)

@@ -128,10 +128,17 @@ class Lattice:
         return out
 
     def load_populations(self, f):
-        """dense float32 [q, nx, ny, nz]"""
+        """dense float32 [q, nx, ny, nz]: a numpy array (host) or a torch tensor (host or CUDA; the C ABI takes
+        either kind of pointer)"""
+        shape = (self.q, self.nx, self.ny, self.nz)
+        if hasattr(f, "data_ptr"):
+            if tuple(f.shape) != shape or str(f.dtype) != "torch.float32" or not f.is_contiguous():
+                raise ValueError("expected a contiguous float32 tensor of shape %r" % (shape,))
+            capi.check(self._lib.lbm_upload_f_soa(self._h, capi.ptr(f.data_ptr())))
+            return
         a = np.ascontiguousarray(f, np.float32)
-        if a.shape != (self.q, self.nx, self.ny, self.nz):
-            raise ValueError("expected shape %r" % ((self.q, self.nx, self.ny, self.nz),))
+        if a.shape != shape:
+            raise ValueError("expected shape %r" % (shape,))
         capi.check(self._lib.lbm_upload_f_soa(self._h, capi.ptr(a)))
 
     def retrieve_populations(self, out=None):
@@ -261,8 +268,14 @@ class Lattice:
         capi.check(self._lib.lbm_sync(self._h))
 
     # -- diagnostics ---------------------------------------------------------------------------
-    def moments(self):
+    def moments(self, out=None):
+        """density and velocity fields [nx, ny, nz]; `out` = four float32 buffers of n_cells elements each (numpy
+        arrays or torch tensors, host or CUDA) to fill instead of allocating host arrays"""
         n = self.n_cells
+        if out is not None:
+            ptrs = [capi.ptr(o.data_ptr() if hasattr(o, "data_ptr") else o) for o in out]
+            capi.check(self._lib.lbm_moments(self._h, *ptrs))
+            return out
         rho, ux, uy, uz = (np.empty(n, np.float32) for _ in range(4))
         capi.check(self._lib.lbm_moments(self._h, capi.ptr(rho), capi.ptr(ux), capi.ptr(uy), capi.ptr(uz)))
         shp = (self.nx, self.ny, self.nz)
