@@ -128,13 +128,20 @@ int rebuild_special(lbm_handle h)
     CK(cudaMemcpyAsync(&n, h->flag, sizeof n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->n_special = n;
-    if (n > 1) {
+    h->special_start.assign((size_t)g.nx + 1, 0u);
+    if (n > 0) {
         // the list is filled in atomic order; sorting it puts the z-words of a row and the rows of a plane next
-        // to each other again, so neighbouring warps share sectors and DRAM pages like in the dense kernels
+        // to each other again, so neighbouring warps share sectors and DRAM pages like in the dense kernels,
+        // and the entries of a range of planes become a range of the list
         std::vector<uint32_t> list(n);
         CK(cudaMemcpy(list.data(), h->special_list, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         std::sort(list.begin(), list.end());
         CK(cudaMemcpy(h->special_list, list.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        for (int x = 0; x <= g.nx; ++x) {
+            const uint64_t first_word = (uint64_t)(x + 1) * g.yp * g.wz;      // mask words of padded plane x + 1 start here
+            h->special_start[x] = (uint32_t)(std::lower_bound(list.begin(), list.end(), first_word,
+                                                              [](uint32_t a, uint64_t b) { return (uint64_t)a < b; }) - list.begin());
+        }
     }
     if (n > h->cellinfo_cap) {
         cudaFree(h->cellinfo);
@@ -181,7 +188,10 @@ void fill_params(lbm_handle h, StepParams& p, unsigned phases, int x0, int x1)
     p.cls_pitch = h->cls_pitch;
     p.cellinfo = h->cellinfo;
     p.special_list = h->special_list;
-    p.n_special = (long long)h->n_special;
+    if (h->n_special && (int)h->special_start.size() == h->g.nx + 1 && x0 >= 0 && x1 <= h->g.nx && x0 < x1) {
+        p.special_k0 = h->special_start[x0];
+        p.n_special = (long long)h->special_start[x1] - (long long)h->special_start[x0];
+    }
     // all-solid words hold zeros and are never read: bounce-back solids are dead in every phase, the
     // reference's solids are emptied by the reflect phase.  They are written while stale values may remain.
     const bool dead_ok = h->cfg.boundary_mode == LBM_BOUNDARY_BOUNCE_BACK || (phases & PH_REFLECT);
@@ -200,6 +210,10 @@ void fill_params(lbm_handle h, StepParams& p, unsigned phases, int x0, int x1)
         for (int a = 0; a < 3; ++a)
             if (h->cfg.wall_u[k][a] != 0.0f) p.wall_moving = 1;
     std::memcpy(p.src_f, h->src_f, sizeof p.src_f);
+    for (int i = 0; i < 27; ++i) {
+        p.pop_off[i] = (long long)i * h->g.np;
+        p.pull_off[i] = p.pop_off[i] - ((long long)dir_c(i, 0) * h->g.plane + (long long)(dir_c(i, 1) * h->g.zp + dir_c(i, 2)));
+    }
 }
 
 // is the dense kernel (pull + collide on an all-fluid lattice) enough for these phases?
@@ -226,7 +240,7 @@ int launch_range(lbm_handle h, unsigned phases, int x0, int x1, cudaStream_t s)
     // the two touch disjoint cells of the output and only read the input, and the latency-bound special
     // kernel fills bandwidth the general kernel leaves.
     static const bool concurrent = [] { const char* e = getenv("LBM_SPECIAL_CONCURRENT"); return e ? atoi(e) != 0 : true; }();
-    const bool split = concurrent && c.general && h->n_special && s == h->stream;
+    const bool split = concurrent && c.general && p.n_special > 0 && s == h->stream;
     if (split) {
         CK(cudaEventRecord(h->ev_main, h->stream));
         CK(cudaStreamWaitEvent(h->side, h->ev_main, 0));
@@ -266,6 +280,12 @@ void fill_inplace(lbm_handle h, InplaceParams& ip)
     ip.parity = h->aa_parity;
     for (int a = 0; a < 3; ++a) ip.bc[a] = h->cfg.bc[a];
     std::memcpy(ip.wall_u, h->cfg.wall_u, sizeof ip.wall_u);
+    for (int i = 0; i < 27; ++i) {
+        const long long c = (long long)dir_c(i, 0) * h->g.plane + (long long)(dir_c(i, 1) * h->g.zp + dir_c(i, 2));
+        ip.pop_off[i] = (long long)i * h->g.np;
+        ip.pull_off[i] = (long long)dir_inv(i) * h->g.np - c;
+        ip.push_off[i] = (long long)i * h->g.np + c;
+    }
 }
 
 int inplace_only(lbm_handle h, const char* what)

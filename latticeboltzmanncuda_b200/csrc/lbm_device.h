@@ -74,7 +74,8 @@ struct StepParams {
     const uint8_t*  cls;      // class of every interior 32-cell word, [x][word][y], pitch cls_pitch
     int   cls_pitch;
     const uint32_t* special_list;   // mask-word indices of the special words
-    long long n_special;
+    long long n_special;      // entries this launch covers ...
+    long long special_k0;     // ... starting at this one (the list is sorted, so a range of planes is a range of entries)
     int   dead_mode;          // all-solid words: 0 process like any other, 1 write zeros, 2 skip
     const uint32_t* cellinfo; // [n_special][32], list order: bits 0..26 solid flags of the cell's 3x3x3 neighbourhood, bit 27 reflection target
     const uint32_t* tmask;    // link-target bits or nullptr
@@ -89,6 +90,11 @@ struct StepParams {
     int   bc[3];
     float wall_u[6][3];       // wall velocities (the z walls are applied at pull time, x and y walls by ghost fills)
     int   wall_moving;
+    // element offsets from a cell, precomputed on the host so that the kernels address with one constant-bank add
+    // and keep no per-population strides in registers: pop_off[i] = i * np (the cell's own slot of population i),
+    // pull_off[i] = i * np - (c_ix * plane + c_iy * zp + c_iz) (the slot population i is pulled from)
+    long long pop_off[27];
+    long long pull_off[27];
 };
 
 // single-buffer (AA pattern) engine, lbm_inplace.cu
@@ -99,6 +105,11 @@ struct InplaceParams {
     int   parity;             // 0: f*_i(x) parked in A[inv(i)][x] (next step pulls and pushes); 1: pushed to A[i][x + c_i]
     int   bc[3];              // 1 periodic, 2 wall
     float wall_u[6][3];
+    // element offsets from a cell, precomputed on the host (see StepParams): pop_off[i] = i * np,
+    // pull_off[i] = inv(i) * np - (c_i as an offset), push_off[i] = i * np + (c_i as an offset)
+    long long pop_off[27];
+    long long pull_off[27];
+    long long push_off[27];
 };
 
 cudaError_t launch_inplace_step(const InplaceParams& p, int q, int moment, int eq64, cudaStream_t stream, int* launches);

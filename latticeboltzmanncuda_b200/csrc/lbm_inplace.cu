@@ -66,21 +66,22 @@ __device__ __forceinline__ Edge edge_lookup(const InplaceParams& p, int i, int x
 }
 
 template <int Q, int MOMENT, bool EQ64>
-__global__ void __launch_bounds__(256) aa_even_kernel(const __grid_constant__ InplaceParams p)
+__global__ void __launch_bounds__(256, (Q == 19 && !EQ64) ? 6 : 4) aa_even_kernel(const __grid_constant__ InplaceParams p)
 {
     const Geom& g = p.g;
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int x = blockIdx.z;
     if (z >= g.nz || y >= g.ny) return;
-    float* __restrict__ a = p.f + g.cell(x, y, z);
+    float* a = p.f + g.cell(x, y, z);
     float f[Q];
 #pragma unroll
-    for (int i = 0; i < Q; ++i) f[i] = a[(long long)i * g.np];
+    for (int i = 0; i < Q; ++i) f[i] = a[p.pop_off[i]];
     if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
     else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
+    asm volatile("" : "+l"(a));          // rebuild the Q addresses next to the stores instead of keeping them alive
 #pragma unroll
-    for (int i = 0; i < Q; ++i) a[(long long)dir_inv(i) * g.np] = f[i];
+    for (int i = 0; i < Q; ++i) a[p.pop_off[dir_inv(i)]] = f[i];
 }
 
 // pull + collide + push of one cell that may sit on a domain edge of the axes in AXES
@@ -153,20 +154,17 @@ __global__ void __launch_bounds__(128, (MODE == 0 && Q == 19 && !EQ64) ? 12 : 8)
             return;
         }
         float f[Q];
-        long long np = g.np, plane = g.plane;
-        int zp = g.zp;
+        // pull_off[i] = inv(i) * np - (c_i as an element offset), push_off[i] = i * np + (c_i as an element offset),
+        // precomputed on the host: every address is the cell plus one constant-bank operand, and no stride or
+        // address has to stay in a register across the collision (the push goes to the very slots the pull read;
+        // with the strides in registers the compiler kept all Q addresses alive: 78 registers for D3Q19)
 #pragma unroll
-        for (int i = 0; i < Q; ++i)
-            f[i] = a[(long long)dir_inv(i) * np - ((long long)dir_c(i, 0) * plane + (long long)(dir_c(i, 1) * zp + dir_c(i, 2)))];
+        for (int i = 0; i < Q; ++i) f[i] = a[p.pull_off[i]];
         if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
         else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
-        // The push goes to the very addresses the pull read.  Left alone, the compiler keeps all Q of them in
-        // registers across the collision (78 registers for D3Q19, 126 for D3Q27); making the strides and the
-        // base opaque here makes it rebuild each address next to its store (a multiply-add) instead.
-        asm volatile("" : "+l"(np), "+l"(plane), "+r"(zp), "+l"(a));
+        asm volatile("" : "+l"(a));
 #pragma unroll
-        for (int i = 0; i < Q; ++i)
-            a[(long long)i * np + ((long long)dir_c(i, 0) * plane + (long long)(dir_c(i, 1) * zp + dir_c(i, 2)))] = f[i];
+        for (int i = 0; i < Q; ++i) a[p.push_off[i]] = f[i];
     } else {
         aa_odd_edge_cell<Q, MOMENT, EQ64, 7>(p, a, x, y, z);
     }

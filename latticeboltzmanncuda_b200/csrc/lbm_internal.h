@@ -29,6 +29,7 @@ struct lbm_lattice_s {
     size_t cellinfo_cap = 0;         // entries allocated
     uint32_t* special_list = nullptr;   // mask-word indices of the special words
     size_t n_special = 0;
+    std::vector<uint32_t> special_start;   // [nx + 1]: first list entry of every interior plane (host side)
     bool any_solid = false;          // some bit set (geometry or wall ghosts)
     uint8_t* solid_bytes = nullptr;  // nx*ny*nz (+2 planes) scratch
     uint32_t *tmask = nullptr, *tprefix = nullptr, *toff = nullptr, *reflected = nullptr;

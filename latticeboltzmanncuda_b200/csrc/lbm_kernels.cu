@@ -76,7 +76,7 @@ __device__ __forceinline__ bool boundary_path(const StepParams& p, float (&f)[Q]
 #pragma unroll
             for (int i = 1; i < Q; ++i) {
                 if ((nb >> nb_bit(-dir_c(i, 0), -dir_c(i, 1), -dir_c(i, 2))) & 1u) {
-                    const float back = fin[(long long)dir_inv(i) * g.np];
+                    const float back = fin[p.pop_off[dir_inv(i)]];
                     f[i] = back;
                     // momentum exchange with an obstacle cell (domain walls are ghost fills and never get
                     // here; periodic or halo images of obstacle cells count): population inv(i) goes in
@@ -197,7 +197,7 @@ __device__ __forceinline__ void pull_populations(const StepParams& p, const floa
     if (!edge_word || p.bc[2] == 0) {
 #pragma unroll
         for (int i = 0; i < Q; ++i)
-            f[i] = fin[(long long)i * g.np - ((long long)dir_c(i, 0) * g.plane + (long long)(dir_c(i, 1) * g.zp + dir_c(i, 2)))];
+            f[i] = fin[p.pull_off[i]];
         return;
     }
     const bool lo = (z == 0), hi = (z == g.nz - 1);
@@ -205,10 +205,10 @@ __device__ __forceinline__ void pull_populations(const StepParams& p, const floa
     // all Q loads first, as one batch (only the address differs on the edge lane) ...
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
-        long long a = (long long)i * g.np - ((long long)dir_c(i, 0) * g.plane + (long long)(dir_c(i, 1) * g.zp + dir_c(i, 2)));
+        long long a = p.pull_off[i];
         if (dir_c(i, 2) != 0) {
             const bool outside = dir_c(i, 2) > 0 ? lo : hi;          // the cell this population comes from is beyond the z edge
-            if (outside) a = wall ? (long long)dir_inv(i) * g.np : a + (dir_c(i, 2) > 0 ? g.nz : -g.nz);
+            if (outside) a = wall ? p.pop_off[dir_inv(i)] : a + (dir_c(i, 2) > 0 ? g.nz : -g.nz);
         }
         f[i] = fin[a];
     }
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
     else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
     float* __restrict__ fout = p.fout + idx;
 #pragma unroll
-    for (int i = 0; i < Q; ++i) fout[(long long)i * g.np] = f[i];
+    for (int i = 0; i < Q; ++i) fout[p.pop_off[i]] = f[i];
 }
 
 // General kernel.  Every 32-cell word of every interior row was classified when the geometry was set
@@ -268,7 +268,7 @@ enum : unsigned { CLS_ORDINARY = 0, CLS_DEAD = 1, CLS_SPECIAL = 2 };
 #define LBM_GEN_ROWS 8         // rows a warp walks (4, 8 or 16)
 #endif
 #ifndef LBM_SPC_MINB
-#define LBM_SPC_MINB 10
+#define LBM_SPC_MINB 8          // 63 registers, no spills (10 blocks/SM = 48 registers spills in the pull loop)
 #endif
 
 template <int Q, int MOMENT, bool EQ64, int ROWS_PER_WARP, bool SRC>
@@ -285,22 +285,23 @@ __global__ void __launch_bounds__(32 * LBM_GEN_WARPS, LBM_GEN_MINB) step_general
     const bool active = z < g.nz;
     const bool do_stream = p.phases & PH_STREAM;
     const uint8_t* cp = p.cls + ((long long)x * wcount + wi) * p.cls_pitch + y0;
-    uint32_t clsw[ROWS_PER_WARP / 4];
+    // the class bytes of this warp's rows, in two 64-bit registers (a small array indexed by the row would live
+    // in local memory)
+    unsigned long long cw0 = 0, cw1 = 0;
     if (ROWS_PER_WARP == 4) {
-        clsw[0] = __ldg(reinterpret_cast<const uint32_t*>(cp));
+        cw0 = __ldg(reinterpret_cast<const uint32_t*>(cp));
     } else if (ROWS_PER_WARP == 8) {
-        const uint2 v = __ldg(reinterpret_cast<const uint2*>(cp));
-        clsw[0] = v.x; clsw[1 % (ROWS_PER_WARP / 4)] = v.y;
+        cw0 = __ldg(reinterpret_cast<const unsigned long long*>(cp));
     } else {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(cp));
-        clsw[0] = v.x; clsw[1 % (ROWS_PER_WARP / 4)] = v.y; clsw[2 % (ROWS_PER_WARP / 4)] = v.z; clsw[3 % (ROWS_PER_WARP / 4)] = v.w;
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(cp));
+        cw0 = v.x; cw1 = v.y;
     }
 
 #pragma unroll 1
     for (int r = 0; r < ROWS_PER_WARP; ++r) {
         const int y = y0 + r;
         if (y >= g.ny) break;
-        const unsigned cls = (clsw[r >> 2] >> (8 * (r & 3))) & 0xffu;
+        const unsigned cls = (unsigned)(((ROWS_PER_WARP > 8 && r >= 8) ? cw1 : cw0) >> (8 * (r & 7))) & 0xffu;
         if (cls == CLS_SPECIAL) continue;              // step_special_kernel owns these words
         const long long idx = ((long long)(x + 1) * g.yp + (y + 1)) * g.zp + (z + PAD_Z);
         float f[Q];
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(32 * LBM_GEN_WARPS, LBM_GEN_MINB) step_general
                 pull_populations<Q>(p, fin, x, y, z, wi == 0 || wi == wcount - 1, f);
             } else {
 #pragma unroll
-                for (int i = 0; i < Q; ++i) f[i] = fin[(long long)i * g.np];
+                for (int i = 0; i < Q; ++i) f[i] = fin[p.pop_off[i]];
             }
             // ---- BGK relaxation (SimCalcFuncs.cu:98-156); runs on every live cell like the reference
             if (p.phases & PH_COLLIDE) {
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(32 * LBM_GEN_WARPS, LBM_GEN_MINB) step_general
         if (active) {
             float* __restrict__ fout = p.fout + idx;
 #pragma unroll
-            for (int i = 0; i < Q; ++i) fout[(long long)i * g.np] = f[i];
+            for (int i = 0; i < Q; ++i) fout[p.pop_off[i]] = f[i];
         }
     }
 }
@@ -358,7 +359,7 @@ __device__ __forceinline__ void pull_bounce_back(const StepParams& p, const floa
     f[0] = live ? fin[0] : 0.0f;
 #pragma unroll
     for (int i = 1; i < Q; ++i) {
-        long long a = (long long)i * g.np - ((long long)dir_c(i, 0) * g.plane + (long long)(dir_c(i, 1) * g.zp + dir_c(i, 2)));
+        long long a = p.pull_off[i];
         bool own = (nb >> nb_bit(-dir_c(i, 0), -dir_c(i, 1), -dir_c(i, 2))) & 1u;
         if (ZEDGE && dir_c(i, 2) != 0) {
             const bool outside = dir_c(i, 2) > 0 ? lo : hi;
@@ -367,7 +368,7 @@ __device__ __forceinline__ void pull_bounce_back(const StepParams& p, const floa
                 else a += (dir_c(i, 2) > 0 ? g.nz : -g.nz);
             }
         }
-        if (own) a = (long long)dir_inv(i) * g.np;
+        if (own) a = p.pop_off[dir_inv(i)];
         f[i] = live ? fin[a] : 0.0f;
     }
     if (p.force) {
@@ -397,14 +398,15 @@ __global__ void __launch_bounds__(128, LBM_SPC_MINB) step_special_kernel(const _
 {
     const Geom& g = p.g;
     const unsigned lane = threadIdx.x & 31u;
-    const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (k >= p.n_special) return;
+    // the launch covers the entries [special_k0, special_k0 + n_special) of the list: those of the planes [x0, x1)
+    const long long kl = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (kl >= p.n_special) return;
+    const long long k = p.special_k0 + kl;
     const uint32_t widx = __ldg(p.special_list + k);          // mask-word index = padded cell index / 32
     const uint32_t nb = __ldg(p.cellinfo + k * 32 + lane);
     const int w = (int)(widx % (uint32_t)g.wz);
     const uint32_t row = widx / (uint32_t)g.wz;
     const int x = (int)(row / (uint32_t)g.yp) - 1, y = (int)(row % (uint32_t)g.yp) - 1;
-    if (x < p.x0 || x >= p.x1) return;
     const int z = w * 32 - PAD_Z + (int)lane;
     const bool active = z < g.nz;
     const bool do_stream = p.phases & PH_STREAM;
@@ -444,7 +446,7 @@ __global__ void __launch_bounds__(128, LBM_SPC_MINB) step_special_kernel(const _
             pull_populations<Q>(p, fin, x, y, z, edge_word, f);
         } else {
 #pragma unroll
-            for (int i = 0; i < Q; ++i) f[i] = fin[(long long)i * g.np];
+            for (int i = 0; i < Q; ++i) f[i] = fin[p.pop_off[i]];
         }
         dead = boundary_path<Q>(p, f, fin, (long long)widx, x, y, z, lane, active, do_stream, nb);
     }
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(128, LBM_SPC_MINB) step_special_kernel(const _
     if (active && !skip_store) {
         float* __restrict__ fout = p.fout + idx;
 #pragma unroll
-        for (int i = 0; i < Q; ++i) fout[(long long)i * g.np] = f[i];
+        for (int i = 0; i < Q; ++i) fout[p.pop_off[i]] = f[i];
     }
 }
 

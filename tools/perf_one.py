@@ -15,3 +15,9 @@ elif name == "inplace":
     run("in-place periodic", 19, lb.EQ_FP32, (P, P, P), BB, False, False, engine=lb.ENGINE_INPLACE)
 elif name == "inplace_walls":
     run("in-place walls", 19, lb.EQ_FP32, (W, W, W), BB, False, False, engine=lb.ENGINE_INPLACE)
+elif name == "walls_yz":
+    run("general, walls y/z", 19, lb.EQ_FP32, (Z, W, W), BB, False, False)
+elif name == "walls_y":
+    run("general, walls y", 19, lb.EQ_FP32, (Z, W, Z), BB, False, False)
+elif name == "periodic":
+    run("general, periodic xyz", 19, lb.EQ_FP32, (P, P, P), BB, False, False)
