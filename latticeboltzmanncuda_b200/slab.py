@@ -77,6 +77,18 @@ class HaloExchange:
         return dist.batch_isend_irecv(p2p)
 
 
+def allreduce_sum(values, dist, device=None):
+    """sum of a small float64 vector over all ranks (mass, momentum[3], force[3] are reduced only
+    on the steps that ask for them; the step path itself has no collective besides the halo exchange).
+    `device` = the CUDA device for NCCL, None for a host tensor (gloo)."""
+    import torch
+    t = torch.as_tensor(np.asarray(values, np.float64).reshape(-1).copy())
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
 class _DevicePlane:
     """zero-copy view of a device plane for torch.as_tensor (CUDA array interface)"""
 
@@ -188,3 +200,28 @@ class SlabLattice:
             self.lattice.setFlowData(None)
         else:
             self.lattice.setFlowData(FlowData(((l, lo[1], lo[2]), (hgh, hi[1], hi[2])), flow))
+
+    # ---- diagnostics over the whole domain (one small all-reduce, only when asked for) -----------------
+    def _dev(self):
+        return self.torch.device("cuda", self.lattice.cfg.device)
+
+    def diagnostics(self):
+        """{"mass": sum rho, "momentum": sum rho u [3], "force": obstacle force [3]} of the global lattice: every
+        rank reduces its own slab on the device (lbm_mass / lbm_momentum / lbm_get_force), then one fp64
+        all-reduce of 7 numbers"""
+        self.stream.synchronize()
+        lat = self.lattice
+        loc = np.zeros(7, np.float64)
+        loc[0] = lat.mass()
+        loc[1:4] = lat.momentum()
+        if lat.m_reflectionData is not None:
+            r = lat.retrieve_reflection_data()
+            loc[4:7] = (r.x, r.y, r.z)
+        tot = allreduce_sum(loc, self.dist, self._dev())
+        return {"mass": float(tot[0]), "momentum": tot[1:4].copy(), "force": tot[4:7].copy()}
+
+    def mass(self):
+        return self.diagnostics()["mass"]
+
+    def momentum(self):
+        return self.diagnostics()["momentum"]

@@ -48,6 +48,8 @@ def _worker(rank, world, port, q, gx, Y, Z, bc_x, bc_yz, steps, overlap, f, soli
         slab.load_populations(np.ascontiguousarray(f[:, x0:x1]))
         slab.step(steps)
         np.save(out % rank, slab.lattice.retrieve_populations())
+        d = slab.diagnostics()                      # one fp64 all-reduce: the global sums, on every rank
+        np.save((out % rank) + ".diag.npy", np.concatenate([[d["mass"]], d["momentum"]]))
     finally:
         dist.destroy_process_group()
 
@@ -68,7 +70,11 @@ def test_two_slabs_equal_one_gpu(tmp_path, q, bc_x, bc_yz, overlap):
     one.load_populations(f)
     one.step(steps)
     want = one.retrieve_populations()
+    want_diag = np.concatenate([[one.mass()], one.momentum()])
     out = str(tmp_path / "slab_%d.npy")
     mp.spawn(_worker, args=(2, _free_port(), q, gx, Y, Z, bc_x, bc_yz, steps, overlap, f, solid, out), nprocs=2, join=True)
     got = np.concatenate([np.load(out % r) for r in range(2)], axis=1)
     assert np.array_equal(got, want)          # same kernel, same operands: bit-identical
+    for r in range(2):
+        got_diag = np.load((out % r) + ".diag.npy")
+        assert np.allclose(got_diag, want_diag, rtol=1e-10, atol=1e-9 * abs(want_diag[0]))   # fp64 sums, different order

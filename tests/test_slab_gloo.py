@@ -115,3 +115,36 @@ def test_decomposed_run_equals_single_domain(tmp_path, world, q, periodic_x, bc_
     mp.spawn(_worker, args=(world, _free_port(), q, gx, Y, Z, periodic_x, bc_yz, steps, f, solid, out), nprocs=world, join=True)
     got = np.concatenate([np.load(out % r) for r in range(world)], axis=1)
     assert np.array_equal(got, want)
+
+
+def _diag_worker(rank, world, port, gx, f_global, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from latticeboltzmanncuda_b200.slab import allreduce_sum
+        x0, x1 = slab_range(gx, rank, world)
+        loc = f_global[:, x0:x1].astype(np.float64)
+        q = loc.shape[0]
+        c = np.asarray(O.DIRECTIONS[:q], np.float64)
+        part = np.concatenate([[loc.sum()], [(loc * c[:, a, None, None, None]).sum() for a in range(3)]])
+        tot = allreduce_sum(part, dist)                 # host tensor over gloo; NCCL takes the same call with a device
+        np.save(out_path % rank, tot)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_global_diagnostics_are_the_sum_over_slabs(tmp_path, world):
+    """mass and momentum of the whole lattice = one fp64 all-reduce of the per-slab sums"""
+    gx, Y, Z, q = 10, 4, 5, 19
+    rng = np.random.default_rng(11)
+    f = rng.random((q, gx, Y, Z)).astype(np.float32)
+    out = str(tmp_path / "diag_%d.npy")
+    mp.spawn(_diag_worker, args=(world, _free_port(), gx, f, out), nprocs=world, join=True)
+    c = np.asarray(O.DIRECTIONS[:q], np.float64)
+    f64 = f.astype(np.float64)
+    want = np.array([f64.sum()] + [(f64 * c[:, a, None, None, None]).sum() for a in range(3)])
+    for r in range(world):
+        got = np.load(out % r)
+        assert np.allclose(got, want, rtol=1e-13, atol=1e-12)     # every rank holds the global sums

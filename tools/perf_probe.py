@@ -11,7 +11,11 @@ from latticeboltzmanncuda_b200.shapes import tapered_hexahedron_mask
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 30
-PEAK = 6546.2
+try:
+    import json
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    PEAK = 6650.0     # B200_PROFILING.md fallback
 
 
 def run(name, q, eq, bc, boundary, obstacle, source, moment=lb.MOMENT_STANDARD, engine=lb.ENGINE_AUTO):
