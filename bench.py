@@ -162,8 +162,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"            # keep NCCL's version banner off stdout: one JSON line only
+        # stdout carries ONE JSON line: NCCL writes its debug output (the version banner at WARN and above) to stdout
+        # unless told otherwise, so whatever level the caller asked for goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # halo transfers must get SM slots next to the interior kernel
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 

@@ -180,6 +180,51 @@ __device__ __noinline__ float moving_wall_term(const StepParams& p, int i, int x
     return 6.0f * w * ((float)c_dir[i][0] * u[0] + (float)c_dir[i][1] * u[1] + (float)c_dir[i][2] * u[2]);
 }
 
+// Launch shape of the general and special kernels; the defaults are the values measured best on B200 at 512^3
+// (profiles/r01_notes.md).  Variants for measurement are built with -D (latticeboltzmanncuda_b200/build.py).
+#ifndef LBM_GEN_WARPS
+#define LBM_GEN_WARPS 4        // z-words (warps) per block
+#endif
+#ifndef LBM_GEN_MINB
+#define LBM_GEN_MINB 8         // resident blocks per SM the register allocation aims at (64 registers; 10 and 12 measured slower)
+#endif
+#ifndef LBM_GEN_ROWS
+#define LBM_GEN_ROWS 8         // rows a warp walks (4, 8 or 16)
+#endif
+#ifndef LBM_GEN_PREFETCH
+#define LBM_GEN_PREFETCH 0     // experiment: per-lane prefetch.global.L2 of the next row's lines. Measured on B200: 2.08 -> 3.08 ms
+#endif                         // (19 divergent requests per instruction load the L1 request path; profiles/r01_notes.md)
+#ifndef LBM_SPC_PREFETCH
+#define LBM_SPC_PREFETCH 0     // the same for the next list entry of the special kernel: 0.35 -> 0.46 ms
+#endif
+#ifndef LBM_STREAM_HINTS
+#define LBM_STREAM_HINTS 0     // experiment: 1 = st.global.cs for population stores, 2 = also ld.global.cs for the pulls
+#endif
+#ifndef LBM_SPC_ENTRIES
+#define LBM_SPC_ENTRIES 1      // consecutive list entries a warp of the special kernel takes (1 = no look-ahead)
+#endif
+#ifndef LBM_SPC_MINB
+#define LBM_SPC_MINB 8          // 63 registers, no spills (10 blocks/SM = 48 registers spills in the pull loop)
+#endif
+
+// population loads / stores of the step kernels (LBM_STREAM_HINTS selects cache-streaming variants for measurement)
+__device__ __forceinline__ float ld_pop(const float* a)
+{
+#if LBM_STREAM_HINTS >= 2
+    return __ldcs(a);
+#else
+    return *a;
+#endif
+}
+__device__ __forceinline__ void st_pop(float* a, float v)
+{
+#if LBM_STREAM_HINTS >= 1
+    __stcs(a, v);
+#else
+    *a = v;
+#endif
+}
+
 // Pull f_i(x) <- f_i(x - c_i)  (SimCalcFuncs.cu:83-94, j = INVERSE[i] relabelled).
 // x and y edges are ghost planes / rows (filled by launch_fill_ghosts or left at zero); the z edge is
 // resolved here, by choosing the address the edge lane reads from, because a z ghost shares its row with
@@ -197,7 +242,7 @@ __device__ __forceinline__ void pull_populations(const StepParams& p, const floa
     if (!edge_word || p.bc[2] == 0) {
 #pragma unroll
         for (int i = 0; i < Q; ++i)
-            f[i] = fin[p.pull_off[i]];
+            f[i] = ld_pop(fin + p.pull_off[i]);
         return;
     }
     const bool lo = (z == 0), hi = (z == g.nz - 1);
@@ -210,7 +255,7 @@ __device__ __forceinline__ void pull_populations(const StepParams& p, const floa
             const bool outside = dir_c(i, 2) > 0 ? lo : hi;          // the cell this population comes from is beyond the z edge
             if (outside) a = wall ? p.pop_off[dir_inv(i)] : a + (dir_c(i, 2) > 0 ? g.nz : -g.nz);
         }
-        f[i] = fin[a];
+        f[i] = ld_pop(fin + a);
     }
     // ... then the moving-wall terms of the populations that bounced (edge lanes of moving-wall set-ups only)
     if (wall && p.wall_moving && (lo || hi)) {
@@ -241,7 +286,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
     else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
     float* __restrict__ fout = p.fout + idx;
 #pragma unroll
-    for (int i = 0; i < Q; ++i) fout[p.pop_off[i]] = f[i];
+    for (int i = 0; i < Q; ++i) st_pop(fout + p.pop_off[i], f[i]);
 }
 
 // General kernel.  Every 32-cell word of every interior row was classified when the geometry was set
@@ -255,21 +300,6 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
 //             (dead_mode 1) and nothing at all afterwards (dead_mode 2);
 //   special   skipped here: step_special_kernel walks the compact list of special words.
 enum : unsigned { CLS_ORDINARY = 0, CLS_DEAD = 1, CLS_SPECIAL = 2 };
-
-// Launch shape of the general and special kernels; the defaults are the values measured best on B200 at 512^3
-// (profiles/r01_notes.md).  Variants for measurement are built with -D (latticeboltzmanncuda_b200/build.py).
-#ifndef LBM_GEN_WARPS
-#define LBM_GEN_WARPS 4        // z-words (warps) per block
-#endif
-#ifndef LBM_GEN_MINB
-#define LBM_GEN_MINB 8         // resident blocks per SM the register allocation aims at (64 registers; 10 and 12 measured slower)
-#endif
-#ifndef LBM_GEN_ROWS
-#define LBM_GEN_ROWS 8         // rows a warp walks (4, 8 or 16)
-#endif
-#ifndef LBM_SPC_MINB
-#define LBM_SPC_MINB 8          // 63 registers, no spills (10 blocks/SM = 48 registers spills in the pull loop)
-#endif
 
 template <int Q, int MOMENT, bool EQ64, int ROWS_PER_WARP, bool SRC>
 __global__ void __launch_bounds__(32 * LBM_GEN_WARPS, LBM_GEN_MINB) step_general_kernel(const __grid_constant__ StepParams p)
@@ -297,11 +327,30 @@ __global__ void __launch_bounds__(32 * LBM_GEN_WARPS, LBM_GEN_MINB) step_general
         cw0 = v.x; cw1 = v.y;
     }
 
+#if LBM_GEN_PREFETCH
+    // ncu: 63 % of this kernel's stall samples sit on the first use of a pulled value (profiles/r01d_*): with one
+    // row of loads in flight per warp the kernel is bound by DRAM latency, not by issue or bandwidth.  Lane i < Q
+    // therefore owns population i's pull offset and, while the warp works on row r, asks L2 for the two 128-byte
+    // lines that population's pull of row r + 1 will touch (first and last lane's address): two instructions per
+    // row, no registers held across the collision besides the offset.
+    const long long my_off = lane < (unsigned)Q ? (do_stream ? p.pull_off[lane] : p.pop_off[lane]) : 0;
+#endif
+
 #pragma unroll 1
     for (int r = 0; r < ROWS_PER_WARP; ++r) {
         const int y = y0 + r;
         if (y >= g.ny) break;
         const unsigned cls = (unsigned)(((ROWS_PER_WARP > 8 && r >= 8) ? cw1 : cw0) >> (8 * (r & 7))) & 0xffu;
+#if LBM_GEN_PREFETCH
+        if (r + 1 < ROWS_PER_WARP && y + 1 < g.ny && lane < (unsigned)Q) {
+            const unsigned cn = (unsigned)(((ROWS_PER_WARP > 8 && r + 1 >= 8) ? cw1 : cw0) >> (8 * ((r + 1) & 7))) & 0xffu;
+            if (cn == CLS_ORDINARY || (cn == CLS_DEAD && !p.dead_mode)) {
+                const float* a = p.fin + (((long long)(x + 1) * g.yp + (y + 2)) * g.zp + (wi * 32 + PAD_Z)) + my_off;
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(a + 31));
+            }
+        }
+#endif
         if (cls == CLS_SPECIAL) continue;              // step_special_kernel owns these words
         const long long idx = ((long long)(x + 1) * g.yp + (y + 1)) * g.zp + (z + PAD_Z);
         float f[Q];
@@ -336,7 +385,7 @@ __global__ void __launch_bounds__(32 * LBM_GEN_WARPS, LBM_GEN_MINB) step_general
         if (active) {
             float* __restrict__ fout = p.fout + idx;
 #pragma unroll
-            for (int i = 0; i < Q; ++i) fout[p.pop_off[i]] = f[i];
+            for (int i = 0; i < Q; ++i) st_pop(fout + p.pop_off[i], f[i]);
         }
     }
 }
@@ -369,7 +418,7 @@ __device__ __forceinline__ void pull_bounce_back(const StepParams& p, const floa
             }
         }
         if (own) a = p.pop_off[dir_inv(i)];
-        f[i] = live ? fin[a] : 0.0f;
+        f[i] = live ? ld_pop(fin + a) : 0.0f;
     }
     if (p.force) {
 #pragma unroll
@@ -398,18 +447,48 @@ __global__ void __launch_bounds__(128, LBM_SPC_MINB) step_special_kernel(const _
 {
     const Geom& g = p.g;
     const unsigned lane = threadIdx.x & 31u;
-    // the launch covers the entries [special_k0, special_k0 + n_special) of the list: those of the planes [x0, x1)
-    const long long kl = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (kl >= p.n_special) return;
+    // the launch covers the entries [special_k0, special_k0 + n_special) of the list: those of the planes [x0, x1);
+    // a warp takes LBM_SPC_ENTRIES consecutive entries.  The list entry and the neighbourhood word of the next
+    // entry are fetched, and its population lines requested from L2, while the current entry is in flight:
+    // the kernel is latency-bound (two dependent loads before the first population load, ncu: long scoreboard).
+    const long long kfirst = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * LBM_SPC_ENTRIES;
+    if (kfirst >= p.n_special) return;
+    const bool do_stream = p.phases & PH_STREAM;
+#if LBM_SPC_ENTRIES > 1
+#if LBM_SPC_PREFETCH
+    const long long my_off = lane < (unsigned)Q ? (do_stream ? p.pull_off[lane] : p.pop_off[lane]) : 0;
+#endif
+    uint32_t widx_next = __ldg(p.special_list + p.special_k0 + kfirst);
+    uint32_t nb_next = __ldg(p.cellinfo + (p.special_k0 + kfirst) * 32 + lane);
+#pragma unroll 1
+    for (int e = 0; e < LBM_SPC_ENTRIES; ++e) {
+    const long long kl = kfirst + e;
+    if (kl >= p.n_special) break;
+    const long long k = p.special_k0 + kl;
+    const uint32_t widx = widx_next, nb = nb_next;
+    if (e + 1 < LBM_SPC_ENTRIES && kl + 1 < p.n_special) {
+        widx_next = __ldg(p.special_list + k + 1);
+        nb_next = __ldg(p.cellinfo + (k + 1) * 32 + lane);
+#if LBM_SPC_PREFETCH
+        if (lane < (unsigned)Q) {
+            const float* a = p.fin + (long long)widx_next * 32 + my_off;
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(a + 31));
+        }
+#endif
+    }
+#else
+    const long long kl = kfirst;
     const long long k = p.special_k0 + kl;
     const uint32_t widx = __ldg(p.special_list + k);          // mask-word index = padded cell index / 32
     const uint32_t nb = __ldg(p.cellinfo + k * 32 + lane);
+    {
+#endif
     const int w = (int)(widx % (uint32_t)g.wz);
     const uint32_t row = widx / (uint32_t)g.wz;
     const int x = (int)(row / (uint32_t)g.yp) - 1, y = (int)(row % (uint32_t)g.yp) - 1;
     const int z = w * 32 - PAD_Z + (int)lane;
     const bool active = z < g.nz;
-    const bool do_stream = p.phases & PH_STREAM;
     const bool edge_word = w == PAD_Z / 32 || w == PAD_Z / 32 + ((g.nz + 31) >> 5) - 1;
     const long long idx = (long long)widx * 32 + lane;
     const float* __restrict__ fin = p.fin + idx;
@@ -464,8 +543,9 @@ __global__ void __launch_bounds__(128, LBM_SPC_MINB) step_special_kernel(const _
     if (active && !skip_store) {
         float* __restrict__ fout = p.fout + idx;
 #pragma unroll
-        for (int i = 0; i < Q; ++i) fout[p.pop_off[i]] = f[i];
+        for (int i = 0; i < Q; ++i) st_pop(fout + p.pop_off[i], f[i]);
     }
+    }   // entries of this warp
 }
 
 // threads per block of the step kernel (tuning knob, LBM_BLOCK_THREADS = 64 / 128 / 256)
@@ -540,7 +620,7 @@ cudaError_t launch_step_tasks(const StepParams& p, cudaStream_t stream, cudaStre
     cudaError_t e = launch_step_general_r<Q, MOMENT, EQ64, LBM_GEN_ROWS>(p, stream, launches);   // cls_pitch is a multiple of 16
     if (e != cudaSuccess) return e;
     if (p.n_special > 0) {
-        const long long blocks = (p.n_special + 3) / 4;
+        const long long blocks = (p.n_special + 4 * LBM_SPC_ENTRIES - 1) / (4 * LBM_SPC_ENTRIES);
         cudaStream_t ss = stream_special ? stream_special : stream;
         step_special_kernel<Q, MOMENT, EQ64><<<(unsigned)blocks, 128, 0, ss>>>(p);
         if (launches) *launches += 1;

@@ -56,7 +56,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the JSON line only
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=dev)
 
@@ -103,6 +103,7 @@ def main():
         f0 = equilibrium(torch, one, z, z, z)
         del z
     del one
+    torch.cuda.empty_cache()          # hand the temporaries back before the library allocates its state
 
     engine = lb.ENGINE_INPLACE if args.engine == "inplace" else lb.ENGINE_PULL2
     if world == 1:
