@@ -273,36 +273,52 @@ int fill_ghosts(lbm_handle h, bool include_x)
 
 void fill_inplace(lbm_handle h, InplaceParams& ip)
 {
+    std::memset(&ip, 0, sizeof ip);
+    set_inplace_offsets(ip, h->g);
     ip.f = h->buf[0];
-    ip.g = h->g;
     ip.tau = h->cfg.tau;
     ip.inv_tau = 1.0f / h->cfg.tau;
     ip.parity = h->aa_parity;
     for (int a = 0; a < 3; ++a) ip.bc[a] = h->cfg.bc[a];
     std::memcpy(ip.wall_u, h->cfg.wall_u, sizeof ip.wall_u);
-    for (int i = 0; i < 27; ++i) {
-        const long long c = (long long)dir_c(i, 0) * h->g.plane + (long long)(dir_c(i, 1) * h->g.zp + dir_c(i, 2));
-        ip.pop_off[i] = (long long)i * h->g.np;
-        ip.pull_off[i] = (long long)dir_inv(i) * h->g.np - c;
-        ip.push_off[i] = (long long)i * h->g.np + c;
+    if (h->any_solid) {       // obstacles: the mask, the word classes and the special list of rebuild_special
+        ip.solid = h->solid;
+        ip.cls = h->cls;
+        ip.cls_pitch = h->cls_pitch;
+        ip.special_list = h->special_list;
+        ip.n_special = (long long)h->n_special;
+        ip.cellinfo = h->cellinfo;
+        ip.force = h->force_on ? h->force : nullptr;
     }
+    ip.src_on = h->src_on;
+    for (int a = 0; a < 3; ++a) { ip.src_lo[a] = h->src_lo[a]; ip.src_hi[a] = h->src_hi[a]; }
+    std::memcpy(ip.src_f, h->src_f, sizeof ip.src_f);
 }
 
 int inplace_only(lbm_handle h, const char* what)
 {
-    if (h->inplace) return fail(LBM_ERR_UNSUPPORTED, "%s is not available on the in-place engine (all-fluid lattices, fused steps, SoA transfers)", what);
+    if (h->inplace) return fail(LBM_ERR_UNSUPPORTED, "%s is not available on the in-place engine (bounce-back obstacles, box source, fused steps, SoA transfers)", what);
     return LBM_OK;
 }
 
 int one_step(lbm_handle h, unsigned phases)
 {
     if (h->inplace) {
-        const bool source_noop = !(phases & PH_SOURCE) || !h->src_on;
-        if (!(phases & PH_STREAM) || !(phases & PH_COLLIDE) || !source_noop)
+        if (!(phases & PH_STREAM) || !(phases & PH_COLLIDE))
             return fail(LBM_ERR_UNSUPPORTED, "the in-place engine runs fused stream + collide steps only");
         InplaceParams ip;
         fill_inplace(h, ip);
+        if (!(phases & PH_SOURCE)) ip.src_on = 0;
         int launched = 0;
+        if (h->aa_dirty) {
+            // first step after the mask or the state was set: solid cells hold zeros from here on
+            if (ip.solid) {
+                if (h->aa_parity != 0) return fail(LBM_ERR_STATE, "in-place engine: solid cells can only be cleared in the parked form");
+                CK(launch_inplace_zero_solid(ip, h->cfg.q, h->stream));
+                ++launched;
+            }
+            h->aa_dirty = false;
+        }
         CK(launch_inplace_step(ip, h->cfg.q, h->cfg.moment_mode, h->cfg.eq_precision == LBM_EQ_FP64, h->stream, &launched));
         h->launches += launched;
         h->aa_parity ^= 1;
@@ -575,6 +591,7 @@ LBM_API int lbm_upload_f_soa(lbm_handle h, const float* f)
     CK(cudaStreamSynchronize(h->stream));
     h->dead_dirty = 2;
     h->aa_parity = 0;
+    h->aa_dirty = true;
     return LBM_OK;
 }
 
@@ -617,8 +634,16 @@ LBM_API int lbm_set_solid_mask(lbm_handle h, const uint8_t* solid, int x_ghost_p
 {
     int rc = use(h);
     if (rc) return rc;
-    if (solid && (rc = inplace_only(h, "lbm_set_solid_mask"))) return rc;
-    if (h->inplace) return LBM_OK;
+    if (h->inplace) {
+        // obstacles on the single-buffer engine are half-way bounce-back; how a population is stored after an odd
+        // number of steps depends on the mask, so the mask may only change in the parked form
+        if (solid && h->cfg.boundary_mode != LBM_BOUNDARY_BOUNCE_BACK)
+            return fail(LBM_ERR_UNSUPPORTED, "the in-place engine takes a solid mask in bounce-back mode only (table reflection runs on the two-buffer engine)");
+        if (!solid && !h->solid) return LBM_OK;
+        if (h->aa_parity != 0)
+            return fail(LBM_ERR_STATE, "in-place engine: set the solid mask before stepping or after an even number of steps");
+        h->aa_dirty = true;
+    }
     const Geom& g = h->g;
     const size_t per = (size_t)g.ny * g.nz;
     const size_t n = per * (size_t)g.nx;
@@ -738,7 +763,6 @@ LBM_API int lbm_set_source(lbm_handle h, int kind, const int32_t lo[3], const in
     if (!h) return fail(LBM_ERR_INVALID, "null handle");
     if (kind == LBM_SOURCE_NONE) { h->src_on = 0; return LBM_OK; }
     if (kind != LBM_SOURCE_BOX || !lo || !hi || !f) return fail(LBM_ERR_INVALID, "bad source arguments");
-    if (h->inplace) return inplace_only(h, "lbm_set_source");
     h->src_on = 1;
     for (int a = 0; a < 3; ++a) { h->src_lo[a] = lo[a]; h->src_hi[a] = hi[a]; }
     for (int i = 0; i < 27; ++i) h->src_f[i] = (i < h->cfg.q) ? f[i] : 0.0f;

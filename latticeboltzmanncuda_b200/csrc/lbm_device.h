@@ -110,8 +110,33 @@ struct InplaceParams {
     long long pop_off[27];
     long long pull_off[27];
     long long push_off[27];
+    // obstacles (half-way bounce-back), shared with the two-buffer engine: padded bit mask, word classes, the
+    // sorted list of special words and their neighbourhood words (all nullptr / 0 on an all-fluid lattice)
+    const uint32_t* solid;
+    const uint8_t*  cls;
+    int   cls_pitch;
+    const uint32_t* special_list;
+    long long n_special;
+    const uint32_t* cellinfo;
+    double* force;            // FORCE_SLOTS x 3 partial sums of the momentum exchange, or nullptr
+    int   src_on;             // additive box source, applied after the collision
+    int   src_lo[3], src_hi[3];
+    float src_f[27];
 };
 
+// offsets of the in-place engine for a lattice of geometry g (everything else is left untouched)
+inline void set_inplace_offsets(InplaceParams& ip, const Geom& g)
+{
+    ip.g = g;
+    for (int i = 0; i < 27; ++i) {
+        const long long c = (long long)dir_c(i, 0) * g.plane + (long long)(dir_c(i, 1) * g.zp + dir_c(i, 2));
+        ip.pop_off[i] = (long long)i * g.np;
+        ip.pull_off[i] = (long long)dir_inv(i) * g.np - c;
+        ip.push_off[i] = (long long)i * g.np + c;
+    }
+}
+
+cudaError_t launch_inplace_zero_solid(const InplaceParams& p, int q, cudaStream_t stream);
 cudaError_t launch_inplace_step(const InplaceParams& p, int q, int moment, int eq64, cudaStream_t stream, int* launches);
 cudaError_t launch_inplace_scatter(const float* dense, float* f, const Geom& g, int q_index, int x0, int nxc, cudaStream_t stream);
 cudaError_t launch_inplace_gather(const InplaceParams& p, int q, float* dense, int q_index, int x0, int nxc, cudaStream_t stream);

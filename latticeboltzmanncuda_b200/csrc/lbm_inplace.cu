@@ -14,8 +14,16 @@
 //   periodic: the neighbour on the far side;
 //   wall    : half-way bounce-back -- the pull reads the cell's own slot i (= f*_inv(i)(x)), the push parks
 //             f*_i(x) in the cell's own slot inv(i); a moving wall adds 6 w (c . u_wall), rho_wall = 1.
-// Scope: all-fluid lattices (no solid mask, no reflection tables, no source), stream + collide fused, periodic
-// or wall edges.  Everything else runs on the two-buffer engine.
+// Obstacles (packed solid bitmask, half-way bounce-back) follow the same rule as a wall, cell by cell: a
+// population whose upstream neighbour x - c_i is solid is pulled from the cell's own slot i, and a population
+// whose downstream neighbour x + c_i is solid is parked in the cell's own slot inv(i) -- again the very slots
+// the cell read, so the update stays in place.  Solid cells are never read or written (they hold zeros).  The
+// word classes of the two-buffer engine are reused: ordinary words run the lean code, all-solid words cost
+// nothing, special words (a cell is solid or sees a solid cell) come from the compact list with their
+// neighbourhood words.  In either storage form the population that bounces into direction i at cell x sits in
+// A[i][x], so one small kernel over the special list sums the momentum exchange before the step.
+// Scope: bounce-back obstacles, additive box source, stream + collide fused, periodic or wall edges.  Reflection
+// tables, unfused phases, zero-inflow edges and slabs run on the two-buffer engine.
 #include "lbm_device.h"
 
 namespace lbm {
@@ -65,7 +73,28 @@ __device__ __forceinline__ Edge edge_lookup(const InplaceParams& p, int i, int x
     return e;
 }
 
-template <int Q, int MOMENT, bool EQ64>
+// solid flag of the padded cell (xpad, ypad, zpad); ghost cells hold the periodic images, wall ghosts are clear
+__device__ __forceinline__ bool solid_bit(const InplaceParams& p, int xpad, int ypad, int zpad)
+{
+    const uint32_t w = __ldg(p.solid + ((long long)xpad * p.g.yp + ypad) * p.g.wz + (zpad >> 5));
+    return (w >> (zpad & 31)) & 1u;
+}
+
+// additive source on the cells of the box (SimCalcFuncs.cu:200-215), after the collision like the two-buffer engine
+template <int Q>
+__device__ __forceinline__ void add_source(const InplaceParams& p, float (&f)[Q], int x, int y, int z)
+{
+    if (x >= p.src_lo[0] && x <= p.src_hi[0] && y >= p.src_lo[1] && y <= p.src_hi[1] &&
+        z >= p.src_lo[2] && z <= p.src_hi[2]) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) f[i] += p.src_f[i];
+    }
+}
+
+enum : unsigned { AA_ORDINARY = 0, AA_DEAD = 1, AA_SPECIAL = 2 };      // word classes, as in lbm_kernels.cu
+
+// EXTRA: the lattice has a solid mask and / or a source (kept out of the all-fluid instantiation)
+template <int Q, int MOMENT, bool EQ64, bool EXTRA>
 __global__ void __launch_bounds__(256, (Q == 19 && !EQ64) ? 6 : 4) aa_even_kernel(const __grid_constant__ InplaceParams p)
 {
     const Geom& g = p.g;
@@ -73,19 +102,24 @@ __global__ void __launch_bounds__(256, (Q == 19 && !EQ64) ? 6 : 4) aa_even_kerne
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int x = blockIdx.z;
     if (z >= g.nz || y >= g.ny) return;
+    if (EXTRA && p.solid) {
+        // a warp is 32 consecutive z of one row = one mask word (blockDim.x is a multiple of 32): one broadcast load
+        if (solid_bit(p, x + 1, y + 1, z + PAD_Z)) return;
+    }
     float* a = p.f + g.cell(x, y, z);
     float f[Q];
 #pragma unroll
     for (int i = 0; i < Q; ++i) f[i] = a[p.pop_off[i]];
     if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
     else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
+    if (EXTRA && p.src_on) add_source<Q>(p, f, x, y, z);
     asm volatile("" : "+l"(a));          // rebuild the Q addresses next to the stores instead of keeping them alive
 #pragma unroll
     for (int i = 0; i < Q; ++i) a[p.pop_off[dir_inv(i)]] = f[i];
 }
 
 // pull + collide + push of one cell that may sit on a domain edge of the axes in AXES
-template <int Q, int MOMENT, bool EQ64, int AXES>
+template <int Q, int MOMENT, bool EQ64, int AXES, bool EXTRA>
 __device__ __forceinline__ void aa_odd_edge_cell(const InplaceParams& p, float* a, int x, int y, int z)
 {
     const Geom& g = p.g;
@@ -97,6 +131,7 @@ __device__ __forceinline__ void aa_odd_edge_cell(const InplaceParams& p, float* 
     }
     if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
     else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
+    if (EXTRA && p.src_on) add_source<Q>(p, f, x, y, z);
     asm volatile("" : "+l"(a), "+r"(x), "+r"(y), "+r"(z));      // rebuild the addresses instead of keeping Q of them alive
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
@@ -112,8 +147,10 @@ __device__ __forceinline__ void aa_odd_edge_cell(const InplaceParams& p, float* 
 //           (periodic wrap / wall) for the populations with c_z != 0 of their first / last lane -- in the same
 //           launch, next to the rest of their row, so that the row is still one contiguous run in DRAM;
 //   MODE 2  the x and y faces, with the per-direction rules of all three axes.
-template <int Q, int MOMENT, bool EQ64, int MODE>
-__global__ void __launch_bounds__(128, (MODE == 0 && Q == 19 && !EQ64) ? 12 : 8) aa_odd_kernel(const __grid_constant__ InplaceParams p)
+// With geometry (EXTRA and a class array) both launches take the ordinary words only: all-solid words are
+// skipped and the special words are left to aa_odd_special_kernel.
+template <int Q, int MOMENT, bool EQ64, int MODE, bool EXTRA>
+__global__ void __launch_bounds__(128, (MODE == 0 && Q == 19 && !EQ64) ? (EXTRA ? 10 : 12) : 8) aa_odd_kernel(const __grid_constant__ InplaceParams p)
 {
     const Geom& g = p.g;
     const int wcount = (g.nz + 31) >> 5;
@@ -147,10 +184,13 @@ __global__ void __launch_bounds__(128, (MODE == 0 && Q == 19 && !EQ64) ? 12 : 8)
     }
     const int z = w * 32 + (int)(threadIdx.x & 31u);
     if (z >= g.nz) return;
+    if (EXTRA && p.cls) {                          // warp-uniform: one class byte per 32-cell word, resident in L2
+        if (__ldg(p.cls + ((long long)x * wcount + w) * p.cls_pitch + y) != AA_ORDINARY) return;
+    }
     float* a = p.f + g.cell(x, y, z);
     if constexpr (MODE == 0) {
         if (w == 0 || w == wcount - 1) {           // warp-uniform
-            aa_odd_edge_cell<Q, MOMENT, EQ64, 4>(p, a, x, y, z);
+            aa_odd_edge_cell<Q, MOMENT, EQ64, 4, EXTRA>(p, a, x, y, z);
             return;
         }
         float f[Q];
@@ -162,12 +202,144 @@ __global__ void __launch_bounds__(128, (MODE == 0 && Q == 19 && !EQ64) ? 12 : 8)
         for (int i = 0; i < Q; ++i) f[i] = a[p.pull_off[i]];
         if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
         else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
+        if (EXTRA && p.src_on) add_source<Q>(p, f, x, y, z);
         asm volatile("" : "+l"(a));
 #pragma unroll
         for (int i = 0; i < Q; ++i) a[p.push_off[i]] = f[i];
     } else {
-        aa_odd_edge_cell<Q, MOMENT, EQ64, 7>(p, a, x, y, z);
+        aa_odd_edge_cell<Q, MOMENT, EQ64, 7, EXTRA>(p, a, x, y, z);
     }
+}
+
+// pull + collide + push of one live cell of a special word.  nb = the cell's neighbourhood word (bit
+// nb_bit(dx,dy,dz) = solid flag of that neighbour, ghost bits = periodic images).  A solid neighbour wins over
+// everything else (own slot, no term); then the domain-edge rule of the axes in AXES (wall: own slot + term,
+// periodic: wrapped neighbour); AXES = 0 is the word away from every edge, with constant-bank offsets only.
+template <int Q, int MOMENT, bool EQ64, int AXES>
+__device__ __forceinline__ void aa_odd_geo_cell(const InplaceParams& p, float* a, int x, int y, int z, uint32_t nb)
+{
+    const Geom& g = p.g;
+    float f[Q];
+    f[0] = a[p.pop_off[0]];
+#pragma unroll
+    for (int i = 1; i < Q; ++i) {
+        const bool own = (nb >> nb_bit(-dir_c(i, 0), -dir_c(i, 1), -dir_c(i, 2))) & 1u;      // x - c_i is solid
+        if constexpr (AXES == 0) {
+            f[i] = a[own ? p.pop_off[i] : p.pull_off[i]];
+        } else {
+            const Edge e = edge_lookup<Q, AXES>(p, i, x, y, z, -1);
+            const bool self = own || e.kind != 0;
+            const float v = a[self ? p.pop_off[i] : (long long)dir_inv(i) * g.np + e.off];
+            f[i] = (!own && e.kind != 0) ? v + e.term : v;
+        }
+    }
+    if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
+    else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
+    if (p.src_on) add_source<Q>(p, f, x, y, z);
+    asm volatile("" : "+l"(a), "+r"(x), "+r"(y), "+r"(z), "+r"(nb));
+    a[p.pop_off[0]] = f[0];
+#pragma unroll
+    for (int i = 1; i < Q; ++i) {
+        const bool own = (nb >> nb_bit(dir_c(i, 0), dir_c(i, 1), dir_c(i, 2))) & 1u;         // x + c_i is solid
+        if constexpr (AXES == 0) {
+            a[own ? p.pop_off[dir_inv(i)] : p.push_off[i]] = f[i];
+        } else {
+            const Edge e = edge_lookup<Q, AXES>(p, i, x, y, z, +1);
+            const bool self = own || e.kind != 0;
+            a[self ? p.pop_off[dir_inv(i)] : (long long)i * g.np + e.off] = (!own && e.kind != 0) ? f[i] + e.term : f[i];
+        }
+    }
+}
+
+// odd step of the special words: one warp per entry of the compact list (sorted, so neighbouring warps touch
+// neighbouring rows); solid and out-of-range lanes do nothing.  Which edge rules a word needs is warp-uniform.
+template <int Q, int MOMENT, bool EQ64>
+__global__ void __launch_bounds__(128, 8) aa_odd_special_kernel(const __grid_constant__ InplaceParams p)
+{
+    const Geom& g = p.g;
+    const unsigned lane = threadIdx.x & 31u;
+    const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= p.n_special) return;
+    const uint32_t widx = __ldg(p.special_list + k);          // mask-word index = padded cell index / 32
+    const uint32_t nb = __ldg(p.cellinfo + k * 32 + lane);
+    const int wpad = (int)(widx % (uint32_t)g.wz);
+    const uint32_t row = widx / (uint32_t)g.wz;
+    const int x = (int)(row / (uint32_t)g.yp) - 1, y = (int)(row % (uint32_t)g.yp) - 1;
+    const int w = wpad - PAD_Z / 32;
+    const int z = w * 32 + (int)lane;
+    if (z >= g.nz || ((nb >> nb_bit(0, 0, 0)) & 1u)) return;
+    float* a = p.f + (long long)widx * 32 + lane;
+    const int wcount = (g.nz + 31) >> 5;
+    if (x == 0 || x == g.nx - 1 || y == 0 || y == g.ny - 1) aa_odd_geo_cell<Q, MOMENT, EQ64, 7>(p, a, x, y, z, nb);
+    else if (w == 0 || w == wcount - 1)                     aa_odd_geo_cell<Q, MOMENT, EQ64, 4>(p, a, x, y, z, nb);
+    else                                                    aa_odd_geo_cell<Q, MOMENT, EQ64, 0>(p, a, x, y, z, nb);
+}
+
+// Momentum handed to the obstacle cells by the coming step (either storage form): population i of a live cell
+// whose upstream neighbour is solid is f*_inv(i)(x) coming back, and it sits in A[i][x]; the obstacle takes
+// -c_i * 2 * that value (the two-buffer engine's and the oracle's sum, oracle/lbm_oracle.c lbo_step_soa).
+template <int Q>
+__global__ void __launch_bounds__(128) aa_force_kernel(const __grid_constant__ InplaceParams p)
+{
+    const Geom& g = p.g;
+    const unsigned lane = threadIdx.x & 31u;
+    const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= p.n_special) return;
+    const uint32_t widx = __ldg(p.special_list + k);
+    const uint32_t nb = __ldg(p.cellinfo + k * 32 + lane);
+    const int z = ((int)(widx % (uint32_t)g.wz) - PAD_Z / 32) * 32 + (int)lane;
+    const bool live = z < g.nz && !((nb >> nb_bit(0, 0, 0)) & 1u);
+    const float* a = p.f + (long long)widx * 32 + lane;
+    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+    bool has_force = false;
+    if (live && (nb & 0x7ffffffu)) {
+#pragma unroll
+        for (int i = 1; i < Q; ++i) {
+            if ((nb >> nb_bit(-dir_c(i, 0), -dir_c(i, 1), -dir_c(i, 2))) & 1u) {
+                const float back = a[p.pop_off[i]];
+                const float m = back + back;
+                fx -= (float)dir_c(i, 0) * m;
+                fy -= (float)dir_c(i, 1) * m;
+                fz -= (float)dir_c(i, 2) * m;
+                has_force = true;
+            }
+        }
+    }
+    double* slot = p.force + 3 * ((unsigned)(widx >> 2) % FORCE_SLOTS);
+#if defined(LBM_HOST_EMULATION)
+    if (has_force) {                    // (the CPU test harness runs lanes one after the other: no shuffles)
+        atomicAdd(slot + 0, (double)fx); atomicAdd(slot + 1, (double)fy); atomicAdd(slot + 2, (double)fz);
+    }
+#else
+    if (__any_sync(0xffffffffu, has_force)) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o);
+            fy += __shfl_xor_sync(0xffffffffu, fy, o);
+            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        }
+        if (lane == 0) {
+            atomicAdd(slot + 0, (double)fx);
+            atomicAdd(slot + 1, (double)fy);
+            atomicAdd(slot + 2, (double)fz);
+        }
+    }
+#endif
+}
+
+// zero the populations of the solid cells (once after the mask or the state was set: from then on nothing
+// reads or writes them, and the state reads back as the two-buffer engine's, which writes zeros there)
+template <int Q>
+__global__ void aa_zero_solid_kernel(const __grid_constant__ InplaceParams p)
+{
+    const Geom& g = p.g;
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, x = blockIdx.z;
+    if (z >= g.nz) return;
+    if (!solid_bit(p, x + 1, y + 1, z + PAD_Z)) return;
+    float* a = p.f + g.cell(x, y, z);
+#pragma unroll
+    for (int i = 0; i < Q; ++i) a[p.pop_off[i]] = 0.0f;
 }
 
 // f*_i(x) from either storage form
@@ -177,6 +349,12 @@ __device__ __forceinline__ float aa_fetch(const InplaceParams& p, int i, int x, 
     const Geom& g = p.g;
     const float* a = p.f + g.cell(x, y, z);
     if (p.parity == 0) return a[(long long)dir_inv(i) * g.np];
+    if (p.solid) {
+        // solid cells are never touched (parked form, zeros); a population that bounced off a solid neighbour
+        // is parked in the cell's own opposite slot
+        if (solid_bit(p, x + 1, y + 1, z + PAD_Z)) return a[(long long)dir_inv(i) * g.np];
+        if (solid_bit(p, x + 1 + dir_c(i, 0), y + 1 + dir_c(i, 1), z + PAD_Z + dir_c(i, 2))) return a[(long long)dir_inv(i) * g.np];
+    }
     const Edge e = edge_lookup<Q>(p, i, x, y, z, +1);
     // a population that bounced off a wall is parked in the opposite slot with the wall term already added
     return (e.kind == 0) ? a[(long long)i * g.np + e.off] : a[(long long)dir_inv(i) * g.np] - e.term;
@@ -264,31 +442,40 @@ __global__ void __launch_bounds__(256) aa_mass_kernel(const __grid_constant__ In
     }
 }
 
-template <int Q, int MOMENT, bool EQ64>
+template <int Q, int MOMENT, bool EQ64, bool EXTRA>
 cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, int* launches)
 {
     const Geom& g = p.g;
     int n = 0;
+    const unsigned special_blocks = (unsigned)((p.n_special + 3) / 4);
+    if (EXTRA && p.force && p.n_special > 0) {      // momentum exchange of this step, read before anything moves
+        aa_force_kernel<Q><<<special_blocks, 128, 0, stream>>>(p);
+        ++n;
+    }
     if (p.parity == 0) {        // parked form -> pull / push
         const int wcount = (g.nz + 31) / 32;
         if (g.nx > 2 && g.ny > 2) {
             dim3 grid((wcount + 3) / 4, g.ny - 2, g.nx - 2);
-            aa_odd_kernel<Q, MOMENT, EQ64, 0><<<grid, 128, 0, stream>>>(p);
+            aa_odd_kernel<Q, MOMENT, EQ64, 0, EXTRA><<<grid, 128, 0, stream>>>(p);
             ++n;
         }
         const long long x2 = g.nx < 2 ? g.nx : 2, y2 = g.ny < 2 ? g.ny : 2;
         const long long xi = g.nx - x2;
         // when there is no interior box (nx or ny <= 2) the faces are the whole lattice
         const long long warps = x2 * g.ny * wcount + xi * y2 * wcount;
-        aa_odd_kernel<Q, MOMENT, EQ64, 2><<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(p);
+        aa_odd_kernel<Q, MOMENT, EQ64, 2, EXTRA><<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(p);
         ++n;
+        if (EXTRA && p.cls && p.n_special > 0) {
+            aa_odd_special_kernel<Q, MOMENT, EQ64><<<special_blocks, 128, 0, stream>>>(p);
+            ++n;
+        }
     } else {                    // arrived form -> local
         int bz = ((g.nz + 31) / 32) * 32;
         if (bz > 128) bz = 128;
         int by = 128 / bz;
         if (by > g.ny) by = g.ny;
         dim3 block(bz, by, 1), grid((g.nz + bz - 1) / bz, (g.ny + by - 1) / by, g.nx);
-        aa_even_kernel<Q, MOMENT, EQ64><<<grid, block, 0, stream>>>(p);
+        aa_even_kernel<Q, MOMENT, EQ64, EXTRA><<<grid, block, 0, stream>>>(p);
         ++n;
     }
     if (launches) *launches += n;
@@ -298,8 +485,14 @@ cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, int* launches)
 template <int Q>
 cudaError_t launch_q(const InplaceParams& p, int moment, int eq64, cudaStream_t s, int* n)
 {
-    if (moment == 0) return eq64 ? launch_t<Q, 0, true>(p, s, n) : launch_t<Q, 0, false>(p, s, n);
-    return eq64 ? launch_t<Q, 1, true>(p, s, n) : launch_t<Q, 1, false>(p, s, n);
+    // the all-fluid, source-free lattice keeps its own instantiation (no class or mask look-ups at all)
+    const bool extra = p.solid != nullptr || p.src_on;
+    if (extra) {
+        if (moment == 0) return eq64 ? launch_t<Q, 0, true, true>(p, s, n) : launch_t<Q, 0, false, true>(p, s, n);
+        return eq64 ? launch_t<Q, 1, true, true>(p, s, n) : launch_t<Q, 1, false, true>(p, s, n);
+    }
+    if (moment == 0) return eq64 ? launch_t<Q, 0, true, false>(p, s, n) : launch_t<Q, 0, false, false>(p, s, n);
+    return eq64 ? launch_t<Q, 1, true, false>(p, s, n) : launch_t<Q, 1, false, false>(p, s, n);
 }
 
 }  // namespace
@@ -307,6 +500,15 @@ cudaError_t launch_q(const InplaceParams& p, int moment, int eq64, cudaStream_t 
 cudaError_t launch_inplace_step(const InplaceParams& p, int q, int moment, int eq64, cudaStream_t stream, int* launches)
 {
     return q == 27 ? launch_q<27>(p, moment, eq64, stream, launches) : launch_q<19>(p, moment, eq64, stream, launches);
+}
+
+cudaError_t launch_inplace_zero_solid(const InplaceParams& p, int q, cudaStream_t stream)
+{
+    if (!p.solid) return cudaSuccess;
+    dim3 grid((p.g.nz + 127) / 128, p.g.ny, p.g.nx);
+    if (q == 27) aa_zero_solid_kernel<27><<<grid, 128, 0, stream>>>(p);
+    else         aa_zero_solid_kernel<19><<<grid, 128, 0, stream>>>(p);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_inplace_scatter(const float* dense, float* f, const Geom& g, int q_index, int x0, int nxc, cudaStream_t stream)

@@ -17,6 +17,7 @@ struct lbm_lattice_s {
     int cur = 0;
     bool inplace = false;            // single-buffer AA engine: only buf[0] exists
     int aa_parity = 0;
+    bool aa_dirty = false;           // in-place engine: the solid cells have not been cleared since the mask / state was set
     bool pending_commit = false;
     bool bulk_used = false;
     unsigned pending_phases = 0;

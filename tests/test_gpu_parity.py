@@ -458,12 +458,100 @@ def test_inplace_engine_equals_two_buffer_engine(q, eq, bc, steps):
         assert np.allclose(a, b, rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("q", [19, 27])
+@pytest.mark.parametrize("bc", [(1, 1, 1), (2, 2, 2), (1, 2, 2), (2, 1, 2)])
+@pytest.mark.parametrize("shape", [(14, 12, 40), (9, 8, 130)])
+def test_inplace_engine_with_obstacles(q, bc, shape):
+    """bounce-back obstacles, the plane source and the momentum exchange on ONE copy of the populations: after every
+    step (either storage form) the state, the force and the moments are the two-buffer engine's and the oracle's"""
+    X, Y, Z = shape
+    rng = np.random.default_rng(23)
+    solid = (rng.random((X, Y, Z)) < (0.08 if Z < 100 else 0.0)).astype(np.uint8)
+    solid[3:6, 2:6, 30:(36 if Z < 100 else 100)] = 1       # the long block makes all-solid words, ordinary words remain
+    solid[0, 4, Z // 2] = 1; solid[X - 1, Y - 1, Z - 1] = 1 # cells on faces and in a corner: images across every edge
+    f = soa_state(q, X, Y, Z, 29, solid)
+    wall_u = np.zeros((6, 3), np.float32)
+    wall_u[3] = (0.03, 0.0, 0.01); wall_u[4] = (0.0, 0.02, 0.0)
+    kw = dict(tau=0.65, q=q, bc=bc, wall_u=wall_u, moment_mode=lb.MOMENT_STANDARD, eq_precision=lb.EQ_FP32,
+              boundary_mode=lb.BOUNDARY_BOUNCE_BACK)
+    flow = np.zeros(27, np.float32); flow[:q] = 1e-3 * (1 + np.arange(q))
+    src = lb.FlowData(((0, None, None), (0, None, None)), flow)          # the plane x == 0, like the CLI
+    lats = []
+    for engine in (lb.ENGINE_PULL2, lb.ENGINE_INPLACE):
+        lat = make(X, Y, Z, engine=engine, **kw)
+        lat.set_solid_mask(solid)
+        lat.load_populations(f)
+        lat.setReflectionData(lb.ReflectionData())
+        lats.append(lat)
+    two, one = lats
+    assert one.layout().n_buffers == 1
+    st1, st2 = one.stats(), two.stats()
+    assert (st1["words_dead"], st1["words_special"]) == (st2["words_dead"], st2["words_special"])
+    if Z > 100:
+        assert st1["words_dead"] > 0 and st1["words_special"] > 0 and st1["words_total"] > 2 * st1["words_special"]
+    force = np.zeros(3, np.float64)
+    state = f
+    for step in range(1, 6):
+        two.step(1); one.step(1)
+        state = O.step_soa(state, X, Y, Z, q, 0.65, bc=bc, wall_u=wall_u, solid=solid, moment=O.MOMENT_STANDARD, eq64=False,
+                           steps=1, force=force)
+        got = one.retrieve_populations()
+        assert rel_err(got, two.retrieve_populations()) <= 2e-6, "step %d" % step
+        assert rel_err(got, state) <= REL, "step %d" % step
+        assert np.all(got[:, solid.astype(bool)] == 0)
+        r1, r2 = one.retrieve_reflection_data(), two.retrieve_reflection_data()
+        assert np.allclose([r1.x, r1.y, r1.z], force, rtol=1e-4, atol=1e-4)
+        assert np.allclose([r1.x, r1.y, r1.z], [r2.x, r2.y, r2.z], rtol=1e-4, atol=1e-4)
+    assert one.mass() == pytest.approx(two.mass(), rel=1e-6)
+    for a, b in zip(one.moments(), two.moments()):
+        assert np.allclose(a, b, rtol=1e-4, atol=1e-6)
+    assert np.array_equal(one.get_solid_mask(), solid)
+    # the source: both engines add it after the collision to the live cells of the box
+    for lat in lats:
+        lat.setFlowData(src)
+    two.step(4); one.step(4)
+    assert rel_err(one.retrieve_populations(), two.retrieve_populations()) <= 2e-6
+    two.step(3); one.step(3)
+    assert rel_err(one.retrieve_populations(), two.retrieve_populations()) <= 4e-6
+
+
+def test_inplace_obstacle_conserves_mass_256():
+    """size-independent property at a size the oracle does not reach: closed box with a body, mass to round-off"""
+    from latticeboltzmanncuda_b200.shapes import tapered_hexahedron_mask
+    n = 256
+    solid = tapered_hexahedron_mask(n, n, n)
+    w = O.weights(19).astype(np.float32)
+    f = np.broadcast_to(w[:, None, None, None], (19, n, n, n)).copy()
+    f[6] *= 1.05; f[1] *= 0.95
+    f[:, solid.astype(bool)] = 0
+    lat = make(n, n, n, tau=0.6, q=19, bc=(1, 2, 2), moment_mode=lb.MOMENT_STANDARD, eq_precision=lb.EQ_FP32,
+               boundary_mode=lb.BOUNDARY_BOUNCE_BACK, engine=lb.ENGINE_INPLACE)
+    lat.set_solid_mask(solid)
+    lat.load_populations(f)
+    m0 = lat.mass()
+    assert m0 == pytest.approx(f.sum(dtype=np.float64), rel=1e-9)
+    lat.step(41)
+    assert lat.mass() == pytest.approx(m0, rel=1e-6)
+    rho = lat.moments()[0]
+    assert np.all(rho[solid.astype(bool)] == 0) and rho[~solid.astype(bool)].min() > 0.5
+
+
 def test_inplace_engine_refuses_what_it_cannot_do():
     with pytest.raises(lb.LbmError):
         make(8, 8, 8, engine=lb.ENGINE_INPLACE)                          # zero-inflow edges (the default)
     lat = make(8, 8, 8, engine=lb.ENGINE_INPLACE, bc=(1, 1, 1))
     with pytest.raises(lb.LbmError):
-        lat.set_solid_mask(np.ones((8, 8, 8), np.uint8))
+        lat.set_solid_mask(np.ones((8, 8, 8), np.uint8))                 # table-reflection mode (the default)
+    with pytest.raises(lb.LbmError):
+        lat.set_reflection_tables(np.zeros(1, O.REFLECTION_VALUES), [3])
+    bb = make(8, 8, 8, engine=lb.ENGINE_INPLACE, bc=(1, 1, 1), boundary_mode=lb.BOUNDARY_BOUNCE_BACK)
+    one_cell = np.zeros((8, 8, 8), np.uint8); one_cell[4, 4, 4] = 1
+    bb.set_solid_mask(one_cell)
+    bb.step(1)
+    with pytest.raises(lb.LbmError):
+        bb.set_solid_mask(one_cell)                                      # pushed form: the mask decides where populations sit
+    bb.step(1)
+    bb.set_solid_mask(one_cell)
     with pytest.raises(lb.LbmError):
         lat.simulateStreaming()                                          # fused steps only
     with pytest.raises(lb.LbmError):

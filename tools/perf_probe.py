@@ -26,10 +26,12 @@ def run(name, q, eq, bc, boundary, obstacle, source, moment=lb.MOMENT_STANDARD, 
     f = np.empty((q, S, S, S), np.float32)
     for i in range(q):
         f[i] = w[i]
+    live = S ** 3
     if obstacle:
         solid = tapered_hexahedron_mask(S, S, S)
         f[:, solid.astype(bool)] = 0
         lat.set_solid_mask(solid)
+        live -= int(solid.sum())
     lat.load_populations(f)
     del f
     if source:
@@ -39,7 +41,7 @@ def run(name, q, eq, bc, boundary, obstacle, source, moment=lb.MOMENT_STANDARD, 
     lat.sync()
     ms, launches = lat.step_timed(K)
     mlups = S ** 3 * K / (ms * 1e-3) / 1e6
-    gbs = mlups * 1e6 * 2 * q * 4 / 1e9
+    gbs = live * K / (ms * 1e-3) * 2 * q * 4 / 1e9        # algorithmic bytes of the live (non-solid) cells
     st = lat.stats()
     name = "%s [dead %.0f%% special %.1f%%]" % (name, 100.0 * st["words_dead"] / st["words_total"], 100.0 * st["words_special"] / st["words_total"])
     print("%-44s %8.0f MLUPS %7.0f GB/s %5.1f%% of %.0f  (%.3f ms/step, %d launches)" %
@@ -63,6 +65,10 @@ if which in ("all", "inplace"):
     run("q19 fp32 IN-PLACE periodic xyz (1 buffer)", 19, lb.EQ_FP32, (P, P, P), BB, False, False, engine=lb.ENGINE_INPLACE)
     run("q19 fp32 IN-PLACE walls xyz (1 buffer)", 19, lb.EQ_FP32, (W, W, W), BB, False, False, engine=lb.ENGINE_INPLACE)
     run("q27 fp32 IN-PLACE periodic xyz (1 buffer)", 27, lb.EQ_FP32, (P, P, P), BB, False, False, engine=lb.ENGINE_INPLACE)
+if which in ("all", "inplace", "inplace-obstacle"):
+    run("q19 fp32 two-buffer obstacle+walls+source, periodic x", 19, lb.EQ_FP32, (P, W, W), BB, True, True)
+    run("q19 fp32 IN-PLACE obstacle+walls+source (1 buffer)", 19, lb.EQ_FP32, (P, W, W), BB, True, True, engine=lb.ENGINE_INPLACE)
+    run("q19 fp32 IN-PLACE obstacle only, periodic xyz", 19, lb.EQ_FP32, (P, P, P), BB, True, False, engine=lb.ENGINE_INPLACE)
 if which in ("all",):
     run("q19 fp32 periodic xyz (3 ghost fills)", 19, lb.EQ_FP32, (P, P, P), BB, False, False)
     run("q27 fp32 fast", 27, lb.EQ_FP32, (Z, Z, Z), BB, False, False)
