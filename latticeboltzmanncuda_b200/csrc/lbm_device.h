@@ -110,6 +110,8 @@ struct InplaceParams {
     long long pop_off[27];
     long long pull_off[27];
     long long push_off[27];
+    long long park_off[27];   // = pop_off[inv(i)]: where the even step parks population i (its own array, so that the row
+                              // loop's loads and stores do not share offsets the compiler then keeps in registers)
     // obstacles (half-way bounce-back), shared with the two-buffer engine: padded bit mask, word classes, the
     // sorted list of special words and their neighbourhood words (all nullptr / 0 on an all-fluid lattice)
     const uint32_t* solid;
@@ -133,6 +135,7 @@ inline void set_inplace_offsets(InplaceParams& ip, const Geom& g)
         ip.pop_off[i] = (long long)i * g.np;
         ip.pull_off[i] = (long long)dir_inv(i) * g.np - c;
         ip.push_off[i] = (long long)i * g.np + c;
+        ip.park_off[i] = (long long)dir_inv(i) * g.np;
     }
 }
 

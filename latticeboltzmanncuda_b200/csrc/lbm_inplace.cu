@@ -26,6 +26,11 @@
 // tables, unfused phases, zero-inflow edges and slabs run on the two-buffer engine.
 #include "lbm_device.h"
 
+// measurement knob (python -m latticeboltzmanncuda_b200.build --variant NAME -DMACRO=VALUE)
+#ifndef LBM_AA_ODD_MINB
+#define LBM_AA_ODD_MINB 12      // blocks/SM of the D3Q19 fp32 odd interior kernel with obstacles (40 registers, no spills)
+#endif
+
 namespace lbm {
 
 namespace {
@@ -103,7 +108,8 @@ __global__ void __launch_bounds__(256, (Q == 19 && !EQ64) ? 6 : 4) aa_even_kerne
     const int x = blockIdx.z;
     if (z >= g.nz || y >= g.ny) return;
     if (EXTRA && p.solid) {
-        // a warp is 32 consecutive z of one row = one mask word (blockDim.x is a multiple of 32): one broadcast load
+        // a warp is 32 consecutive z of one row = one 32-cell word (blockDim.x is a multiple of 32)
+        // (one broadcast load of the mask word; going through the L2-resident class byte first measured the same)
         if (solid_bit(p, x + 1, y + 1, z + PAD_Z)) return;
     }
     float* a = p.f + g.cell(x, y, z);
@@ -141,6 +147,60 @@ __device__ __forceinline__ void aa_odd_edge_cell(const InplaceParams& p, float* 
     }
 }
 
+// pull + collide + push of a cell of the first or last z-word of an interior row: only the z rule applies, and only
+// to the populations with c_z != 0 of the one lane that sits on the edge.  Everything else is the plain code
+// (constant-bank offsets): the generic edge_lookup costs ~4x the instructions of a plain word, and with one edge
+// word in every other block the kernel waited for those warps (ncu: 570 warp instructions per word on average).
+template <int Q, int MOMENT, bool EQ64, bool EXTRA>
+__device__ __forceinline__ void aa_odd_zedge_cell(const InplaceParams& p, float* a, int x, int y, int z)
+{
+    const Geom& g = p.g;
+    const bool lo = z == 0, hi = z == g.nz - 1;
+    const bool wall = p.bc[2] == 2;
+    float f[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        long long off = p.pull_off[i];
+        if (dir_c(i, 2) != 0) {
+            const bool outside = dir_c(i, 2) > 0 ? lo : hi;           // x - c_i lies beyond the z edge
+            if (outside) off = wall ? p.pop_off[i] : off + (dir_c(i, 2) > 0 ? g.nz : -g.nz);
+        }
+        f[i] = a[off];
+    }
+    if (wall && (lo || hi)) {       // moving-wall terms of the populations that came back from the wall
+#pragma unroll
+        for (int i = 1; i < Q; ++i) {
+            if (dir_c(i, 2) != 0 && (dir_c(i, 2) > 0 ? lo : hi)) {
+                const float* u = p.wall_u[dir_c(i, 2) > 0 ? 4 : 5];
+                f[i] += 6.0f * (float)dir_weight<Q>(i) * 1.0f *
+                        ((float)dir_c(i, 0) * u[0] + (float)dir_c(i, 1) * u[1] + (float)dir_c(i, 2) * u[2]);
+            }
+        }
+    }
+    if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
+    else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
+    if (EXTRA && p.src_on) add_source<Q>(p, f, x, y, z);
+    asm volatile("" : "+l"(a), "+r"(z));
+    const bool lo2 = z == 0, hi2 = z == g.nz - 1;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        long long off = p.push_off[i];
+        float v = f[i];
+        if (dir_c(i, 2) != 0) {
+            const bool outside = dir_c(i, 2) < 0 ? lo2 : hi2;         // x + c_i lies beyond the z edge
+            if (outside) {
+                off = wall ? p.park_off[i] : off + (dir_c(i, 2) < 0 ? g.nz : -g.nz);
+                if (wall) {
+                    const float* u = p.wall_u[dir_c(i, 2) < 0 ? 4 : 5];
+                    v += 6.0f * (float)dir_weight<Q>(i) * -1.0f *
+                         ((float)dir_c(i, 0) * u[0] + (float)dir_c(i, 1) * u[1] + (float)dir_c(i, 2) * u[2]);
+                }
+            }
+        }
+        a[off] = v;
+    }
+}
+
 // Two launches cover the lattice, each thread touching only its own slots (no ordering between them):
 //   MODE 0  the interior box, rows 1..ny-2 of planes 1..nx-2: a block owns 4 consecutive z-words of a row.  Words
 //           away from the z edge run plain offsets (lean code); the first and last word of the row take the z rule
@@ -150,7 +210,7 @@ __device__ __forceinline__ void aa_odd_edge_cell(const InplaceParams& p, float* 
 // With geometry (EXTRA and a class array) both launches take the ordinary words only: all-solid words are
 // skipped and the special words are left to aa_odd_special_kernel.
 template <int Q, int MOMENT, bool EQ64, int MODE, bool EXTRA>
-__global__ void __launch_bounds__(128, (MODE == 0 && Q == 19 && !EQ64) ? (EXTRA ? 10 : 12) : 8) aa_odd_kernel(const __grid_constant__ InplaceParams p)
+__global__ void __launch_bounds__(128, (MODE == 0 && Q == 19 && !EQ64) ? (EXTRA ? LBM_AA_ODD_MINB : 12) : 8) aa_odd_kernel(const __grid_constant__ InplaceParams p)
 {
     const Geom& g = p.g;
     const int wcount = (g.nz + 31) >> 5;
@@ -190,7 +250,7 @@ __global__ void __launch_bounds__(128, (MODE == 0 && Q == 19 && !EQ64) ? (EXTRA 
     float* a = p.f + g.cell(x, y, z);
     if constexpr (MODE == 0) {
         if (w == 0 || w == wcount - 1) {           // warp-uniform
-            aa_odd_edge_cell<Q, MOMENT, EQ64, 4, EXTRA>(p, a, x, y, z);
+            aa_odd_zedge_cell<Q, MOMENT, EQ64, EXTRA>(p, a, x, y, z);
             return;
         }
         float f[Q];

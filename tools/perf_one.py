@@ -21,3 +21,5 @@ elif name == "walls_y":
     run("general, walls y", 19, lb.EQ_FP32, (Z, W, Z), BB, False, False)
 elif name == "periodic":
     run("general, periodic xyz", 19, lb.EQ_FP32, (P, P, P), BB, False, False)
+elif name == "inplace_obst":
+    run("in-place obstacle+walls+source", 19, lb.EQ_FP32, (P, W, W), BB, True, True, engine=lb.ENGINE_INPLACE)

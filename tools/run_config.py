@@ -5,6 +5,7 @@
     torchrun --nproc-per-node N tools/run_config.py channel   # configs[3]: periodic channel 2048x512x512, N = 2/4/8 x-slabs
     torchrun --nproc-per-node 8 tools/run_config.py taylor-green [--size 1024]   # configs[4]: Taylor-Green 1024^3, decay check
     python tools/run_config.py taylor-green --size 1024 --engine inplace         # the same domain on ONE GPU (single buffer)
+    python tools/run_config.py obstacle [--size 896 --engine inplace]            # configs[2]: flow past the reference test geometry
 
 `bench.py` keeps the weak-scaling contract (512^3 cells per GPU); this script is for the fixed-size domains the
 configs name (strong scaling: the domain is split into N x-slabs).  Initial states are generated on the GPU with
@@ -41,7 +42,7 @@ def equilibrium(torch, rho, ux, uy, uz):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("config", choices=["cavity", "channel", "taylor-green"])
+    ap.add_argument("config", choices=["cavity", "channel", "taylor-green", "obstacle"])
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--size", type=int, default=0, help="override the edge length (taylor-green, cavity) for small trials")
@@ -73,6 +74,13 @@ def main():
     elif args.config == "channel":
         gx, gy, gz, bc = (args.size * 4 if args.size else 2048), (args.size or 512), (args.size or 512), (P, W, P)
         name = "periodic channel %dx%dx%d D3Q19 BGK fp32, periodic x and z, bounce-back walls in y, initial u=(0.04,0,0)" % (gx, gy, gz)
+    elif args.config == "obstacle":
+        n = args.size or 512
+        gx, gy, gz, bc = n, n, n, (P, W, W)
+        name = ("flow past obstacle (reference test geometry, tapered hexahedron) %d^3 D3Q19 BGK fp32, half-way bounce-back, "
+                "periodic x, walls y/z, initial u=(0.04,0,0), plane source at x=0, force accumulator on" % n)
+        if world > 1:
+            raise SystemExit("bench.py runs the obstacle configuration on slabs (one body per GPU)")
     else:
         n = args.size or 1024
         gx, gy, gz, bc = n, n, n, (P, P, P)
@@ -96,7 +104,7 @@ def main():
         rho = (1.0 - u0 * u0 * 0.75 * (torch.cos(2 * k * xs) + torch.cos(2 * k * ys))).to(torch.float32) * one
         f0 = equilibrium(torch, rho, ux, uy, torch.zeros_like(one))
         del ux, uy, rho
-    elif args.config == "channel":
+    elif args.config in ("channel", "obstacle"):
         f0 = equilibrium(torch, one, 0.04 * one, torch.zeros_like(one), torch.zeros_like(one))
     else:
         z = torch.zeros_like(one)
@@ -114,6 +122,20 @@ def main():
         stepper = SlabLattice(gx, gy, gz, lb.FluidData(1.0, tau), rank=rank, world=world, device=local, bc_x=P,
                               bc_yz=(bc[1], bc[2]), **common)
         lat = stepper.lattice
+    live = gx * gy * gz
+    if args.config == "obstacle":
+        from latticeboltzmanncuda_b200.shapes import tapered_hexahedron_mask
+        solid = tapered_hexahedron_mask(gx, gy, gz)
+        live -= int(solid.sum())
+        keep = torch.from_numpy(1 - solid).to(dev).to(torch.float32)
+        for i in range(19):
+            f0[i] *= keep          # solid cells hold zeros
+        del keep
+        lat.set_solid_mask(solid)
+        flow = np.zeros(27, np.float32); flow[:19] = 1e-6; flow[6] = 2e-6
+        lat.setFlowData(lb.FlowData(((0, None, None), (0, None, None)), flow))
+        lat.setReflectionData(lb.ReflectionData())
+        del solid
     stepper.load_populations(f0)
     del f0
     torch.cuda.empty_cache()
@@ -166,7 +188,7 @@ def main():
     mlups = cells * args.steps / (ms * 1e-3) / 1e6
     out = {"config": name, "n_gpus": world, "engine": "in-place single buffer" if args.engine == "inplace" else "two-buffer fused pull",
            "slab": "%dx%dx%d per GPU" % (nx, gy, gz), "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-           "mlups": mlups, "mlups_per_gpu": mlups / world, "hbm_gbs_per_gpu": mlups / world * 1e6 * 152 / 1e9,
+           "mlups": mlups, "mlups_per_gpu": mlups / world, "hbm_gbs_per_gpu": mlups / world * 1e6 * 152 / 1e9 * live / cells,
            "gpu_launches": int(launches), "state_gb_per_gpu": lat.layout().state_bytes * lat.layout().n_buffers / 1e9,
            "mass_drift_rel": (mass1 - mass0) / mass0, "setup_seconds": t_setup}
     if args.config == "taylor-green":
@@ -180,6 +202,10 @@ def main():
         out["acoustic_period_steps"] = gx * math.sqrt(3.0)
     if args.config == "cavity":
         out["lid_layer_mean_ux"] = lid
+    if args.config == "obstacle":
+        r = lat.retrieve_reflection_data()
+        out["live_cells"] = live
+        out["force_on_body"] = [r.x, r.y, r.z]
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
