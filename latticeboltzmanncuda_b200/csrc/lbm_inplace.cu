@@ -21,7 +21,8 @@
 // word classes of the two-buffer engine are reused: ordinary words run the lean code, all-solid words cost
 // nothing, special words (a cell is solid or sees a solid cell) come from the compact list with their
 // neighbourhood words.  In either storage form the population that bounces into direction i at cell x sits in
-// A[i][x], so one small kernel over the special list sums the momentum exchange before the step.
+// A[i][x] and is among the values the cell reads anyway, so the momentum exchange with the obstacle is summed by
+// the special-word kernels of both steps at no extra traffic.
 // Scope: bounce-back obstacles, additive box source, stream + collide fused, periodic or wall edges.  Reflection
 // tables, unfused phases, zero-inflow edges and slabs run on the two-buffer engine.
 #include "lbm_device.h"
@@ -109,8 +110,14 @@ __global__ void __launch_bounds__(256, (Q == 19 && !EQ64) ? 6 : 4) aa_even_kerne
     if (z >= g.nz || y >= g.ny) return;
     if (EXTRA && p.solid) {
         // a warp is 32 consecutive z of one row = one 32-cell word (blockDim.x is a multiple of 32)
-        // (one broadcast load of the mask word; going through the L2-resident class byte first measured the same)
-        if (solid_bit(p, x + 1, y + 1, z + PAD_Z)) return;
+        if (p.force) {
+            // the momentum exchange is summed by aa_even_special_kernel, which takes the special words: ordinary words only
+            if (__ldg(p.cls + ((long long)x * ((g.nz + 31) >> 5) + (z >> 5)) * p.cls_pitch + y) != AA_ORDINARY) return;
+        } else {
+            // everything in one launch (measured: 2.35 ms against 2.11 + 0.34 ms for the split): one broadcast load of
+            // the mask word, solid lanes leave; going through the L2-resident class byte first measured the same
+            if (solid_bit(p, x + 1, y + 1, z + PAD_Z)) return;
+        }
     }
     float* a = p.f + g.cell(x, y, z);
     float f[Q];
@@ -271,12 +278,55 @@ __global__ void __launch_bounds__(128, (MODE == 0 && Q == 19 && !EQ64) ? (EXTRA 
     }
 }
 
+// Momentum handed to the obstacle cells by this step: population i of a live cell whose upstream neighbour is
+// solid is f*_inv(i)(x) coming back, the obstacle takes -c_i * 2 * that value (the two-buffer engine's and the
+// oracle's sum, oracle/lbm_oracle.c lbo_step_soa).  f[i] holds exactly that value in both steps: the odd step
+// pulled it from the cell's own slot i, the even step finds it arrived in slot i.
+template <int Q>
+__device__ __forceinline__ void bounce_momentum(const float (&f)[Q], uint32_t nb, float& fx, float& fy, float& fz)
+{
+#pragma unroll
+    for (int i = 1; i < Q; ++i) {
+        if ((nb >> nb_bit(-dir_c(i, 0), -dir_c(i, 1), -dir_c(i, 2))) & 1u) {
+            const float m = f[i] + f[i];
+            fx -= (float)dir_c(i, 0) * m;
+            fy -= (float)dir_c(i, 1) * m;
+            fz -= (float)dir_c(i, 2) * m;
+        }
+    }
+}
+
+// one atomic triple per warp into one of FORCE_SLOTS partial sums (all 32 lanes of the warp arrive here)
+__device__ __forceinline__ void warp_force_add(const InplaceParams& p, uint32_t widx, float fx, float fy, float fz)
+{
+    double* slot = p.force + 3 * ((unsigned)(widx >> 2) % FORCE_SLOTS);
+#if defined(LBM_HOST_EMULATION)
+    if (fx != 0.0f || fy != 0.0f || fz != 0.0f) {       // (the CPU test harness runs lanes one after the other: no shuffles)
+        atomicAdd(slot + 0, (double)fx); atomicAdd(slot + 1, (double)fy); atomicAdd(slot + 2, (double)fz);
+    }
+#else
+    if (!__any_sync(0xffffffffu, fx != 0.0f || fy != 0.0f || fz != 0.0f)) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        fx += __shfl_xor_sync(0xffffffffu, fx, o);
+        fy += __shfl_xor_sync(0xffffffffu, fy, o);
+        fz += __shfl_xor_sync(0xffffffffu, fz, o);
+    }
+    if ((threadIdx.x & 31u) == 0) {
+        atomicAdd(slot + 0, (double)fx);
+        atomicAdd(slot + 1, (double)fy);
+        atomicAdd(slot + 2, (double)fz);
+    }
+#endif
+}
+
 // pull + collide + push of one live cell of a special word.  nb = the cell's neighbourhood word (bit
 // nb_bit(dx,dy,dz) = solid flag of that neighbour, ghost bits = periodic images).  A solid neighbour wins over
 // everything else (own slot, no term); then the domain-edge rule of the axes in AXES (wall: own slot + term,
 // periodic: wrapped neighbour); AXES = 0 is the word away from every edge, with constant-bank offsets only.
-template <int Q, int MOMENT, bool EQ64, int AXES>
-__device__ __forceinline__ void aa_odd_geo_cell(const InplaceParams& p, float* a, int x, int y, int z, uint32_t nb)
+template <int Q, int MOMENT, bool EQ64, int AXES, bool FORCE>
+__device__ __forceinline__ void aa_odd_geo_cell(const InplaceParams& p, float* a, int x, int y, int z, uint32_t nb,
+                                                float& fx, float& fy, float& fz)
 {
     const Geom& g = p.g;
     float f[Q];
@@ -293,6 +343,7 @@ __device__ __forceinline__ void aa_odd_geo_cell(const InplaceParams& p, float* a
             f[i] = (!own && e.kind != 0) ? v + e.term : v;
         }
     }
+    if (FORCE) bounce_momentum<Q>(f, nb, fx, fy, fz);
     if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
     else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
     if (p.src_on) add_source<Q>(p, f, x, y, z);
@@ -312,9 +363,11 @@ __device__ __forceinline__ void aa_odd_geo_cell(const InplaceParams& p, float* a
 }
 
 // odd step of the special words: one warp per entry of the compact list (sorted, so neighbouring warps touch
-// neighbouring rows); solid and out-of-range lanes do nothing.  Which edge rules a word needs is warp-uniform.
-template <int Q, int MOMENT, bool EQ64>
-__global__ void __launch_bounds__(128, 8) aa_odd_special_kernel(const __grid_constant__ InplaceParams p)
+// neighbouring rows).  Which edge rules a word needs is warp-uniform.  FORCE: the momentum exchange is summed here
+// (solid and out-of-range lanes then stay for the warp sum; without it they leave at once -- keeping them cost the
+// kernel 0.09 ms of 0.41 in a measurement, hence the two instantiations).
+template <int Q, int MOMENT, bool EQ64, bool FORCE>
+__global__ void __launch_bounds__(128, Q == 19 ? 8 : 6) aa_odd_special_kernel(const __grid_constant__ InplaceParams p)
 {
     const Geom& g = p.g;
     const unsigned lane = threadIdx.x & 31u;
@@ -327,19 +380,24 @@ __global__ void __launch_bounds__(128, 8) aa_odd_special_kernel(const __grid_con
     const int x = (int)(row / (uint32_t)g.yp) - 1, y = (int)(row % (uint32_t)g.yp) - 1;
     const int w = wpad - PAD_Z / 32;
     const int z = w * 32 + (int)lane;
-    if (z >= g.nz || ((nb >> nb_bit(0, 0, 0)) & 1u)) return;
-    float* a = p.f + (long long)widx * 32 + lane;
-    const int wcount = (g.nz + 31) >> 5;
-    if (x == 0 || x == g.nx - 1 || y == 0 || y == g.ny - 1) aa_odd_geo_cell<Q, MOMENT, EQ64, 7>(p, a, x, y, z, nb);
-    else if (w == 0 || w == wcount - 1)                     aa_odd_geo_cell<Q, MOMENT, EQ64, 4>(p, a, x, y, z, nb);
-    else                                                    aa_odd_geo_cell<Q, MOMENT, EQ64, 0>(p, a, x, y, z, nb);
+    const bool live = z < g.nz && !((nb >> nb_bit(0, 0, 0)) & 1u);
+    if (!FORCE && !live) return;
+    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+    if (live) {
+        float* a = p.f + (long long)widx * 32 + lane;
+        const int wcount = (g.nz + 31) >> 5;
+        if (x == 0 || x == g.nx - 1 || y == 0 || y == g.ny - 1) aa_odd_geo_cell<Q, MOMENT, EQ64, 7, FORCE>(p, a, x, y, z, nb, fx, fy, fz);
+        else if (w == 0 || w == wcount - 1)                     aa_odd_geo_cell<Q, MOMENT, EQ64, 4, FORCE>(p, a, x, y, z, nb, fx, fy, fz);
+        else                                                    aa_odd_geo_cell<Q, MOMENT, EQ64, 0, FORCE>(p, a, x, y, z, nb, fx, fy, fz);
+    }
+    if (FORCE) warp_force_add(p, widx, fx, fy, fz);
 }
 
-// Momentum handed to the obstacle cells by the coming step (either storage form): population i of a live cell
-// whose upstream neighbour is solid is f*_inv(i)(x) coming back, and it sits in A[i][x]; the obstacle takes
-// -c_i * 2 * that value (the two-buffer engine's and the oracle's sum, oracle/lbm_oracle.c lbo_step_soa).
-template <int Q>
-__global__ void __launch_bounds__(128) aa_force_kernel(const __grid_constant__ InplaceParams p)
+// even step of the special words when the momentum exchange is summed (otherwise aa_even_kernel takes them too):
+// cell-local like aa_even_kernel, solid lanes skipped; the populations that arrived by bounce-back are among the Q
+// values read, so the sum costs no extra traffic
+template <int Q, int MOMENT, bool EQ64>
+__global__ void __launch_bounds__(128, 8) aa_even_special_kernel(const __grid_constant__ InplaceParams p)
 {
     const Geom& g = p.g;
     const unsigned lane = threadIdx.x & 31u;
@@ -347,44 +405,26 @@ __global__ void __launch_bounds__(128) aa_force_kernel(const __grid_constant__ I
     if (k >= p.n_special) return;
     const uint32_t widx = __ldg(p.special_list + k);
     const uint32_t nb = __ldg(p.cellinfo + k * 32 + lane);
-    const int z = ((int)(widx % (uint32_t)g.wz) - PAD_Z / 32) * 32 + (int)lane;
+    const int wpad = (int)(widx % (uint32_t)g.wz);
+    const uint32_t row = widx / (uint32_t)g.wz;
+    const int x = (int)(row / (uint32_t)g.yp) - 1, y = (int)(row % (uint32_t)g.yp) - 1;
+    const int z = (wpad - PAD_Z / 32) * 32 + (int)lane;
     const bool live = z < g.nz && !((nb >> nb_bit(0, 0, 0)) & 1u);
-    const float* a = p.f + (long long)widx * 32 + lane;
     float fx = 0.0f, fy = 0.0f, fz = 0.0f;
-    bool has_force = false;
-    if (live && (nb & 0x7ffffffu)) {
+    if (live) {
+        float* a = p.f + (long long)widx * 32 + lane;
+        float f[Q];
 #pragma unroll
-        for (int i = 1; i < Q; ++i) {
-            if ((nb >> nb_bit(-dir_c(i, 0), -dir_c(i, 1), -dir_c(i, 2))) & 1u) {
-                const float back = a[p.pop_off[i]];
-                const float m = back + back;
-                fx -= (float)dir_c(i, 0) * m;
-                fy -= (float)dir_c(i, 1) * m;
-                fz -= (float)dir_c(i, 2) * m;
-                has_force = true;
-            }
-        }
-    }
-    double* slot = p.force + 3 * ((unsigned)(widx >> 2) % FORCE_SLOTS);
-#if defined(LBM_HOST_EMULATION)
-    if (has_force) {                    // (the CPU test harness runs lanes one after the other: no shuffles)
-        atomicAdd(slot + 0, (double)fx); atomicAdd(slot + 1, (double)fy); atomicAdd(slot + 2, (double)fz);
-    }
-#else
-    if (__any_sync(0xffffffffu, has_force)) {
+        for (int i = 0; i < Q; ++i) f[i] = a[p.pop_off[i]];
+        bounce_momentum<Q>(f, nb, fx, fy, fz);
+        if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
+        else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
+        if (p.src_on) add_source<Q>(p, f, x, y, z);
+        asm volatile("" : "+l"(a));
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            fx += __shfl_xor_sync(0xffffffffu, fx, o);
-            fy += __shfl_xor_sync(0xffffffffu, fy, o);
-            fz += __shfl_xor_sync(0xffffffffu, fz, o);
-        }
-        if (lane == 0) {
-            atomicAdd(slot + 0, (double)fx);
-            atomicAdd(slot + 1, (double)fy);
-            atomicAdd(slot + 2, (double)fz);
-        }
+        for (int i = 0; i < Q; ++i) a[p.park_off[i]] = f[i];
     }
-#endif
+    warp_force_add(p, widx, fx, fy, fz);
 }
 
 // zero the populations of the solid cells (once after the mask or the state was set: from then on nothing
@@ -508,10 +548,6 @@ cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, int* launches)
     const Geom& g = p.g;
     int n = 0;
     const unsigned special_blocks = (unsigned)((p.n_special + 3) / 4);
-    if (EXTRA && p.force && p.n_special > 0) {      // momentum exchange of this step, read before anything moves
-        aa_force_kernel<Q><<<special_blocks, 128, 0, stream>>>(p);
-        ++n;
-    }
     if (p.parity == 0) {        // parked form -> pull / push
         const int wcount = (g.nz + 31) / 32;
         if (g.nx > 2 && g.ny > 2) {
@@ -526,7 +562,8 @@ cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, int* launches)
         aa_odd_kernel<Q, MOMENT, EQ64, 2, EXTRA><<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(p);
         ++n;
         if (EXTRA && p.cls && p.n_special > 0) {
-            aa_odd_special_kernel<Q, MOMENT, EQ64><<<special_blocks, 128, 0, stream>>>(p);
+            if (p.force) aa_odd_special_kernel<Q, MOMENT, EQ64, true><<<special_blocks, 128, 0, stream>>>(p);
+            else         aa_odd_special_kernel<Q, MOMENT, EQ64, false><<<special_blocks, 128, 0, stream>>>(p);
             ++n;
         }
     } else {                    // arrived form -> local
@@ -537,6 +574,10 @@ cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, int* launches)
         dim3 block(bz, by, 1), grid((g.nz + bz - 1) / bz, (g.ny + by - 1) / by, g.nx);
         aa_even_kernel<Q, MOMENT, EQ64, EXTRA><<<grid, block, 0, stream>>>(p);
         ++n;
+        if (EXTRA && p.cls && p.force && p.n_special > 0) {
+            aa_even_special_kernel<Q, MOMENT, EQ64><<<special_blocks, 128, 0, stream>>>(p);
+            ++n;
+        }
     }
     if (launches) *launches += n;
     return cudaGetLastError();

@@ -37,6 +37,8 @@ def run(name, q, eq, bc, boundary, obstacle, source, moment=lb.MOMENT_STANDARD, 
     if source:
         flow = np.zeros(27, np.float32); flow[:q] = 0.001; flow[6] = 0.002
         lat.setFlowData(lb.FlowData(((0, None, None), (0, None, None)), flow))
+    if os.environ.get("LBM_PROBE_FORCE"):      # momentum exchange with the obstacle, like bench.py
+        lat.setReflectionData(lb.ReflectionData())
     lat.step(5)
     lat.sync()
     ms, launches = lat.step_timed(K)
