@@ -84,8 +84,14 @@ enum lbm_phase {
 
 enum lbm_source_kind { LBM_SOURCE_NONE = 0, LBM_SOURCE_BOX = 1 };
 
-/* streaming engine.  PULL2 keeps two copies of the populations (A -> B);
- * INPLACE is the single-buffer AA pattern (half the footprint, same traffic). */
+/* streaming engine.  PULL2 keeps two copies of the populations (A -> B) and runs everything.
+ * INPLACE is the single-buffer AA pattern (half the footprint, same traffic): fused
+ * stream + collide steps (lbm_step / lbm_step_phases with STREAM and COLLIDE set) on one GPU,
+ * periodic or wall edges, all-fluid lattices or a solid mask in LBM_BOUNDARY_BOUNCE_BACK mode,
+ * box source, force accumulator, SoA transfers; everything else (table reflection, unfused
+ * phases, zero-inflow edges, AoS transfers, slabs) returns LBM_ERR_UNSUPPORTED.  On this engine
+ * lbm_set_solid_mask is accepted before stepping or after an even number of steps
+ * (LBM_ERR_STATE otherwise).  AUTO = PULL2.  TMA is reserved (LBM_ERR_UNSUPPORTED). */
 enum lbm_engine { LBM_ENGINE_AUTO = 0, LBM_ENGINE_PULL2 = 1, LBM_ENGINE_INPLACE = 2, LBM_ENGINE_TMA = 3 };
 
 typedef struct lbm_config {
