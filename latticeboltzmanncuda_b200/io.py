@@ -34,9 +34,11 @@ def load_checkpoint(lat, path):
         dims = tuple(int(v) for v in z["dims"])
         if dims != (lat.nx, lat.ny, lat.nz, lat.q):
             raise ValueError("checkpoint is for a %r lattice, this one is %r" % (dims, (lat.nx, lat.ny, lat.nz, lat.q)))
+        # populations first: on the single-buffer engine a fresh state is in the parked form, the only one in which
+        # the mask may change (include/lbm_b200.h, enum lbm_engine)
+        lat.load_populations(z["f"])
         if z["solid"].any():
             lat.set_solid_mask(z["solid"])
-        lat.load_populations(z["f"])
         if len(z["table_cells"]):
             lat.set_reflection_tables(z["tables"].reshape(-1).view(capi.REFLECTION_VALUES), z["table_cells"])
         if len(z["source_f"]):
