@@ -1,12 +1,3 @@
-// Constants.h -- host copies of the velocity set (simulation/include/Constants.h:4-9)
-#ifndef LBM_COMPAT_CONSTANTS_H
-#define LBM_COMPAT_CONSTANTS_H
-
-namespace CONSTANTS
-{
-    extern const float GEOMETRIC_TOLERANCE;
-    extern const int DIRECTIONS[27][3];
-    extern const int INVERSE_DIRECTIONS[27];
-}
-
-#endif
+// Constants.h -- include name of the reference kept for source compatibility; the interface lives in lbm_reference_api.hpp
+#pragma once
+#include "lbm_reference_api.hpp"

@@ -1,7 +1,3 @@
-// Utils.h -- simulation/include/Utils.h
+// Utils.h -- include name of the reference kept for source compatibility; the interface lives in lbm_reference_api.hpp
 #pragma once
-
-namespace Utils
-{
-    unsigned int compressInts(int* array, const int num, const int bitLength);
-}
+#include "lbm_reference_api.hpp"

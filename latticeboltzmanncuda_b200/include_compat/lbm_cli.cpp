@@ -1,64 +1,92 @@
-// lbm_cli.cpp -- the reference's command line (LatticeBoltzmannCuda.cpp:11-96) on the compatibility layer:
-//   lbm_cli <model.obj> <threads x y z> <blocks x y z> <fluid density> <tau> <lattice spacing> <steps>
-// The lattice is threads*blocks cells per axis; every population starts at 0.001 with the +x population at
-// 0.002; the same values are injected each step on the plane x == 0; the accumulated reflection force is
-// printed before every step, as the reference does.  Optional 12th argument: print the force every K steps only
-// (the reference blocks on a device-to-host copy every step).
+// lbm_cli.cpp -- the reference's command line contract (LatticeBoltzmannCuda.cpp:11-96) on the compatibility layer:
+//
+//   lbm_cli <model.obj> <threads x y z> <blocks x y z> <fluid density> <tau> <lattice spacing> <steps> [print_every]
+//
+// The lattice is threads * blocks cells per axis; every population starts at 0.001 and the +x population at 0.002;
+// the same values are injected on the plane x == 0 after every step; the force accumulated on the body is written
+// as one "Fx Fy Fz" line before each step.  The optional 12th argument prints that line every K steps only (the
+// reference blocks on a device-to-host copy every step; 0 = never).
 #include <cstdio>
 #include <cstdlib>
-#include <cstring>
 #include <iostream>
+#include <memory>
 
-#include "Lattice.h"
-#include "LatticePoint.h"
-#include "FlowSurface.h"
-#include "FlowCriterion.cuh"
-#include "SimCalcFuncs.cuh"
+#include "lbm_reference_api.hpp"
+
+namespace {
+
+struct Options {
+    const char* model = nullptr;
+    dim3 threads, blocks;
+    float density = 1.0f, tau = 1.0f, spacing = 1.0f;
+    int steps = 0, print_every = 1;
+    int nx() const { return (int)(threads.x * blocks.x); }
+    int ny() const { return (int)(threads.y * blocks.y); }
+    int nz() const { return (int)(threads.z * blocks.z); }
+};
+
+bool parse(int argc, char* argv[], Options& o)
+{
+    if (argc < 12) return false;
+    auto u = [&](int k) { return (unsigned)std::atoi(argv[k]); };
+    o.model = argv[1];
+    o.threads = dim3(u(2), u(3), u(4));
+    o.blocks = dim3(u(5), u(6), u(7));
+    o.density = (float)std::atof(argv[8]);
+    o.tau = (float)std::atof(argv[9]);
+    o.spacing = (float)std::atof(argv[10]);
+    o.steps = std::atoi(argv[11]);
+    if (argc > 12) o.print_every = std::atoi(argv[12]);
+    return true;
+}
+
+// the inflow record: what every cell starts with and what the source plane receives each step
+LatticePoint inflow_record()
+{
+    LatticePoint p{};
+    for (float& f : p.particle_distribution) f = 0.001f;
+    p.particle_distribution[6] = 0.002f;        // direction 6 is +x
+    return p;
+}
+
+void fill_uniform(Lattice& lattice, const Options& o, const LatticePoint& value)
+{
+    const size_t cells = (size_t)o.nx() * o.ny() * o.nz();
+    std::unique_ptr<LatticePoint[]> host(new LatticePoint[cells]());
+    for (size_t k = 0; k < cells; ++k)
+        for (int i = 0; i < 27; ++i) host[k].particle_distribution[i] = value.particle_distribution[i];
+    lattice.load_data(host.get());
+}
+
+}  // namespace
 
 int main(int argc, char* argv[])
 {
-    if (argc < 12) {
-        fprintf(stderr, "usage: %s model.obj tx ty tz bx by bz density tau spacing steps [print_every]\n", argv[0]);
+    Options o;
+    if (!parse(argc, argv, o)) {
+        std::fprintf(stderr, "usage: %s model.obj tx ty tz bx by bz density tau spacing steps [print_every]\n", argv[0]);
         return -1;
     }
-    dim3 threads(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]));
-    dim3 blocks(atoi(argv[5]), atoi(argv[6]), atoi(argv[7]));
-    FluidData fluid(atof(argv[8]), atof(argv[9]));
-    const int nx = threads.x * blocks.x, ny = threads.y * blocks.y, nz = threads.z * blocks.z;
-    const int steps = atoi(argv[11]);
-    const int every = argc > 12 ? atoi(argv[12]) : 1;
+    Lattice lattice(o.nx(), o.ny(), o.nz(), o.blocks, o.threads, FluidData(o.density, o.tau), o.spacing);
+    const LatticePoint inflow = inflow_record();
+    fill_uniform(lattice, o, inflow);
 
-    Lattice lattice(nx, ny, nz, blocks, threads, fluid, atof(argv[10]));
-
-    LatticePoint flowRef;
-    std::memset((void*)&flowRef, 0, sizeof flowRef);
-    for (int i = 0; i < 27; ++i) flowRef.particle_distribution[i] = 0.001;
-    flowRef.particle_distribution[6] = 0.002;
-
-    const size_t n = (size_t)nx * ny * nz;
-    LatticePoint* data = new LatticePoint[n];
-    std::memset((void*)data, 0, sizeof(LatticePoint) * n);
-    for (size_t k = 0; k < n; ++k)
-        for (int i = 0; i < 27; ++i) data[k].particle_distribution[i] = flowRef.particle_distribution[i];
-    lattice.load_data(data);
-    delete[] data;
-
-    lattice.insertModel(argv[1]);
+    // geometry: voxelise the mesh, build the reflection tables
+    lattice.insertModel(o.model);
     lattice.preProcessModel();
 
-    FlowData* inducedFlow = new FlowData(&FlowCriterion::ptestPlaneCriteria, flowRef);
-    lattice.setFlowData(inducedFlow);
+    // source on the plane x == 0, force accumulator starting at zero
+    FlowData source(&FlowCriterion::ptestPlaneCriteria, inflow);
+    lattice.setFlowData(&source);
+    ReflectionData force;
+    lattice.setReflectionData(&force);
 
-    ReflectionData* reflection = new ReflectionData;
-    lattice.setReflectionData(reflection);
+    RunCudaFunctions::run_prime_points(o.blocks, o.threads, LatticeData(lattice.getCudaDataPointer(), lattice.getDimensions()));
 
-    LatticeData latticeData(lattice.getCudaDataPointer(), lattice.getDimensions());
-    RunCudaFunctions::run_prime_points(blocks, threads, latticeData);
-
-    for (int step = 0; step < steps; ++step) {
-        if (every > 0 && step % every == 0) {
-            reflection = lattice.retrieve_reflection_data();
-            std::cout << reflection->x << " " << reflection->y << " " << reflection->z << std::endl;
+    for (int step = 0; step < o.steps; ++step) {
+        if (o.print_every > 0 && step % o.print_every == 0) {
+            const ReflectionData* f = lattice.retrieve_reflection_data();
+            std::cout << f->x << " " << f->y << " " << f->z << std::endl;
         }
         lattice.simulateStreaming();
         lattice.simulateReflections();

@@ -1,11 +1,7 @@
 // lbm_compat.cpp -- the reference's C++ interface (Lattice, RunCudaFunctions, Model, rotateVectorAroundAxis,
 // CONSTANTS, Utils, FlowCriterion) implemented on the C ABI of liblbm_b200.so (include/lbm_b200.h).
 // Host code only: every line of device work sits behind the C ABI.
-#include "Lattice.h"
-#include "SimCalcFuncs.cuh"
-#include "Model.h"
-#include "Constants.h"
-#include "Utils.h"
+#include "lbm_reference_api.hpp"
 
 #include "../../include/lbm_b200.h"
 
@@ -50,33 +46,33 @@ namespace FlowCriterion
 
 // ---- Model ---------------------------------------------------------------------------------------------------
 
-Model::~Model() { lbm_mesh_destroy(m_mesh); }
+Model::~Model() { lbm_mesh_destroy(mesh_); }
 
 void Model::importModel(std::string filename)
 {
-    lbm_mesh_destroy(m_mesh);
-    m_mesh = nullptr;
-    lbm_mesh_load(filename.c_str(), &m_mesh);
+    lbm_mesh_destroy(mesh_);
+    mesh_ = nullptr;
+    lbm_mesh_load(filename.c_str(), &mesh_);
 }
 
 bool Model::isModelClosed()
 {
     int closed = 0;
-    if (m_mesh) lbm_mesh_info(m_mesh, nullptr, nullptr, &closed, nullptr);
+    if (mesh_) lbm_mesh_info(mesh_, nullptr, nullptr, &closed, nullptr);
     return closed != 0;
 }
 
 int Model::number_of_vertices()
 {
     int n = 0;
-    if (m_mesh) lbm_mesh_info(m_mesh, &n, nullptr, nullptr, nullptr);
+    if (mesh_) lbm_mesh_info(mesh_, &n, nullptr, nullptr, nullptr);
     return n;
 }
 
 bool Model::checkError()
 {
     int valid = 1;
-    if (m_mesh) lbm_mesh_info(m_mesh, nullptr, nullptr, nullptr, &valid);
+    if (mesh_) lbm_mesh_info(mesh_, nullptr, nullptr, nullptr, &valid);
     return !valid;
 }
 
@@ -84,7 +80,7 @@ bool Model::isPointInsideModel(Point_3 point)
 {
     int inside = 0;
     const float p[3] = {point.x, point.y, point.z};
-    if (m_mesh) lbm_mesh_point_inside(m_mesh, p, &inside);
+    if (mesh_) lbm_mesh_point_inside(mesh_, p, &inside);
     return inside != 0;
 }
 
@@ -92,7 +88,7 @@ BoundingBox Model::bounding_box()
 {
     BoundingBox b;
     std::memset(&b, 0, sizeof b);
-    if (m_mesh) lbm_mesh_bounding_box(m_mesh, b.lo, b.hi);
+    if (mesh_) lbm_mesh_bounding_box(mesh_, b.lo, b.hi);
     return b;
 }
 
@@ -100,7 +96,7 @@ Point_3 Model::reflectionVector(Point_3 point_1, Point_3 point_2)
 {
     const float a[3] = {point_1.x, point_1.y, point_1.z}, b[3] = {point_2.x, point_2.y, point_2.z};
     float out[3] = {0, 0, 0};
-    if (m_mesh) lbm_mesh_reflection_vector(m_mesh, a, b, out);
+    if (mesh_) lbm_mesh_reflection_vector(mesh_, a, b, out);
     return Point_3(out[0], out[1], out[2]);
 }
 
@@ -109,34 +105,34 @@ Point_3 Model::reflectionVector(Point_3 point_1, Point_3 point_2)
 bool Lattice::check(int rc, const char* what)
 {
     if (rc == LBM_OK) return true;
-    m_lastError = std::string(what) + ": " + lbm_last_error();
+    last_error_ = std::string(what) + ": " + lbm_last_error();
     printf("Lattice::%s failed: %s\n", what, lbm_last_error());     // the reference prints and carries on
     return false;
 }
 
 Lattice::Lattice(int x, int y, int z, dim3 blocks, dim3 threads, FluidData fluid, float spacing)
 {
-    m_xResolution = x; m_yResolution = y; m_zResolution = z;
-    m_blocks = blocks; m_threads = threads;
-    m_fluid = fluid;
-    m_latticeSpacing = spacing;
+    nx_ = x; ny_ = y; nz_ = z;
+    blocks_ = blocks; threads_ = threads;
+    fluid_ = fluid;
+    spacing_ = spacing;
     lbm_config cfg;
     lbm_config_default(&cfg);          // the reference's behaviour: D3Q27, SPLIT moments, fp64 equilibrium, zero inflow, tables
     cfg.nx = x; cfg.ny = y; cfg.nz = z;
     cfg.tau = fluid.m_characteristicTimescale;
-    check(lbm_create(&cfg, &m_handle), "Lattice");
+    check(lbm_create(&cfg, &handle_), "Lattice");
 }
 
 Lattice::~Lattice()
 {
-    lbm_destroy(m_handle);
-    delete m_simModel;
+    lbm_destroy(handle_);
+    delete model_;
 }
 
 cudaPitchedPtr Lattice::getCudaDataPointer()
 {
     flush();
-    return make_cudaPitchedPtr((void*)m_handle, sizeof(LatticePoint) * m_xResolution, m_xResolution, m_yResolution);
+    return make_cudaPitchedPtr((void*)handle_, sizeof(LatticePoint) * nx_, nx_, ny_);
 }
 
 // Phases arrive one call at a time in the CLI's order stream, reflect, collide, source
@@ -144,96 +140,96 @@ cudaPitchedPtr Lattice::getCudaDataPointer()
 // kernel step when the sequence is complete; anything else executes what is queued phase by phase first.
 void Lattice::queue(unsigned phase)
 {
-    if (!m_handle) return;
+    if (!handle_) return;
     // `phase` extends the queued prefix iff it is the next phase in CLI order: S -> S|R -> S|R|C -> S|R|C|F
-    const bool extends = m_pending != 0 && (m_pending & LBM_PHASE_STREAM) && phase == ((m_pending + 1) & ~m_pending) &&
-                         (m_pending | phase) == ((phase << 1) - 1);
+    const bool extends = pending_ != 0 && (pending_ & LBM_PHASE_STREAM) && phase == ((pending_ + 1) & ~pending_) &&
+                         (pending_ | phase) == ((phase << 1) - 1);
     if (!extends) flush();
-    m_pending |= phase;
-    if (m_pending == LBM_PHASE_ALL) flush();
+    pending_ |= phase;
+    if (pending_ == LBM_PHASE_ALL) flush();
 }
 
 void Lattice::flush()
 {
-    if (!m_handle || m_pending == 0) return;
-    const unsigned p = m_pending;
-    m_pending = 0;
-    check(lbm_step_phases(m_handle, 1, p), "simulate");      // one launch for whatever prefix was queued
+    if (!handle_ || pending_ == 0) return;
+    const unsigned p = pending_;
+    pending_ = 0;
+    check(lbm_step_phases(handle_, 1, p), "simulate");      // one launch for whatever prefix was queued
 }
 
 void Lattice::simulateStreaming() { queue(LBM_PHASE_STREAM); }
 void Lattice::simulateReflections() { queue(LBM_PHASE_REFLECT); }
 void Lattice::simulateCollision() { queue(LBM_PHASE_COLLIDE); }
-void Lattice::simulateFlow() { if (m_flowData != nullptr) queue(LBM_PHASE_SOURCE); else flush(); }
+void Lattice::simulateFlow() { if (flow_ != nullptr) queue(LBM_PHASE_SOURCE); else flush(); }
 
 void Lattice::simulateLattice()
 {
     flush();
-    if (m_handle) check(lbm_step_phases(m_handle, 1, LBM_PHASE_STREAM | LBM_PHASE_COLLIDE), "simulateLattice");
+    if (handle_) check(lbm_step_phases(handle_, 1, LBM_PHASE_STREAM | LBM_PHASE_COLLIDE), "simulateLattice");
 }
 
 void Lattice::simulateSteps(int n)
 {
     flush();
-    if (m_handle) check(lbm_step(m_handle, n), "simulateSteps");
+    if (handle_) check(lbm_step(handle_, n), "simulateSteps");
 }
 
 void Lattice::synchronize()
 {
     flush();
-    if (m_handle) check(lbm_sync(m_handle), "synchronize");
+    if (handle_) check(lbm_sync(handle_), "synchronize");
 }
 
 void Lattice::load_data(LatticePoint* lattice_array)
 {
     flush();
-    if (!m_handle) return;
-    check(lbm_upload_aos(m_handle, lattice_array, (size_t)m_xResolution * m_yResolution * m_zResolution), "load_data");
+    if (!handle_) return;
+    check(lbm_upload_aos(handle_, lattice_array, (size_t)nx_ * ny_ * nz_), "load_data");
 }
 
 LatticePoint* Lattice::retrieve_data()
 {
     flush();
-    if (!m_handle) return nullptr;
-    const size_t n = (size_t)m_xResolution * m_yResolution * m_zResolution;
+    if (!handle_) return nullptr;
+    const size_t n = (size_t)nx_ * ny_ * nz_;
     LatticePoint* out = new LatticePoint[n];
-    if (!check(lbm_download_aos(m_handle, out, n), "retrieve_data")) {
+    if (!check(lbm_download_aos(handle_, out, n), "retrieve_data")) {
         delete[] out;
         return nullptr;
     }
     // reflecting cells point at their host table, as in the reference (tests read point->reflections)
-    for (size_t i = 0; i < m_reflectionCells.size(); ++i) out[m_reflectionCells[i]].reflections = &m_reflections[i];
+    for (size_t i = 0; i < table_cells_.size(); ++i) out[table_cells_[i]].reflections = &tables_[i];
     return out;
 }
 
 void Lattice::setReflectionData(ReflectionData* reflection)
 {
     flush();
-    m_reflectionData = reflection;
-    if (!m_handle) return;
-    if (!reflection) { check(lbm_set_force_accumulator(m_handle, 0, nullptr), "setReflectionData"); return; }
+    force_ = reflection;
+    if (!handle_) return;
+    if (!reflection) { check(lbm_set_force_accumulator(handle_, 0, nullptr), "setReflectionData"); return; }
     const float init[3] = {reflection->x, reflection->y, reflection->z};
-    check(lbm_set_force_accumulator(m_handle, 1, init), "setReflectionData");
+    check(lbm_set_force_accumulator(handle_, 1, init), "setReflectionData");
 }
 
 ReflectionData* Lattice::retrieve_reflection_data()
 {
     flush();
-    if (!m_handle || !m_reflectionData) return m_reflectionData;
+    if (!handle_ || !force_) return force_;
     float f[3] = {0, 0, 0};
-    if (check(lbm_get_force(m_handle, f), "retrieve_reflection_data")) {
-        m_reflectionData->x = f[0]; m_reflectionData->y = f[1]; m_reflectionData->z = f[2];
+    if (check(lbm_get_force(handle_, f), "retrieve_reflection_data")) {
+        force_->x = f[0]; force_->y = f[1]; force_->z = f[2];
     }
-    return m_reflectionData;
+    return force_;
 }
 
 void Lattice::setFlowData(FlowData* flowData)
 {
     flush();
-    m_flowData = flowData;
-    if (!m_handle) return;
-    if (!flowData) { check(lbm_set_source(m_handle, LBM_SOURCE_NONE, nullptr, nullptr, nullptr), "setFlowData"); return; }
-    const int dims[3] = {m_xResolution, m_yResolution, m_zResolution};
+    flow_ = flowData;
+    if (!handle_) return;
+    if (!flowData) { check(lbm_set_source(handle_, LBM_SOURCE_NONE, nullptr, nullptr, nullptr), "setFlowData"); return; }
+    const int dims[3] = {nx_, ny_, nz_};
     int32_t lo[3] = {0, 0, 0}, hi[3] = {dims[0] - 1, dims[1] - 1, dims[2] - 1};
     if (flowData->pointCriterion == &FlowCriterion::testCriteria) {
         lo[0] = lo[1] = lo[2] = hi[0] = hi[1] = hi[2] = 1;
@@ -251,39 +247,39 @@ void Lattice::setFlowData(FlowData* flowData)
                         for (int a = 0; a < 3; ++a) { if (c[a] < l[a]) l[a] = c[a]; if (c[a] > h[a]) h[a] = c[a]; }
                         ++count;
                     }
-        if (count == 0) { check(lbm_set_source(m_handle, LBM_SOURCE_NONE, nullptr, nullptr, nullptr), "setFlowData"); return; }
+        if (count == 0) { check(lbm_set_source(handle_, LBM_SOURCE_NONE, nullptr, nullptr, nullptr), "setFlowData"); return; }
         if (count != (long long)(h[0] - l[0] + 1) * (h[1] - l[1] + 1) * (h[2] - l[2] + 1)) {
-            m_lastError = "setFlowData: the criterion does not select an index box";
+            last_error_ = "setFlowData: the criterion does not select an index box";
             printf("Lattice::setFlowData failed: the criterion does not select an index box\n");
             return;
         }
         for (int a = 0; a < 3; ++a) { lo[a] = l[a]; hi[a] = h[a]; }
     }
-    check(lbm_set_source(m_handle, LBM_SOURCE_BOX, lo, hi, flowData->inducedFlow.particle_distribution), "setFlowData");
+    check(lbm_set_source(handle_, LBM_SOURCE_BOX, lo, hi, flowData->inducedFlow.particle_distribution), "setFlowData");
 }
 
 void Lattice::insertModel(std::string filename)
 {
     flush();
-    delete m_simModel;
-    m_simModel = new Model();
-    m_simModel->importModel(filename);
-    if (!m_handle || !m_simModel->handle()) return;
+    delete model_;
+    model_ = new Model();
+    model_->importModel(filename);
+    if (!handle_ || !model_->handle()) return;
     int accepted = 0;
-    check(lbm_insert_model(m_handle, m_simModel->handle(), m_latticeSpacing, &accepted), "insertModel");
+    check(lbm_insert_model(handle_, model_->handle(), spacing_, &accepted), "insertModel");
 }
 
 void Lattice::preProcessModel()
 {
     flush();
-    if (m_simModel == nullptr || !m_handle || !m_simModel->handle()) return;
-    if (!check(lbm_preprocess_model(m_handle, m_simModel->handle(), m_latticeSpacing), "preProcessModel")) return;
+    if (model_ == nullptr || !handle_ || !model_->handle()) return;
+    if (!check(lbm_preprocess_model(handle_, model_->handle(), spacing_), "preProcessModel")) return;
     int n = 0;
-    lbm_get_reflection_tables(m_handle, nullptr, nullptr, 0, &n);
-    m_reflections.assign((size_t)n, ReflectionValues());
+    lbm_get_reflection_tables(handle_, nullptr, nullptr, 0, &n);
+    tables_.assign((size_t)n, ReflectionValues());
     std::vector<int64_t> cells((size_t)n);
-    if (n) lbm_get_reflection_tables(m_handle, m_reflections.data(), cells.data(), n, &n);
-    m_reflectionCells.assign(cells.begin(), cells.end());
+    if (n) lbm_get_reflection_tables(handle_, tables_.data(), cells.data(), n, &n);
+    table_cells_.assign(cells.begin(), cells.end());
 }
 
 std::array<std::pair<float, int>, 27> Lattice::distributeVector(Point_3 vector)
