@@ -300,11 +300,6 @@ __device__ __forceinline__ void bounce_momentum(const float (&f)[Q], uint32_t nb
 __device__ __forceinline__ void warp_force_add(const InplaceParams& p, uint32_t widx, float fx, float fy, float fz)
 {
     double* slot = p.force + 3 * ((unsigned)(widx >> 2) % FORCE_SLOTS);
-#if defined(LBM_HOST_EMULATION)
-    if (fx != 0.0f || fy != 0.0f || fz != 0.0f) {       // (the CPU test harness runs lanes one after the other: no shuffles)
-        atomicAdd(slot + 0, (double)fx); atomicAdd(slot + 1, (double)fy); atomicAdd(slot + 2, (double)fz);
-    }
-#else
     if (!__any_sync(0xffffffffu, fx != 0.0f || fy != 0.0f || fz != 0.0f)) return;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -317,7 +312,6 @@ __device__ __forceinline__ void warp_force_add(const InplaceParams& p, uint32_t 
         atomicAdd(slot + 1, (double)fy);
         atomicAdd(slot + 2, (double)fz);
     }
-#endif
 }
 
 // pull + collide + push of one live cell of a special word.  nb = the cell's neighbourhood word (bit

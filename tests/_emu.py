@@ -62,7 +62,7 @@ def rewrite(src):
             break
         out += src[:k]
         src = src[_balanced(src, src.index("(", k)):]
-    src = out + src
+    src = (out + src).replace("__noinline__", "__attribute__((noinline))")     # (libstdc++ spells the attribute itself that way)
     pat = re.compile(r"([A-Za-z_]\w*(?:<[^<>;(){}]*>)?)\s*<<<(.*?)>>>\s*\(")
     out = ""
     while True:
@@ -78,9 +78,29 @@ def rewrite(src):
 
 
 _lib = None
+_full = None
+# _FORTIFY_SOURCE off: the executor longjmps between fiber stacks, which glibc's checked longjmp refuses
+GXX = ["g++", "-std=c++17", "-O1", "-fPIC", "-Wno-attributes", "-Wno-unknown-pragmas", "-ffp-contract=off",
+       "-U_FORTIFY_SOURCE", "-D_FORTIFY_SOURCE=0"]
+
+
+def _includes():
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    return ["-I", cuda_inc, "-I", CSRC, "-I", BUILD, "-I", EMU, "-I", os.path.join(ROOT, "include")]
+
+
+def _newer(target, deps):
+    return not os.path.exists(target) or any(os.path.getmtime(d) > os.path.getmtime(target) for d in deps)
+
+
+def _common_deps():
+    return [os.path.join(EMU, "simt.h"), os.path.join(EMU, "simt_runtime.cpp"), os.path.abspath(__file__),
+            os.path.join(ROOT, "include", "lbm_b200.h")] + \
+           [os.path.join(CSRC, h) for h in ("lbm_device.h", "lbm_internal.h", "d3q.h", "lbm_collide.inl")]
 
 
 def lib():
+    """the in-place engine's launch functions only, driven directly (class Lattice below)"""
     global _lib
     if _lib is not None:
         return _lib
@@ -88,19 +108,64 @@ def lib():
     src = os.path.join(CSRC, "lbm_inplace.cu")
     inc = os.path.join(BUILD, "lbm_inplace_emu.inc")
     so = os.path.join(BUILD, "libinplace_emu.so")
-    deps = [src, os.path.join(EMU, "cuda_shim.h"), os.path.join(EMU, "emu_api.cpp"), os.path.abspath(__file__)] + \
-           [os.path.join(CSRC, h) for h in ("lbm_device.h", "d3q.h", "lbm_collide.inl")]
-    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+    if _newer(so, [src, os.path.join(EMU, "emu_api.cpp")] + _common_deps()):
         with open(src) as fh:
             text = rewrite(fh.read())
         with open(inc, "w") as fh:
             fh.write(text)
-        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-Wno-attributes", "-Wno-unknown-pragmas",
-                               "-ffp-contract=off", "-I", cuda_inc, "-I", CSRC, "-I", BUILD, "-I", EMU,
-                               os.path.join(EMU, "emu_api.cpp"), "-o", so])
+        subprocess.check_call(GXX + ["-shared", "-Wl,-Bsymbolic"] + _includes() +
+                              [os.path.join(EMU, "emu_api.cpp"), os.path.join(EMU, "simt_runtime.cpp"), "-o", so])
     _lib = C.CDLL(so)
     return _lib
+
+
+def full_library():
+    """all of liblbm_b200 (the four .cu files: kernels, C ABI, geometry, in-place engine) compiled for the host on the
+    SIMT executor of tests/emu/: returns the path of tests/emu/_build/liblbm_b200_emu.so"""
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, "liblbm_b200_emu.so")
+    units = ["lbm_kernels.cu", "lbm_capi.cu", "lbm_geometry.cu", "lbm_inplace.cu"]
+    if _newer(so, [os.path.join(CSRC, u) for u in units] + _common_deps()):
+        procs, objs = [], []
+        for u in units:
+            cpp = os.path.join(BUILD, u + ".emu.cpp")
+            with open(os.path.join(CSRC, u)) as fh:
+                text = rewrite(fh.read())
+            with open(cpp, "w") as fh:
+                fh.write('#include "simt.h"\n#line 1 "%s"\n' % os.path.join(CSRC, u) + text)
+            obj = cpp + ".o"
+            objs.append(obj)
+            procs.append(subprocess.Popen(GXX + ["-c"] + _includes() + [cpp, "-o", obj]))
+        rt = os.path.join(BUILD, "simt_runtime.o")
+        procs.append(subprocess.Popen(GXX + ["-c"] + _includes() + [os.path.join(EMU, "simt_runtime.cpp"), "-o", rt]))
+        for pr in procs:
+            if pr.wait() != 0:
+                raise RuntimeError("host build of the library failed")
+        # -Bsymbolic: the stand-ins for the CUDA runtime calls must win over a libcudart that torch may have loaded globally
+        subprocess.check_call(["g++", "-shared", "-Wl,-Bsymbolic", "-o", so] + objs + [rt])
+    return so
+
+
+class emulated_library:
+    """context manager: the Python binding (latticeboltzmanncuda_b200.capi) talks to the host build for the duration.
+    For the CPU test suite only -- the binding itself never looks for anything but the CUDA library."""
+
+    def __enter__(self):
+        from latticeboltzmanncuda_b200 import capi
+        global _full
+        if _full is None:
+            _full = C.CDLL(full_library())
+            for name, res, args in capi.SYMBOLS:
+                fn = getattr(_full, name)
+                fn.restype = res
+                fn.argtypes = args
+        self.capi = capi
+        self.saved = capi._lib
+        capi._lib = _full
+        return _full
+
+    def __exit__(self, *exc):
+        self.capi._lib = self.saved
 
 
 class EmuArgs(C.Structure):
