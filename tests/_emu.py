@@ -146,6 +146,19 @@ def full_library():
     return so
 
 
+def compat_executable(name):
+    """`compat_selftest` / `lbm_cli` of latticeboltzmanncuda_b200/include_compat, linked against the host build"""
+    lib_so = full_library()
+    compat = os.path.join(ROOT, "latticeboltzmanncuda_b200", "include_compat")
+    exe = os.path.join(BUILD, name + "_emu")
+    srcs = [os.path.join(compat, "lbm_compat.cpp"), os.path.join(compat, name + ".cpp")]
+    if _newer(exe, srcs + [os.path.join(compat, "lbm_reference_api.hpp"), lib_so]):
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", compat, "-I", cuda_inc] + srcs +
+                              ["-o", exe, "-L", BUILD, "-llbm_b200_emu", "-Wl,-rpath," + BUILD])
+    return exe
+
+
 class emulated_library:
     """context manager: the Python binding (latticeboltzmanncuda_b200.capi) talks to the host build for the duration.
     For the CPU test suite only -- the binding itself never looks for anything but the CUDA library."""

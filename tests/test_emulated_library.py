@@ -13,6 +13,7 @@ import itertools
 import pytest
 
 import _emu
+import test_gpu_compat as TC
 import test_gpu_geometry as TG
 import test_gpu_parity as TP
 import test_io as TI
@@ -73,3 +74,11 @@ def test_on_the_host_build(host_build, fn, kw):
 
 def test_checkpoint_round_trip_on_the_host_build(host_build, tmp_path):
     TI.test_checkpoint_round_trip_continues_bit_for_bit(tmp_path)
+
+
+@pytest.mark.parametrize("body", [TC.test_reference_gtest_cases_through_the_cpp_headers, TC.test_cli_force_trace_matches_oracle],
+                         ids=["reference_gtest_cases", "cli_force_trace"])
+def test_cpp_layer_on_the_host_build(monkeypatch, body):
+    """the C++ drop-in layer (the reference's gtest cases, the CLI's force trace) linked against the host build"""
+    monkeypatch.setattr(TC, "_built", _emu.compat_executable)
+    body()
