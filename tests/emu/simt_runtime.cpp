@@ -3,11 +3,14 @@
 #include "simt.h"
 
 #include <setjmp.h>
+#include <sys/mman.h>
 #include <ucontext.h>
 
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <utility>
 #include <vector>
 
 uint3 threadIdx, blockIdx;
@@ -192,6 +195,7 @@ void run_grid(dim3 grid, dim3 block, const std::function<void()>& thread_body)
 namespace {
 struct EmuEvent { std::chrono::steady_clock::time_point t; };
 int g_dummy_stream;
+std::map<void*, std::pair<void*, size_t>> g_allocations;      // user pointer -> mapping
 }
 
 extern "C" {
@@ -205,13 +209,42 @@ cudaError_t cudaDeviceSetLimit(enum cudaLimit, size_t) { return cudaSuccess; }
 cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = 0; return cudaSuccess; }
 cudaError_t cudaFuncSetAttribute(const void*, enum cudaFuncAttribute, int) { return cudaSuccess; }
 
+// "Device" allocations sit flush against an inaccessible page (electric-fence style): a kernel that reads or writes
+// past the end of a buffer faults at once instead of passing silently.  SIMT_GUARD=start puts the page in front of
+// the buffer instead (underruns); SIMT_GUARD=off uses plain malloc.
 cudaError_t cudaMalloc(void** p, size_t n)
 {
+    static const int mode = [] {
+        const char* e = std::getenv("SIMT_GUARD");
+        return !e ? 1 : (std::strcmp(e, "start") == 0 ? 2 : (std::strcmp(e, "off") == 0 ? 0 : 1));
+    }();
     *p = nullptr;
-    if (posix_memalign(p, 256, n ? n : 1) != 0) return cudaErrorMemoryAllocation;
+    if (n == 0) n = 1;
+    if (mode == 0) return posix_memalign(p, 256, n) == 0 ? cudaSuccess : cudaErrorMemoryAllocation;
+    const size_t page = 4096, body = (n + page - 1) / page * page, total = body + page;
+    char* base = (char*)mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (base == (char*)MAP_FAILED) return cudaErrorMemoryAllocation;
+    char* user;
+    if (mode == 1) {
+        mprotect(base + body, page, PROT_NONE);
+        user = base + body - (n + 7) / 8 * 8;
+    } else {
+        mprotect(base, page, PROT_NONE);
+        user = base + page;
+    }
+    g_allocations[user] = std::make_pair((void*)base, total);
+    *p = user;
     return cudaSuccess;
 }
-cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+cudaError_t cudaFree(void* p)
+{
+    if (!p) return cudaSuccess;
+    auto it = g_allocations.find(p);
+    if (it == g_allocations.end()) { std::free(p); return cudaSuccess; }
+    munmap(it->second.first, it->second.second);
+    g_allocations.erase(it);
+    return cudaSuccess;
+}
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, enum cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, enum cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
