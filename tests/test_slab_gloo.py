@@ -148,3 +148,85 @@ def test_global_diagnostics_are_the_sum_over_slabs(tmp_path, world):
     for r in range(world):
         got = np.load(out % r)
         assert np.allclose(got, want, rtol=1e-13, atol=1e-12)     # every rank holds the global sums
+
+
+# ---- the product's own SlabLattice (edge planes first, lbm_step_range / lbm_step_commit, plane pointers, halo masks)
+# ---- over gloo, on the host build of the library (tests/_emu.py): what `bench.py --gpus N` runs, minus NCCL and the GPU
+
+def _slab_lattice_worker(rank, world, port, q, gx, Y, Z, bc_yz, steps, f_global, solid_global, flow, out_path):
+    import contextlib
+    import ctypes as C
+    import _emu
+    import latticeboltzmanncuda_b200 as lb
+    from latticeboltzmanncuda_b200.slab import SlabLattice
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class HostStream:                      # stands in for torch.cuda.Stream: the host build runs everything in order
+        cuda_stream = 0
+
+        def __init__(self, device=None):
+            pass
+
+        def synchronize(self):
+            pass
+
+    class HostSlab(SlabLattice):           # plane views and reductions on host memory; everything else is the product's
+        def _plane(self, i, xp, nxt):
+            ptr, nbytes = C.c_void_p(), C.c_size_t()
+            fn = self._lib.lbm_next_plane_ptr if nxt else self._lib.lbm_plane_ptr
+            lb.capi.check(fn(self.lattice.handle, i, xp, C.byref(ptr), C.byref(nbytes)))
+            return torch.from_numpy(np.ctypeslib.as_array((C.c_float * (nbytes.value // 4)).from_address(ptr.value)))
+
+        def _dev(self):
+            return None
+
+    try:
+        with _emu.emulated_library():
+            torch.cuda.Stream, torch.cuda.stream = HostStream, lambda s: contextlib.nullcontext()
+            slab = HostSlab(gx, Y, Z, lb.FluidData(1.0, 0.7), rank=rank, world=world, device=0, bc_x=lb.BC_PERIODIC, bc_yz=bc_yz,
+                            q=q, moment_mode=lb.MOMENT_STANDARD, eq_precision=lb.EQ_FP32, boundary_mode=lb.BOUNDARY_BOUNCE_BACK)
+            x0, x1 = slab.x0, slab.x1
+            xs = np.arange(x0 - 1, x1 + 1) % gx
+            slab.lattice.set_solid_mask(np.ascontiguousarray(solid_global[xs]), x_ghost_planes=True)
+            slab.load_populations(np.ascontiguousarray(f_global[:, x0:x1]))
+            slab.set_source_global((0, None, None), (0, None, None), flow)
+            slab.lattice.setReflectionData(lb.ReflectionData())
+            slab.step(steps)
+            d = slab.diagnostics()
+            np.save(out_path % rank, slab.lattice.retrieve_populations())
+            np.save((out_path % rank) + ".diag.npy", np.concatenate([[d["mass"]], d["momentum"], d["force"]]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,q,bc_yz,gx", [(2, 19, (2, 2), 12), (3, 27, (1, 2), 13)])
+def test_product_slab_lattice_on_the_host_build(tmp_path, world, q, bc_yz, gx):
+    Y, Z, steps = 5, 37, 5
+    rng = np.random.default_rng(5)
+    w = O.weights(q).astype(np.float32)
+    f = (w[:, None, None, None] * (1 + 0.05 * rng.standard_normal((q, gx, Y, Z)))).astype(np.float32)
+    solid = (rng.random((gx, Y, Z)) < 0.08).astype(np.uint8)
+    solid[0, 2, 3] = 1; solid[gx - 1, 2, 4] = 1                 # bodies on the slab edges: their images live in the ghost planes
+    f[:, solid.astype(bool)] = 0
+    flow = np.zeros(27, np.float32); flow[:q] = 1e-3
+    bc = (O.BC_PERIODIC,) + tuple(bc_yz)
+    force = np.zeros(3, np.float64)
+    want = f
+    for _ in range(steps):
+        want = O.step_soa(want, gx, Y, Z, q, 0.7, bc=bc, solid=solid, moment=O.MOMENT_STANDARD, eq64=False, steps=1, force=force)
+        add = np.zeros_like(want); add[:, 0] = flow[:q, None, None]; add[:, solid.astype(bool)] = 0
+        want = want + add
+    out = str(tmp_path / "slab_%d.npy")
+    mp.spawn(_slab_lattice_worker, args=(world, _free_port(), q, gx, Y, Z, bc_yz, steps, f, solid, flow, out), nprocs=world, join=True)
+    got = np.concatenate([np.load(out % r) for r in range(world)], axis=1)
+    scale = float(np.abs(want).max())
+    assert float(np.abs(got.astype(np.float64) - want).max()) / scale <= 1e-5
+    c = np.asarray(O.DIRECTIONS[:q], np.float64)
+    w64 = want.astype(np.float64)
+    for r in range(world):
+        d = np.load((out % r) + ".diag.npy")
+        assert d[0] == pytest.approx(w64.sum(), rel=1e-6)                                   # every rank holds the global mass ...
+        assert np.allclose(d[1:4], [(w64 * c[:, a, None, None, None]).sum() for a in range(3)], atol=1e-4)
+        assert np.allclose(d[4:7], force, rtol=1e-4, atol=1e-4)                            # ... and the force on all bodies
