@@ -87,9 +87,11 @@ enum lbm_source_kind { LBM_SOURCE_NONE = 0, LBM_SOURCE_BOX = 1 };
 /* streaming engine.  PULL2 keeps two copies of the populations (A -> B) and runs everything.
  * INPLACE is the single-buffer AA pattern (half the footprint, same traffic): fused
  * stream + collide steps (lbm_step / lbm_step_phases with STREAM and COLLIDE set) on one GPU,
- * periodic or wall edges, all-fluid lattices or a solid mask in LBM_BOUNDARY_BOUNCE_BACK mode,
- * box source, force accumulator, SoA transfers; everything else (table reflection, unfused
- * phases, zero-inflow edges, AoS transfers, slabs) returns LBM_ERR_UNSUPPORTED.  On this engine
+ * periodic or wall edges (LBM_BC_HALO on x for slabs: the caller moves the edge planes around
+ * every odd step through lbm_plane_ptr, see latticeboltzmanncuda_b200/slab.py), all-fluid
+ * lattices or a solid mask in LBM_BOUNDARY_BOUNCE_BACK mode, box source, force accumulator, SoA
+ * transfers; everything else (table reflection, unfused phases, zero-inflow edges, AoS
+ * transfers, lbm_step_range) returns LBM_ERR_UNSUPPORTED.  On this engine
  * lbm_set_solid_mask is accepted before stepping or after an even number of steps
  * (LBM_ERR_STATE otherwise).  AUTO = PULL2.  TMA is reserved (LBM_ERR_UNSUPPORTED). */
 enum lbm_engine { LBM_ENGINE_AUTO = 0, LBM_ENGINE_PULL2 = 1, LBM_ENGINE_INPLACE = 2, LBM_ENGINE_TMA = 3 };
@@ -202,6 +204,11 @@ LBM_API int lbm_step_commit(lbm_handle h);
 LBM_API int lbm_next_plane_ptr(lbm_handle h, int q, int xp, void **dev_ptr, size_t *bytes);
 /* fill the y and z ghost layers (periodic axes) of the current state, including the x ghost planes */
 LBM_API int lbm_fill_ghosts(lbm_handle h);
+/* single-buffer slabs (LBM_ENGINE_INPLACE with LBM_BC_HALO on x), after an odd step: the populations the
+ * neighbouring slabs pushed across the faces have been delivered into the unused slots of the ghost planes
+ * (c_x = +1 slots of padded plane 0, c_x = -1 slots of padded plane nx+1); this moves them into the edge planes,
+ * except where the slot holds this slab's own bounced population (y/z wall, solid neighbour). */
+LBM_API int lbm_inplace_merge_edges(lbm_handle h);
 
 /* layout facts for tools: padded dims and strides in floats */
 typedef struct lbm_layout {

@@ -105,6 +105,7 @@ SYMBOLS = [
     ("lbm_step_range", _i, [_vp, _u, _i, _i, _i]),
     ("lbm_step_commit", _i, [_vp]),
     ("lbm_fill_ghosts", _i, [_vp]),
+    ("lbm_inplace_merge_edges", _i, [_vp]),
     ("lbm_get_layout", _i, [_vp, C.POINTER(Layout)]),
     ("lbm_get_stats", _i, [_vp, C.POINTER(Stats)]),
     ("lbm_mesh_load", _i, [C.c_char_p, C.POINTER(_vp)]),

@@ -382,8 +382,8 @@ LBM_API int lbm_create(const lbm_config* cfg, lbm_handle* out)
         return fail(LBM_ERR_UNSUPPORTED, "engine %d is not built in this version", cfg->engine);
     if (cfg->engine == LBM_ENGINE_INPLACE)
         for (int a = 0; a < 3; ++a)
-            if (cfg->bc[a] != LBM_BC_PERIODIC && cfg->bc[a] != LBM_BC_WALL)
-                return fail(LBM_ERR_UNSUPPORTED, "the in-place engine takes periodic or wall edges only");
+            if (cfg->bc[a] != LBM_BC_PERIODIC && cfg->bc[a] != LBM_BC_WALL && cfg->bc[a] != LBM_BC_HALO)
+                return fail(LBM_ERR_UNSUPPORTED, "the in-place engine takes periodic, wall or halo (x slab) edges only");
     const Geom g = make_geom(cfg->nx, cfg->ny, cfg->nz);
     if (g.np >= (1ll << 32)) return fail(LBM_ERR_INVALID, "more than 2^32 padded cells per slab");
 
@@ -912,14 +912,14 @@ static int plane_ptr(lbm_handle h, float* base, int q, int xp, void** dev_ptr, s
 LBM_API int lbm_plane_ptr(lbm_handle h, int q, int xp, void** dev_ptr, size_t* bytes)
 {
     if (!h) return fail(LBM_ERR_INVALID, "null handle");
-    if (h->inplace) return inplace_only(h, "lbm_plane_ptr");
+    if (h->inplace) return plane_ptr(h, h->buf[0], q, xp, dev_ptr, bytes);      // one copy: slot q of padded plane xp
     return plane_ptr(h, h->buf[h->cur], q, xp, dev_ptr, bytes);
 }
 
 LBM_API int lbm_next_plane_ptr(lbm_handle h, int q, int xp, void** dev_ptr, size_t* bytes)
 {
     if (!h) return fail(LBM_ERR_INVALID, "null handle");
-    if (h->inplace) return inplace_only(h, "lbm_next_plane_ptr");
+    if (h->inplace) return plane_ptr(h, h->buf[0], q, xp, dev_ptr, bytes);      // the update is in place
     return plane_ptr(h, h->buf[h->cur ^ 1], q, xp, dev_ptr, bytes);
 }
 
@@ -975,6 +975,19 @@ LBM_API int lbm_step_range(lbm_handle h, unsigned phases, int x0, int x1, int on
     if (rc) return rc;
     h->pending_commit = true;
     h->pending_phases = phases;
+    return LBM_OK;
+}
+
+LBM_API int lbm_inplace_merge_edges(lbm_handle h)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    if (!h->inplace || h->cfg.bc[0] != LBM_BC_HALO) return fail(LBM_ERR_STATE, "lbm_inplace_merge_edges is for single-buffer slab handles");
+    if (h->aa_parity != 1) return fail(LBM_ERR_STATE, "lbm_inplace_merge_edges follows an odd (pull / push) step");
+    InplaceParams ip;
+    fill_inplace(h, ip);
+    CK(launch_inplace_merge_edges(ip, h->cfg.q, h->stream));
+    h->launches += 2;
     return LBM_OK;
 }
 

@@ -140,6 +140,7 @@ inline void set_inplace_offsets(InplaceParams& ip, const Geom& g)
 }
 
 cudaError_t launch_inplace_zero_solid(const InplaceParams& p, int q, cudaStream_t stream);
+cudaError_t launch_inplace_merge_edges(const InplaceParams& p, int q, cudaStream_t stream);
 cudaError_t launch_inplace_step(const InplaceParams& p, int q, int moment, int eq64, cudaStream_t stream, int* launches);
 cudaError_t launch_inplace_scatter(const float* dense, float* f, const Geom& g, int q_index, int x0, int nxc, cudaStream_t stream);
 cudaError_t launch_inplace_gather(const InplaceParams& p, int q, float* dense, int q_index, int x0, int nxc, cudaStream_t stream);

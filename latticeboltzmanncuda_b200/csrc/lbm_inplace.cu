@@ -23,8 +23,12 @@
 // neighbourhood words.  In either storage form the population that bounces into direction i at cell x sits in
 // A[i][x] and is among the values the cell reads anyway, so the momentum exchange with the obstacle is summed by
 // the special-word kernels of both steps at no extra traffic.
-// Scope: bounce-back obstacles, additive box source, stream + collide fused, periodic or wall edges.  Reflection
-// tables, unfused phases, zero-inflow edges and slabs run on the two-buffer engine.
+// x slabs (LBM_BC_HALO on x): the ghost planes are ordinary neighbours.  Before an odd step they receive the
+// neighbouring slabs' edge planes of the populations the edge cells pull (c_x = -1 slots below, c_x = +1 slots
+// above); the edge cells push into the same slots, and after the step those planes go back to their owners.  Even
+// steps are cell-local and need no exchange at all (latticeboltzmanncuda_b200/slab.py).
+// Scope: bounce-back obstacles, additive box source, stream + collide fused, periodic / wall / halo edges.
+// Reflection tables, unfused phases and zero-inflow edges run on the two-buffer engine.
 #include "lbm_device.h"
 
 // measurement knob (python -m latticeboltzmanncuda_b200.build --variant NAME -DMACRO=VALUE)
@@ -63,6 +67,10 @@ __device__ __forceinline__ Edge edge_lookup(const InplaceParams& p, int i, int x
     for (int a = 0; a < 3; ++a) {
         const int t = pos[a] + c[a];
         if (!((AXES >> a) & 1) || (t >= 0 && t < n[a])) { e.off += (long long)c[a] * stride[a]; continue; }
+        if (p.bc[a] == 3) {          // halo (x slabs): the ghost plane is an ordinary neighbour, filled from / returned to the next slab
+            e.off += (long long)c[a] * stride[a];
+            continue;
+        }
         if (p.bc[a] == 2) {
             if (e.kind == 0) {       // the wall named first in x, y, z order supplies the velocity
                 const float* u = p.wall_u[a * 2 + (t < 0 ? 0 : 1)];
@@ -421,6 +429,34 @@ __global__ void __launch_bounds__(128, 8) aa_even_special_kernel(const __grid_co
     warp_force_add(p, widx, fx, fy, fz);
 }
 
+// x slabs, after an odd step.  The neighbouring slab pushed populations across the shared face into its ghost copy
+// of my edge plane; slab.py delivers those planes into the UNUSED slots of my ghost planes (the low ghost plane
+// only ever holds the c_x = -1 slots, so its c_x = +1 slots are free, and vice versa).  This kernel moves them
+// into the edge plane -- but only the entries the neighbour really wrote: where the pushing cell would lie beyond
+// a y/z wall or is solid, the slot holds my own cell's bounced population (written by my own edge cell in the same
+// step) and the neighbour's copy of it is stale.
+template <int Q>
+__global__ void aa_merge_edge_kernel(const __grid_constant__ InplaceParams p, int side)
+{
+    const Geom& g = p.g;
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (z >= g.nz) return;
+    const int x = side ? g.nx - 1 : 0;                 // my edge plane
+    const int xg = side ? g.nx : -1;                   // the ghost plane next to it
+    if (p.solid && solid_bit(p, x + 1, y + 1, z + PAD_Z)) return;
+#pragma unroll
+    for (int k = 1; k < Q; ++k) {
+        if (dir_c(k, 0) != (side ? -1 : 1)) continue;  // populations that ENTER my slab through this face
+        const int ys = y - dir_c(k, 1), zs = z - dir_c(k, 2);      // the cell that pushed it sits at (xg, ys, zs)
+        if (p.bc[1] == 2 && (ys < 0 || ys >= g.ny)) continue;
+        if (p.bc[2] == 2 && (zs < 0 || zs >= g.nz)) continue;
+        if (p.solid && solid_bit(p, xg + 1, ys + 1, zs + PAD_Z)) continue;      // (ghost rows / columns hold the periodic images)
+        const long long slot = (long long)k * g.np;
+        p.f[slot + g.cell(x, y, z)] = p.f[slot + g.cell(xg, y, z)];
+    }
+}
+
 // zero the populations of the solid cells (once after the mask or the state was set: from then on nothing
 // reads or writes them, and the state reads back as the two-buffer engine's, which writes zeros there)
 template <int Q>
@@ -603,6 +639,16 @@ cudaError_t launch_inplace_zero_solid(const InplaceParams& p, int q, cudaStream_
     dim3 grid((p.g.nz + 127) / 128, p.g.ny, p.g.nx);
     if (q == 27) aa_zero_solid_kernel<27><<<grid, 128, 0, stream>>>(p);
     else         aa_zero_solid_kernel<19><<<grid, 128, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_inplace_merge_edges(const InplaceParams& p, int q, cudaStream_t stream)
+{
+    dim3 grid((p.g.nz + 127) / 128, p.g.ny, 1);
+    for (int side = 0; side < 2; ++side) {
+        if (q == 27) aa_merge_edge_kernel<27><<<grid, 128, 0, stream>>>(p, side);
+        else         aa_merge_edge_kernel<19><<<grid, 128, 0, stream>>>(p, side);
+    }
     return cudaGetLastError();
 }
 

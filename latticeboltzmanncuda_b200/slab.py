@@ -115,6 +115,11 @@ class SlabLattice:
         self.lattice = Lattice(self.nx, gy, gz, None, None, fluid, 1.0, bc=(capi.BC_HALO, bc_yz[0], bc_yz[1]),
                                device=device, **kw)
         self.q = self.lattice.q
+        # single-buffer engine: no ghost refresh per step; the edge planes travel around every odd step instead
+        self.inplace = kw.get("engine") == capi.ENGINE_INPLACE
+        self._aa_odd_next = True
+        if self.inplace and bc_x != capi.BC_PERIODIC:
+            raise ValueError("single-buffer slabs need a periodic global x axis")
         self.halo = HaloExchange(rank, world, bc_x == capi.BC_PERIODIC, self.q)
         self.overlap = bool(overlap) and not os.environ.get("LBM_SLAB_NOOVERLAP")
         self._lib = capi.load()
@@ -153,8 +158,57 @@ class SlabLattice:
             w.wait()
         self._ghosts_current = True
 
+    def _inplace_exchange(self, fetch):
+        """single-buffer engine, around an odd step.  fetch=True: the neighbours' edge planes of the populations my
+        edge cells pull (slots with c_x = -1 of the left neighbour's last plane, c_x = +1 of the right neighbour's
+        first plane) -> my ghost planes.  fetch=False: the same slots, now holding what my edge cells pushed, go
+        back from my ghost planes to the planes they belong to.  Same posting order as HaloExchange (rightward wave
+        first), so NCCL pairs sends and receives correctly."""
+        nx, h = self.nx, self.halo
+        plane = lambda i, xp: self._plane(i, xp, False)
+        ops = []
+        if fetch:
+            if h.right is not None:
+                ops += [("send", plane(i, nx), h.right, i) for i in h.down]            # my last plane -> right's low ghost
+            if h.left is not None:
+                ops += [("recv", plane(i, 0), h.left, i) for i in h.down]
+                ops += [("send", plane(i, 1), h.left, 100 + i) for i in h.up]          # my first plane -> left's high ghost
+            if h.right is not None:
+                ops += [("recv", plane(i, nx + 1), h.right, 100 + i) for i in h.up]
+        else:
+            # delivered into the slots of the receiver's ghost planes that it does not use itself (its low ghost plane
+            # holds c_x = -1 slots only); lbm_inplace_merge_edges then moves what the neighbour really wrote
+            if h.right is not None:
+                ops += [("send", plane(i, nx + 1), h.right, i) for i in h.up]          # pushed across +x -> right's low ghost
+            if h.left is not None:
+                ops += [("recv", plane(i, 0), h.left, i) for i in h.up]
+                ops += [("send", plane(i, 0), h.left, 100 + i) for i in h.down]        # pushed across -x -> left's high ghost
+            if h.right is not None:
+                ops += [("recv", plane(i, nx + 1), h.right, 100 + i) for i in h.down]
+        if not ops:
+            return
+        dist = self.dist
+        p2p = [dist.P2POp(dist.isend if kind == "send" else dist.irecv, t, peer, tag=tag) for kind, t, peer, tag in ops]
+        for w in dist.batch_isend_irecv(p2p):
+            w.wait()                                                                   # stream-ordered for NCCL, blocking for gloo
+
+    def _step_inplace(self, n, phases):
+        lib, h = self._lib, self.lattice.handle
+        with self.torch.cuda.stream(self.stream):
+            for _ in range(int(n)):
+                if self._aa_odd_next:
+                    self._inplace_exchange(fetch=True)
+                    capi.check(lib.lbm_step_phases(h, 1, int(phases)))
+                    self._inplace_exchange(fetch=False)
+                    capi.check(lib.lbm_inplace_merge_edges(h))
+                else:
+                    capi.check(lib.lbm_step_phases(h, 1, int(phases)))                 # even steps are cell-local
+                self._aa_odd_next = not self._aa_odd_next
+
     def step(self, n=1, phases=capi.PHASE_ALL):
         lib, h = self._lib, self.lattice.handle
+        if self.inplace:
+            return self._step_inplace(n, phases)
         if not self._ghosts_current:
             self.prime()
         with self.torch.cuda.stream(self.stream):
@@ -177,7 +231,7 @@ class SlabLattice:
         torch = self.torch
         st0 = self.lattice.stats()["kernel_launches"]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if not self._ghosts_current:
+        if not self._ghosts_current and not self.inplace:
             self.prime()
         self.stream.synchronize()
         e0.record(self.stream)
@@ -190,6 +244,7 @@ class SlabLattice:
     def load_populations(self, f_local):
         self.lattice.load_populations(f_local)
         self._ghosts_current = False
+        self._aa_odd_next = True               # a fresh state is in the parked form: the next step pulls and pushes
 
     def set_source_global(self, lo, hi, flow):
         """source box in global cell coordinates (None = whole axis); ranks the box misses get none"""

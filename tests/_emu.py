@@ -125,6 +125,14 @@ def full_library():
     os.makedirs(BUILD, exist_ok=True)
     so = os.path.join(BUILD, "liblbm_b200_emu.so")
     units = ["lbm_kernels.cu", "lbm_capi.cu", "lbm_geometry.cu", "lbm_inplace.cu"]
+    import fcntl
+    with open(os.path.join(BUILD, ".lock"), "w") as lock:          # spawned test workers may all arrive here at once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        _build_full(so, units)
+    return so
+
+
+def _build_full(so, units):
     if _newer(so, [os.path.join(CSRC, u) for u in units] + _common_deps()):
         procs, objs = [], []
         for u in units:
@@ -142,8 +150,8 @@ def full_library():
             if pr.wait() != 0:
                 raise RuntimeError("host build of the library failed")
         # -Bsymbolic: the stand-ins for the CUDA runtime calls must win over a libcudart that torch may have loaded globally
-        subprocess.check_call(["g++", "-shared", "-Wl,-Bsymbolic", "-o", so] + objs + [rt])
-    return so
+        subprocess.check_call(["g++", "-shared", "-Wl,-Bsymbolic", "-o", so + ".tmp"] + objs + [rt])
+        os.replace(so + ".tmp", so)
 
 
 def compat_executable(name):

@@ -153,7 +153,7 @@ def test_global_diagnostics_are_the_sum_over_slabs(tmp_path, world):
 # ---- the product's own SlabLattice (edge planes first, lbm_step_range / lbm_step_commit, plane pointers, halo masks)
 # ---- over gloo, on the host build of the library (tests/_emu.py): what `bench.py --gpus N` runs, minus NCCL and the GPU
 
-def _slab_lattice_worker(rank, world, port, q, gx, Y, Z, bc_yz, steps, f_global, solid_global, flow, out_path):
+def _slab_lattice_worker(rank, world, port, q, gx, Y, Z, bc_yz, steps, f_global, solid_global, flow, out_path, inplace):
     import contextlib
     import ctypes as C
     import _emu
@@ -186,7 +186,8 @@ def _slab_lattice_worker(rank, world, port, q, gx, Y, Z, bc_yz, steps, f_global,
         with _emu.emulated_library():
             torch.cuda.Stream, torch.cuda.stream = HostStream, lambda s: contextlib.nullcontext()
             slab = HostSlab(gx, Y, Z, lb.FluidData(1.0, 0.7), rank=rank, world=world, device=0, bc_x=lb.BC_PERIODIC, bc_yz=bc_yz,
-                            q=q, moment_mode=lb.MOMENT_STANDARD, eq_precision=lb.EQ_FP32, boundary_mode=lb.BOUNDARY_BOUNCE_BACK)
+                            q=q, moment_mode=lb.MOMENT_STANDARD, eq_precision=lb.EQ_FP32, boundary_mode=lb.BOUNDARY_BOUNCE_BACK,
+                            **({"engine": lb.ENGINE_INPLACE} if inplace else {}))
             x0, x1 = slab.x0, slab.x1
             xs = np.arange(x0 - 1, x1 + 1) % gx
             slab.lattice.set_solid_mask(np.ascontiguousarray(solid_global[xs]), x_ghost_planes=True)
@@ -201,8 +202,10 @@ def _slab_lattice_worker(rank, world, port, q, gx, Y, Z, bc_yz, steps, f_global,
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,q,bc_yz,gx", [(2, 19, (2, 2), 12), (3, 27, (1, 2), 13)])
-def test_product_slab_lattice_on_the_host_build(tmp_path, world, q, bc_yz, gx):
+@pytest.mark.parametrize("world,q,bc_yz,gx,inplace", [(2, 19, (2, 2), 12, False), (2, 19, (2, 2), 12, True),
+                                                      (3, 27, (1, 2), 13, True), (2, 19, (1, 1), 4, True)])
+def test_product_slab_lattice_on_the_host_build(tmp_path, world, q, bc_yz, gx, inplace):
+    """inplace: one copy of the populations per slab; the edge planes travel before and after every odd step"""
     Y, Z, steps = 5, 37, 5
     rng = np.random.default_rng(5)
     w = O.weights(q).astype(np.float32)
@@ -219,7 +222,9 @@ def test_product_slab_lattice_on_the_host_build(tmp_path, world, q, bc_yz, gx):
         add = np.zeros_like(want); add[:, 0] = flow[:q, None, None]; add[:, solid.astype(bool)] = 0
         want = want + add
     out = str(tmp_path / "slab_%d.npy")
-    mp.spawn(_slab_lattice_worker, args=(world, _free_port(), q, gx, Y, Z, bc_yz, steps, f, solid, flow, out), nprocs=world, join=True)
+    import _emu
+    _emu.full_library()                                         # built once here, not by every worker
+    mp.spawn(_slab_lattice_worker, args=(world, _free_port(), q, gx, Y, Z, bc_yz, steps, f, solid, flow, out, inplace), nprocs=world, join=True)
     got = np.concatenate([np.load(out % r) for r in range(world)], axis=1)
     scale = float(np.abs(want).max())
     assert float(np.abs(got.astype(np.float64) - want).max()) / scale <= 1e-5
