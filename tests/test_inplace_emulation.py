@@ -53,9 +53,8 @@ def obstacle(X, Y, Z, seed, frac=0.08):
     return solid
 
 
-@pytest.mark.parametrize("q", [19, 27])
 @pytest.mark.parametrize("bc", [(1, 1, 1), (2, 2, 2), (1, 2, 1), (2, 1, 2), (1, 2, 2)])
-@pytest.mark.parametrize("shape", [(14, 12, 40), (6, 5, 70), (9, 7, 32)])
+@pytest.mark.parametrize("q,shape", [(19, (14, 12, 40)), (19, (6, 5, 70)), (19, (9, 7, 32)), (27, (6, 5, 70))])
 def test_bounce_back_obstacles(q, bc, shape):
     X, Y, Z = shape
     solid = obstacle(X, Y, Z, 23 + X)
