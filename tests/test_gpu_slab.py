@@ -25,7 +25,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, q, gx, Y, Z, bc_x, bc_yz, steps, overlap, f, solid, out):
+def _worker(rank, world, port, q, gx, Y, Z, bc_x, bc_yz, steps, overlap, f, solid, out, engine=None):
     import torch.distributed as dist
     import latticeboltzmanncuda_b200 as lb
     from latticeboltzmanncuda_b200.slab import SlabLattice, slab_range
@@ -35,7 +35,8 @@ def _worker(rank, world, port, q, gx, Y, Z, bc_x, bc_yz, steps, overlap, f, soli
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         slab = SlabLattice(gx, Y, Z, lb.FluidData(1.0, 0.7), rank, world, rank, bc_x=bc_x, bc_yz=bc_yz, overlap=overlap,
-                           q=q, moment_mode=lb.MOMENT_STANDARD, eq_precision=lb.EQ_FP32, boundary_mode=lb.BOUNDARY_BOUNCE_BACK)
+                           q=q, moment_mode=lb.MOMENT_STANDARD, eq_precision=lb.EQ_FP32, boundary_mode=lb.BOUNDARY_BOUNCE_BACK,
+                           **({"engine": engine} if engine is not None else {}))
         x0, x1 = slab_range(gx, rank, world)
         xs = np.arange(x0 - 1, x1 + 1)
         if bc_x == lb.BC_PERIODIC:
@@ -78,3 +79,29 @@ def test_two_slabs_equal_one_gpu(tmp_path, q, bc_x, bc_yz, overlap):
     for r in range(2):
         got_diag = np.load((out % r) + ".diag.npy")
         assert np.allclose(got_diag, want_diag, rtol=1e-10, atol=1e-9 * abs(want_diag[0]))   # fp64 sums, different order
+
+
+@pytest.mark.xfail(strict=False, reason="single-buffer slabs are verified over gloo on the host build (tests/test_slab_gloo.py) "
+                                        "but had not been run over NCCL when round 1 ended")
+@pytest.mark.parametrize("q,bc_yz,steps", [(19, (2, 2), 9), (27, (1, 2), 6)])
+def test_two_single_buffer_slabs_equal_one_gpu(tmp_path, q, bc_yz, steps):
+    """one copy of the populations per slab: the edge planes travel before and after every odd step"""
+    import latticeboltzmanncuda_b200 as lb
+    gx, Y, Z = 24, 10, 40
+    rng = np.random.default_rng(5)
+    w = O.weights(q).astype(np.float32)
+    f = (w[:, None, None, None] * (1 + 0.05 * rng.standard_normal((q, gx, Y, Z)))).astype(np.float32)
+    solid = (rng.random((gx, Y, Z)) < 0.08).astype(np.uint8)
+    solid[10:14, 3:7, 8:30] = 1
+    f[:, solid.astype(bool)] = 0
+    one = lb.Lattice(gx, Y, Z, None, None, lb.FluidData(1.0, 0.7), 1.0, q=q, bc=(1,) + tuple(bc_yz),
+                     moment_mode=lb.MOMENT_STANDARD, eq_precision=lb.EQ_FP32, boundary_mode=lb.BOUNDARY_BOUNCE_BACK)
+    one.set_solid_mask(solid)
+    one.load_populations(f)
+    one.step(steps)
+    want = one.retrieve_populations()
+    out = str(tmp_path / "slab_%d.npy")
+    mp.spawn(_worker, args=(2, _free_port(), q, gx, Y, Z, 1, bc_yz, steps, False, f, solid, out, lb.ENGINE_INPLACE), nprocs=2, join=True)
+    got = np.concatenate([np.load(out % r) for r in range(2)], axis=1)
+    scale = float(np.abs(want).max())
+    assert float(np.abs(got.astype(np.float64) - want.astype(np.float64)).max()) / scale <= 2e-6
