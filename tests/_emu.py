@@ -63,7 +63,7 @@ def rewrite(src):
         out += src[:k]
         src = src[_balanced(src, src.index("(", k)):]
     src = (out + src).replace("__noinline__", "__attribute__((noinline))")     # (libstdc++ spells the attribute itself that way)
-    pat = re.compile(r"([A-Za-z_]\w*(?:<[^<>;(){}]*>)?)\s*<<<(.*?)>>>\s*\(")
+    pat = re.compile(r"((?:[A-Za-z_]\w*::)*[A-Za-z_]\w*(?:<[^<>;(){}]*>)?)\s*<<<(.*?)>>>\s*\(")
     out = ""
     while True:
         m = pat.search(src)
@@ -165,6 +165,52 @@ def compat_executable(name):
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", compat, "-I", cuda_inc] + srcs +
                               ["-o", exe, "-L", BUILD, "-llbm_b200_emu", "-Wl,-rpath," + BUILD])
     return exe
+
+
+def reference_library():
+    """the REFERENCE's own Lattice class and CUDA kernels (unmodified sources under /root/reference, compiled where they
+    lie, like oracle/Makefile does for the GPU) on the host executor: oracle/_ref/libref_simt.so.  Rebuilt only when
+    /root/reference is present; outputs go to oracle/_ref/ (git-ignored), never into the repository."""
+    ref = os.environ.get("LBM_REFERENCE_ROOT", "/root/reference")
+    oracle = os.path.join(ROOT, "oracle")
+    out_dir = os.path.join(oracle, "_ref")
+    so = os.path.join(out_dir, "libref_simt.so")
+    src_dir = os.path.join(ref, "simulation", "source")
+    if not os.path.isdir(src_dir):
+        return so if os.path.exists(so) else None
+    import fcntl
+    os.makedirs(os.path.join(out_dir, "simt"), exist_ok=True)
+    with open(os.path.join(out_dir, "simt", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        mine = [os.path.join(oracle, f) for f in ("ref_harness.cpp", "ref_model_stub.cpp")]
+        host = [os.path.join(src_dir, f) for f in ("Lattice.cpp", "Geometry.cpp", "Constants.cpp", "Utils.cpp")]
+        dev = [os.path.join(src_dir, f) for f in ("SimCalcFuncs.cu", "FlowCriterion.cu")]
+        if _newer(so, mine + host + dev + [os.path.join(EMU, "simt.h"), os.path.join(EMU, "simt_runtime.cpp"), os.path.abspath(__file__)]):
+            import _oracle
+            _oracle.lib()                                              # liblbm_oracle.so answers the mesh queries of the model stub
+            cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+            inc = ["-I", os.path.join(oracle, "cgal_stub"), "-I", os.path.join(ref, "simulation", "include"), "-I", oracle,
+                   "-I", cuda_inc, "-I", EMU]
+            objs = []
+            for k, f in enumerate(mine + host):
+                obj = os.path.join(out_dir, "simt", "%d_%s.o" % (k, os.path.basename(f)))
+                subprocess.check_call(["g++", "-O1", "-fPIC", "-std=c++17", "-w"] + inc + ["-c", f, "-o", obj])
+                objs.append(obj)
+            for f in dev:
+                cpp = os.path.join(out_dir, "simt", os.path.basename(f) + ".host.cpp")
+                with open(f) as fh:
+                    text = rewrite(fh.read())
+                with open(cpp, "w") as fh:
+                    fh.write('#include "simt.h"\n' + text)
+                obj = cpp + ".o"
+                subprocess.check_call(GXX + ["-w"] + inc + ["-c", cpp, "-o", obj])
+                objs.append(obj)
+            rt = os.path.join(out_dir, "simt", "simt_runtime.o")
+            subprocess.check_call(GXX + ["-c", "-I", cuda_inc, "-I", EMU, os.path.join(EMU, "simt_runtime.cpp"), "-o", rt])
+            subprocess.check_call(["g++", "-shared", "-Wl,-Bsymbolic", "-o", so + ".tmp"] + objs + [rt, "-L", oracle, "-llbm_oracle",
+                                   "-Wl,-rpath," + oracle])
+            os.replace(so + ".tmp", so)
+    return so
 
 
 class emulated_library:

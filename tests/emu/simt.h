@@ -12,6 +12,7 @@
 #include <cstring>
 #include <functional>
 
+#define __DEVICE_LAUNCH_PARAMETERS_H__      // (its `extern const uint3 threadIdx` would clash with the executor's variables)
 #undef __shared__
 #define __shared__ static          // blocks run one after the other, so one static copy per kernel is the block's copy
 
@@ -68,3 +69,4 @@ inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)
 inline unsigned atomicOr(unsigned* p, unsigned v) { const unsigned old = *p; *p = old | v; return old; }
 
 template <class T> inline cudaError_t cudaFuncSetAttribute(T*, enum cudaFuncAttribute, int) { return cudaSuccess; }
+

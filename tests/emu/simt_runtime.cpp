@@ -261,6 +261,28 @@ cudaError_t cudaMemcpy3DAsync(const struct cudaMemcpy3DParms* p, cudaStream_t)
     return cudaSuccess;
 }
 
+cudaError_t cudaMemcpy3D(const struct cudaMemcpy3DParms* p) { return cudaMemcpy3DAsync(p, nullptr); }
+cudaError_t cudaMalloc3D(struct cudaPitchedPtr* out, struct cudaExtent e)
+{
+    void* p = nullptr;
+    const cudaError_t rc = cudaMalloc(&p, e.width * e.height * e.depth);
+    *out = make_cudaPitchedPtr(p, e.width, e.width, e.height);
+    return rc;
+}
+cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+// (the reference fetches a device function pointer through the address of a __device__ variable; on this executor
+// that variable is an ordinary global, initialised with the function's address)
+cudaError_t cudaMemcpyFromSymbol(void* dst, const void* symbol, size_t count, size_t offset, enum cudaMemcpyKind)
+{
+    std::memcpy(dst, (const char*)symbol + offset, count);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpyToSymbol(const void* symbol, const void* src, size_t count, size_t offset, enum cudaMemcpyKind)
+{
+    std::memcpy((char*)symbol + offset, src, count);
+    return cudaSuccess;
+}
+
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)&g_dummy_stream; return cudaSuccess; }
 cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = (cudaStream_t)&g_dummy_stream; return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }

@@ -119,3 +119,39 @@ def test_degenerate_shapes_on_the_host_build(host_build, shape, bc):
         assert TP.rel_err(lat.retrieve_populations(), want) <= tol, "engine %d" % engine
         assert lat.mass() == pytest.approx(float(want.astype(np.float64).sum()), rel=1e-5, abs=1e-7)
         lat.close()
+
+
+# ---- the reference itself on the host executor ---------------------------------------------------------------------
+# tests/_emu.py reference_library() compiles the reference's own Lattice class and CUDA kernels -- the unmodified
+# sources, where they lie under /root/reference, exactly the set oracle/Makefile compiles for the GPU -- on the same
+# SIMT executor (output: oracle/_ref/libref_simt.so, git-ignored).  The bodies of tests/test_gpu_vs_reference.py then
+# compare the reference's kernels, the oracle and this library's kernels without a GPU.
+
+import _ref_gpu
+import test_gpu_vs_reference as TR
+
+
+@pytest.fixture(scope="module")
+def reference_on_the_host():
+    so = _emu.reference_library()
+    if so is None:
+        pytest.skip("neither /root/reference nor a prebuilt oracle/_ref/libref_simt.so")
+    saved = (_ref_gpu.SO, _ref_gpu._lib)
+    _ref_gpu.SO, _ref_gpu._lib = so, None
+    yield so
+    _ref_gpu.SO, _ref_gpu._lib = saved
+
+
+def _reference_cases():
+    out = []
+    for name in sorted(n for n in dir(TR) if n.startswith("test_")):
+        fn = getattr(TR, name)
+        for kw in parametrisations(fn):
+            label = name[5:] + ("[%s]" % "-".join(str(v) for v in kw.values()) if kw else "")
+            out.append(pytest.param(fn, kw, id=label.replace(" ", "")))
+    return out
+
+
+@pytest.mark.parametrize("fn,kw", _reference_cases())
+def test_against_the_reference_on_the_host_build(host_build, reference_on_the_host, fn, kw):
+    fn(**kw)
