@@ -128,7 +128,11 @@ def test_degenerate_shapes_on_the_host_build(host_build, shape, bc):
 # compare the reference's kernels, the oracle and this library's kernels without a GPU.
 
 import _ref_gpu
-import test_gpu_vs_reference as TR
+
+try:
+    import test_gpu_vs_reference as TR          # skips itself at import when oracle/_ref/libref_gpu.so was never built
+except pytest.skip.Exception:
+    TR = None
 
 
 @pytest.fixture(scope="module")
@@ -144,7 +148,7 @@ def reference_on_the_host():
 
 def _reference_cases():
     out = []
-    for name in sorted(n for n in dir(TR) if n.startswith("test_")):
+    for name in sorted(n for n in dir(TR) if n.startswith("test_")) if TR else []:
         fn = getattr(TR, name)
         for kw in parametrisations(fn):
             label = name[5:] + ("[%s]" % "-".join(str(v) for v in kw.values()) if kw else "")
