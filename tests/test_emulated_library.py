@@ -17,6 +17,7 @@ import test_gpu_compat as TC
 import test_gpu_geometry as TG
 import test_gpu_parity as TP
 import test_io as TI
+import test_reference_vectors as TV
 
 # (module, test, keep every n-th parametrisation) -- sized so that the module runs in about a minute
 SELECTION = [
@@ -31,6 +32,8 @@ SELECTION = [
     (TG, "test_coordinates_with_model", 1), (TG, "test_mask_and_tables_bit_exact", 1),
     (TG, "test_missing_file_and_bounding_box_guard", 1), (TG, "test_reflection_table_known_answer", 1),
     (TG, "test_reflections_known_answer_end_to_end", 1),
+    (TV, "test_library_streaming_equals_the_reference", 1), (TV, "test_library_collision_equals_the_reference", 1),
+    (TV, "test_library_geometry_and_cli_loop_equal_the_reference", 1),
 ]
 
 
