@@ -197,13 +197,11 @@ def reference_library():
                 subprocess.check_call(["g++", "-O1", "-fPIC", "-std=c++17", "-w"] + inc + ["-c", f, "-o", obj])
                 objs.append(obj)
             for f in dev:
-                cpp = os.path.join(out_dir, "simt", os.path.basename(f) + ".host.cpp")
+                # the rewritten text goes to the compiler through a pipe: no copy of a reference source is ever written
                 with open(f) as fh:
-                    text = rewrite(fh.read())
-                with open(cpp, "w") as fh:
-                    fh.write('#include "simt.h"\n' + text)
-                obj = cpp + ".o"
-                subprocess.check_call(GXX + ["-w"] + inc + ["-c", cpp, "-o", obj])
+                    text = '#include "simt.h"\n' + rewrite(fh.read())
+                obj = os.path.join(out_dir, "simt", os.path.basename(f) + ".host.o")
+                subprocess.run(GXX + ["-w"] + inc + ["-x", "c++", "-", "-c", "-o", obj], input=text.encode(), check=True)
                 objs.append(obj)
             rt = os.path.join(out_dir, "simt", "simt_runtime.o")
             subprocess.check_call(GXX + ["-c", "-I", cuda_inc, "-I", EMU, os.path.join(EMU, "simt_runtime.cpp"), "-o", rt])
