@@ -3,17 +3,23 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size S] [--q 19|27]
 
-One "step" is one fused lattice update (pull-stream + bounce-back + BGK collide + source) of the
-whole lattice.  Workload at N = 1: BASELINE.json configs[2], "flow past obstacle voxelised from
-the reference test geometry, 512^3, bounce-back", D3Q19 fp32 -- the configuration BASELINE.json's
-80%-of-HBM target is quoted on.  At N > 1 the lattice is slab-decomposed along x with the same
-cells per GPU (weak scaling; N = 8 is the 1024^3 domain of configs[4]).
+One "step" is one fused lattice update (stream + bounce-back + BGK collide + source) of the whole
+lattice on ONE copy of the populations (single-buffer "AA" streaming, the north star's engine).
+Workload at N = 1: BASELINE.json configs[2], "flow past obstacle voxelised from the reference test
+geometry, 512^3, bounce-back", D3Q19 fp32 -- the configuration the 80%-of-HBM target is quoted on.
+At N > 1 every GPU holds a 128 x 1024 x 1024 x-slab (the same 2^27 cells as 512^3) of a
+128N x 1024 x 1024 domain -- N = 8 is the slab-decomposed 1024^3 domain of configs[4] -- with the
+same obstacle squeezed into a 128 x 512 x 512 box and tiled 2 x 2 over the cross-section, so that
+every GPU has the same work (weak scaling).  The slabs are joined by peer-memory halos below the
+C ABI (lbm_halo_connect): no communication library runs in the step.
 
-Prints ONE JSON line (see the task contract): value = whole-job MLUPS with the state resident in
-HBM; e2e = the same job through the host API with pinned host buffers (state upload, per-step
-force read-back like the reference CLI, moments download) inside the timed region; roofline =
-algorithmic bytes (2*Q*4 per cell update) over the CUDA-event time of the step kernel against the
-measured copy bandwidth in MEASURED_PEAKS.json; cpu_baseline = the CPU oracle port on this box's cores.
+Prints ONE JSON line (see the task contract): value = whole-job MLUPS over the LIVE (non-solid)
+cells -- solid cells move no bytes -- with the state resident in HBM; e2e = the same job through
+the host API with pinned host buffers (state upload, per-step force read-back like the reference
+CLI, moments download) inside the timed region; roofline = algorithmic bytes (2*Q*4 per live cell
+update) over the CUDA-event time of the step against the measured copy bandwidth in
+MEASURED_PEAKS.json; cpu_baseline = the CPU oracle port on this box's cores on BASELINE.json
+configs[0] (64^3 reference geometry, the reference's own arithmetic).
 """
 import argparse
 import ctypes as C
@@ -37,12 +43,17 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", type=int, default=512, help="cells per axis of one GPU's share")
+    ap.add_argument("--size", type=int, default=512, help="N = 1: cells per axis")
+    ap.add_argument("--slab", default="128,1024,1024", help="N > 1: cells of one GPU's x-slab (nx,ny,nz)")
     ap.add_argument("--q", type=int, default=19, choices=[19, 27])
+    ap.add_argument("--engine", default="inplace", choices=["inplace", "pull2"],
+                    help="inplace = single-buffer AA streaming (headline), pull2 = two-buffer fused pull")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: peer = peer-memory halos below the C ABI, nccl = torch.distributed P2P of the edge planes")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the all-fluid dense / in-place side measurements")
-    ap.add_argument("--ref-size", type=int, default=int(os.environ.get("LBM_REF_SIZE", "256")))
+    ap.add_argument("--no-extra", action="store_true", help="skip the side measurements (other engines, reference mode, config 1)")
+    ap.add_argument("--ref-size", type=int, default=int(os.environ.get("LBM_REF_SIZE", "512")))
     return ap.parse_args()
 
 
@@ -127,33 +138,63 @@ def source_flow(q, scale=1.0):
 # our arm
 # -------------------------------------------------------------------------------------------------
 
-def cpu_baseline(q, target_seconds=12.0):
-    """the CPU oracle port (oracle/lbm_oracle.c, OpenMP) on a bounded sample of the same workload"""
+def config1_inputs(n=64):
+    """BASELINE.json configs[0]: the reference test geometry on a 64^3 grid as the CLI sets it up
+    (LatticeBoltzmannCuda.cpp:29-76): all f = 0.001, f[6] = 0.002, plane source at x == 0, force accumulator"""
+    flow = source_flow(27)
+    obj = os.path.join(ROOT, "tests", "golden", "obj", "cube_angled.obj")
+    return n, float(np.float32(1.0 / n)), flow, obj
+
+
+def cpu_baseline(target_seconds=10.0):
+    """the CPU oracle port (oracle/lbm_oracle.c, OpenMP) on BASELINE.json configs[0]: 64^3 D3Q27, the reference's own
+    arithmetic (table reflection, fp64 equilibrium, SPLIT moments, zero-inflow edges), CLI loop; all cores for
+    ~target_seconds, then one thread for a fifth of that"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle as O
+    n, spacing, flow, obj = config1_inputs()
+    cells = O.new_cells(n, n, n)
+    cells["f"] = flow[None, :]
+    mesh = O.Mesh(obj)
+    mesh.insert(cells, n, n, n, np.float32(spacing))
+    tables, tindex = mesh.preprocess(cells, n, n, n, np.float32(spacing))
+    force = np.zeros(3, np.float32)
+
+    def run(seconds, cap):
+        cur, steps, t0 = cells, 0, time.perf_counter()
+        while True:
+            cur = O.step_cli(cur, n, n, n, 1.0, tables, tindex, force, O.SRC_PLANE_X0, flow, steps=10)
+            steps += 10
+            dt = time.perf_counter() - t0
+            if dt >= seconds or steps >= cap:
+                return steps, dt
+
+    cores = int(O.lib().lbo_num_threads())
+    run(0.5, 10)                                                       # warm-up
+    steps, dt = run(target_seconds, 1000)
+    out = {"value": n ** 3 * steps / dt / 1e6, "unit": "MLUPS", "cores": cores, "kind": "port",
+           "sample": "BASELINE configs[0]: %d^3 D3Q27 reference mode (table reflection, fp64 equilibrium), CLI loop, %d of 1000 steps in "
+                     "%.1f s (oracle/lbm_oracle.c, OpenMP, %d threads)" % (n, steps, dt, cores)}
+    if hasattr(O.lib(), "lbo_set_num_threads"):
+        O.lib().lbo_set_num_threads(1)
+        s1, d1 = run(target_seconds / 5.0, 200)
+        O.lib().lbo_set_num_threads(cores)
+        out["one_thread_mlups"] = n ** 3 * s1 / d1 / 1e6
+    return out
+
+
+def obstacle_mask(world, nx, gy, gz):
+    """N = 1: the reference's tapered hexahedron in the box.  N > 1: the same solid squeezed into an nx x gy/2 x gz/2 box and
+    tiled 2 x 2 over the slab's cross-section -- every slab holds the same four bodies, none touches a slab face"""
     from latticeboltzmanncuda_b200.shapes import tapered_hexahedron_mask
-    n = 128
-    solid = tapered_hexahedron_mask(n, n, n)
-    w = O.weights(q).astype(np.float32)
-    f = np.ascontiguousarray(np.broadcast_to(w[:, None, None, None], (q, n, n, n))).copy()
-    f[:, solid.astype(bool)] = 0
-    bc = (O.BC_ZERO, O.BC_WALL, O.BC_WALL)
-    f = O.step_soa(f, n, n, n, q, 0.6, bc=bc, solid=solid, steps=1)          # warm-up
-    steps, t0 = 0, time.perf_counter()
-    while True:
-        f = O.step_soa(f, n, n, n, q, 0.6, bc=bc, solid=solid, steps=2)
-        steps += 2
-        dt = time.perf_counter() - t0
-        if dt >= target_seconds or steps >= 400:
-            break
-    return {"value": n ** 3 * steps / dt / 1e6, "unit": "MLUPS", "cores": int(O.lib().lbo_num_threads()),
-            "kind": "port", "sample": "%d^3 D3Q%d bounce-back obstacle, %d steps in %.1f s (oracle/lbm_oracle.c, OpenMP)" % (n, q, steps, dt)}
+    if world == 1:
+        return tapered_hexahedron_mask(nx, gy, gz)
+    return np.tile(tapered_hexahedron_mask(nx, gy // 2, gz // 2), (1, 2, 2))
 
 
 def run_ours(args):
     import torch
     import latticeboltzmanncuda_b200 as lb
-    from latticeboltzmanncuda_b200.shapes import tapered_hexahedron_mask
 
     rank, world, local = dist_env()
     if world != args.gpus:
@@ -165,58 +206,67 @@ def run_ours(args):
         # stdout carries ONE JSON line: NCCL writes its debug output (the version banner at WARN and above) to stdout
         # unless told otherwise, so whatever level the caller asked for goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")   # halo transfers must get SM slots next to the interior kernel
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    q, S = args.q, args.size
-    tau = 0.6
-    # global domain: a channel of N boxes of S^3 cells in a row along x, one box (x-slab) per GPU, each with its own
-    # copy of the obstacle, so that every GPU has exactly the N = 1 work (weak scaling; cf. BASELINE.json configs[3])
-    gx, gy, gz = world * S, S, S
-    nx = gx // world
+    q, tau = args.q, 0.6
+    if world == 1:
+        nx = gy = gz = args.size
+    else:
+        nx, gy, gz = (int(v) for v in args.slab.split(","))
+    gx = nx * world
     x_off = rank * nx
     cells_total = gx * gy * gz
+    engine = lb.ENGINE_INPLACE if args.engine == "inplace" else lb.ENGINE_PULL2
     # the CLI injects 0.001 per population per step into a fluid of density 0.028 with open (vacuum) edges;
     # here the fluid starts at density 1 with a uniform velocity, the x direction is periodic and the same
     # source shape at 0.1 % of the amplitude keeps the inflow phase in the step without driving it unstable
     flow = source_flow(q, 0.001)
     u0 = 0.04
 
-    bc_x = lb.BC_PERIODIC if world == 1 else lb.BC_HALO
-    kw = dict(q=q, bc=(bc_x, lb.BC_WALL, lb.BC_WALL), moment_mode=lb.MOMENT_STANDARD, eq_precision=lb.EQ_FP32,
-              boundary_mode=lb.BOUNDARY_BOUNCE_BACK, device=local)
+    kw = dict(q=q, moment_mode=lb.MOMENT_STANDARD, eq_precision=lb.EQ_FP32, boundary_mode=lb.BOUNDARY_BOUNCE_BACK, engine=engine)
     if world == 1:
-        lat = lb.Lattice(nx, gy, gz, None, None, lb.FluidData(1.0, tau), 1.0 / gx, **kw)
+        lat = lb.Lattice(nx, gy, gz, None, None, lb.FluidData(1.0, tau), 1.0 / gx, bc=(lb.BC_PERIODIC, lb.BC_WALL, lb.BC_WALL),
+                         device=local, **kw)
         slab = None
     else:
         from latticeboltzmanncuda_b200.slab import SlabLattice
-        slab = SlabLattice(gx, gy, gz, lb.FluidData(1.0, tau), rank=rank, world=world, device=local,
-                           bc_x=lb.BC_PERIODIC, **{k: v for k, v in kw.items() if k not in ("bc", "device")},
-                           bc_yz=(lb.BC_WALL, lb.BC_WALL))
+        slab = SlabLattice(gx, gy, gz, lb.FluidData(1.0, tau), rank=rank, world=world, device=local, bc_x=lb.BC_PERIODIC,
+                           bc_yz=(lb.BC_WALL, lb.BC_WALL), transport=args.transport, **kw)
         lat = slab.lattice
 
     # synthetic inputs: obstacle mask + uniform initial state (host, pinned) + inflow plane source at global x == 0
-    solid = tapered_hexahedron_mask(nx, gy, gz)
+    interior = obstacle_mask(world, nx, gy, gz)
+    solid = interior
     if world > 1:
-        # the neighbours' edge planes (periodic tiling of the same box): the obstacle keeps clear of the box faces
-        ghost = np.zeros((1, gy, gz), np.uint8)
-        solid = np.concatenate([ghost, solid, ghost], axis=0)
+        ghost = np.zeros((1, gy, gz), np.uint8)          # the bodies keep clear of the slab faces
+        solid = np.concatenate([ghost, interior, ghost], axis=0)
     w = np.array([1 / 3] + [1 / 18] * 6 + [1 / 36] * 12, np.float32) if q == 19 else \
         np.array([8 / 27] + [2 / 27] * 6 + [1 / 54] * 12 + [1 / 216] * 8, np.float32)
     host_f = torch.empty((q, nx, gy, gz), dtype=torch.float32, pin_memory=True)
     hf = host_f.numpy()
-    interior = solid[1:-1] if world > 1 else solid
     live_local = int(interior.size - int(interior.sum()))
     cx = np.array([0, -1, 0, 0, 0, 0, 1, -1, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 1, -1, -1, -1, -1, 1, 1, 1, 1], np.float32)
-    for i in range(q):
-        hf[i] = w[i] * (1.0 + 3.0 * cx[i] * u0 + 4.5 * (cx[i] * u0) ** 2 - 1.5 * u0 * u0)   # equilibrium at rho = 1, u = (u0, 0, 0)
-        hf[i][interior.astype(bool)] = 0.0
+    fluid = interior == 0
 
+    def fill_state(with_body=True):
+        for i in range(q):
+            v = w[i] * (1.0 + 3.0 * cx[i] * u0 + 4.5 * (cx[i] * u0) ** 2 - 1.5 * u0 * u0)   # equilibrium at rho = 1, u = (u0, 0, 0)
+            if with_body:
+                np.multiply(fluid, np.float32(v), out=hf[i], casting="unsafe")
+            else:
+                hf[i] = v
+
+    fill_state()
     stepper = slab if slab is not None else lat
     lat.set_solid_mask(solid, x_ghost_planes=(world > 1))
     stepper.load_populations(hf)
-    if x_off == 0:
-        lat.setFlowData(lb.FlowData(((0, None, None), (0, None, None)), flow))
+
+    def set_inflow(l):
+        if x_off == 0:
+            l.setFlowData(lb.FlowData(((0, None, None), (0, None, None)), flow))
+
+    set_inflow(lat)
     lat.setReflectionData(lb.ReflectionData())
 
     def barrier():
@@ -237,7 +287,6 @@ def run_ours(args):
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    mlups = cells_total * args.steps / (ms * 1e-3) / 1e6
     b_alg = 2 * q * 4
     peak, peak_src = peak_hbm()
     live_total = live_local
@@ -245,13 +294,15 @@ def run_ours(args):
         t = torch.tensor([live_local], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         live_total = int(t.item())
-    # algorithmic bytes: every live (non-solid) cell reads Q and writes Q populations; solid cells move nothing
+    # every live (non-solid) cell reads Q and writes Q populations; solid cells move nothing and are not counted
+    mflups = live_total * args.steps / (ms * 1e-3) / 1e6
     per_gpu_gbs = (live_total / world) * args.steps * b_alg / (ms * 1e-3) / 1e9
-    mass = lat.mass()
+    mass = lat.mass() if world == 1 else slab.mass()
     finite = bool(np.isfinite(mass))
-    state_gb = lat.layout().state_bytes / 1e9
+    lay = lat.layout()
+    state_gb = lay.state_bytes * lay.n_buffers / 1e9
 
-    # ---- end to end through the host API: upload (pinned) + K x (step + force read-back) + moments download
+    # ---- end to end through the host API: upload (pinned) + K x (set source, step, force read-back) + moments download
     e2e = None
     if not args.no_e2e:
         n_local = nx * gy * gz
@@ -262,10 +313,11 @@ def run_ours(args):
         t0 = time.perf_counter()
         stepper.load_populations(hf)
         for _ in range(args.steps):
-            if x_off == 0:
-                lat.setFlowData(lb.FlowData(((0, None, None), (0, None, None)), flow))   # this step's inflow, from the host
+            set_inflow(lat)                                                                    # this step's inflow, from the host
             stepper.step(1)
-            lb.capi.check(lib.lbm_get_force(h, lb.capi.ptr(force)))                         # the CLI prints this every step
+            lb.capi.check(lib.lbm_get_force(h, lb.capi.ptr(force)))                            # the CLI prints this every step
+        if slab is not None:
+            slab.sync()
         lb.capi.check(lib.lbm_moments(h, lb.capi.ptr(host_m[0]), lb.capi.ptr(host_m[1]), lb.capi.ptr(host_m[2]),
                                       lb.capi.ptr(host_m[3])))
         barrier()
@@ -274,80 +326,94 @@ def run_ours(args):
             t = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": cells_total * args.steps / dt / 1e6, "unit": "MLUPS",
+        e2e = {"value": live_total * args.steps / dt / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": int(hf.nbytes / args.steps + 27 * 4 + 24),
                "d2h_bytes_per_step": int(host_m.nbytes / args.steps + 12),
                "what": "lbm_upload_f_soa from pinned host + %d x (lbm_set_source, lbm_step, lbm_get_force) + lbm_moments to pinned host" % args.steps,
-               "seconds": dt}
+               "seconds": dt, "mlups_all_cells": cells_total * args.steps / dt / 1e6}
 
-    # ---- the two dense engines on an all-fluid lattice of the same size (context for the roofline; N = 1 only)
-    extra = None
+    extra, refmode, config1 = None, None, None
     if world == 1 and not args.no_extra:
-        extra = {}
         lat.close()
-        for name, engine, bc in (("dense_two_buffer", lb.ENGINE_PULL2, (lb.BC_PERIODIC, lb.BC_PERIODIC, lb.BC_ZERO_INFLOW)),
-                                 ("in_place_single_buffer", lb.ENGINE_INPLACE, (lb.BC_PERIODIC,) * 3)):
-            l2 = lb.Lattice(nx, gy, gz, None, None, lb.FluidData(1.0, tau), 1.0 / gx, q=q, bc=bc, moment_mode=lb.MOMENT_STANDARD,
-                            eq_precision=lb.EQ_FP32, boundary_mode=lb.BOUNDARY_BOUNCE_BACK, device=local, engine=engine)
-            for i in range(q):
-                hf[i] = w[i]
-            l2.load_populations(hf)
-            l2.step(4)
-            l2.sync()
-            ms2, _ = l2.step_timed(40)
-            gbs2 = cells_total * 40 * b_alg / (ms2 * 1e-3) / 1e9
-            extra[name] = {"mlups": cells_total * 40 / (ms2 * 1e-3) / 1e6, "gbs": gbs2, "frac": gbs2 / peak,
-                           "state_gb": l2.layout().state_bytes * l2.layout().n_buffers / 1e9}
-            l2.close()
-        # the timed workload itself (obstacle, walls, plane source, force) on the single-buffer engine: half the memory
-        l4 = lb.Lattice(nx, gy, gz, None, None, lb.FluidData(1.0, tau), 1.0 / gx, engine=lb.ENGINE_INPLACE,
-                        **{**kw, "bc": (lb.BC_PERIODIC, lb.BC_WALL, lb.BC_WALL)})
-        for i in range(q):
-            hf[i] = w[i] * (1.0 + 3.0 * cx[i] * u0 + 4.5 * (cx[i] * u0) ** 2 - 1.5 * u0 * u0)
-            hf[i][interior.astype(bool)] = 0.0
-        l4.set_solid_mask(solid)
-        l4.load_populations(hf)
-        l4.setFlowData(lb.FlowData(((0, None, None), (0, None, None)), flow))
-        l4.setReflectionData(lb.ReflectionData())
-        l4.step(4)
-        l4.sync()
-        ms4, n4 = l4.step_timed(40)
-        gbs4 = live_local * 40 * b_alg / (ms4 * 1e-3) / 1e9
-        extra["obstacle_in_place_single_buffer"] = {
-            "mlups": cells_total * 40 / (ms4 * 1e-3) / 1e6, "gbs": gbs4, "frac": gbs4 / peak, "ms_per_step": ms4 / 40,
-            "launches_per_step": n4 / 40, "state_gb": l4.layout().state_bytes * l4.layout().n_buffers / 1e9,
-            "mass_finite": bool(np.isfinite(l4.mass()))}
-        l4.close()
+        extra = {}
 
-    # ---- the reference arm's own workload in the reference's own mode (N = 1 only): D3Q27, SPLIT moments, fp64
-    # equilibrium, zero-inflow edges, table reflection built from the OBJ fixture on the GPU, plane source, force
-    # accumulator, driven through the four per-phase calls like the CLI -- the like-for-like number for --impl reference
-    refmode = None
-    if world == 1 and not args.no_extra:
+        def probe(name, eng, bc, body):
+            l = lb.Lattice(nx, gy, gz, None, None, lb.FluidData(1.0, tau), 1.0 / gx, q=q, bc=bc, moment_mode=lb.MOMENT_STANDARD,
+                           eq_precision=lb.EQ_FP32, boundary_mode=lb.BOUNDARY_BOUNCE_BACK, device=local, engine=eng)
+            fill_state(with_body=body)
+            if body:
+                l.set_solid_mask(interior)
+            l.load_populations(hf)
+            if body:
+                set_inflow(l)
+                l.setReflectionData(lb.ReflectionData())
+            l.step(4)
+            l.sync()
+            ms2, n2 = l.step_timed(40)
+            cells = live_local if body else cells_total
+            gbs2 = cells * 40 * b_alg / (ms2 * 1e-3) / 1e9
+            extra[name] = {"mflups": cells * 40 / (ms2 * 1e-3) / 1e6, "gbs": gbs2, "frac": gbs2 / peak, "ms_per_step": ms2 / 40,
+                           "launches_per_step": n2 / 40, "state_gb": l.layout().state_bytes * l.layout().n_buffers / 1e9}
+            l.close()
+
+        # the same workload on the other engine, and both engines on an all-fluid lattice of the same size
+        other = lb.ENGINE_PULL2 if engine == lb.ENGINE_INPLACE else lb.ENGINE_INPLACE
+        probe("obstacle_two_buffer" if other == lb.ENGINE_PULL2 else "obstacle_in_place_single_buffer", other,
+              (lb.BC_PERIODIC, lb.BC_WALL, lb.BC_WALL), True)
+        probe("dense_two_buffer", lb.ENGINE_PULL2, (lb.BC_PERIODIC, lb.BC_PERIODIC, lb.BC_ZERO_INFLOW), False)
+        probe("in_place_single_buffer", lb.ENGINE_INPLACE, (lb.BC_PERIODIC,) * 3, False)
+
+        # ---- the reference arm's own workload in the reference's own mode: D3Q27, SPLIT moments, fp64 equilibrium,
+        # zero-inflow edges, table reflection built from the OBJ fixture on the GPU, plane source, force accumulator --
+        # the like-for-like number for --impl reference (same size, same arithmetic, same phases)
         n = args.ref_size
         obj = os.path.join(ROOT, "tests", "golden", "obj", "cube_angled.obj")
         flow27 = source_flow(27)
-        l3 = lb.Lattice(n, n, n, None, None, lb.FluidData(1.0, tau), float(np.float32(1.0 / n)), device=local)   # defaults = reference behaviour
-        start = np.zeros(n * n * n, dtype=lb.LATTICE_POINT)
-        start["f"] = flow27[None, :]
-        l3.load_data(start)
-        del start
-        t_geo = time.perf_counter()
-        l3.insertModel(obj)
-        l3.preProcessModel()
-        l3.sync()
-        t_geo = time.perf_counter() - t_geo
-        l3.setFlowData(lb.FlowData(lb.FlowCriterion.ptestPlaneCriteria, flow27))
-        l3.setReflectionData(lb.ReflectionData())
-        l3.step(3)
-        l3.sync()
-        ms3, _ = l3.step_timed(20)
-        st3 = l3.stats()
-        refmode = {"mlups": n ** 3 * 20 / (ms3 * 1e-3) / 1e6, "ms_per_step": ms3 / 20,
-                   "config": "%d^3 D3Q27, reference arithmetic (fp64 equilibrium, SPLIT moments), zero-inflow edges, table reflection "
-                             "(%d links), plane source, force accumulator" % (n, st3["links"]),
-                   "geometry_seconds": t_geo, "geometry": "lbm_insert_model + lbm_preprocess_model on the GPU (voxelise %d^3 cells, build tables)" % n}
-        l3.close()
+        try:
+            l3 = lb.Lattice(n, n, n, None, None, lb.FluidData(1.0, tau), float(np.float32(1.0 / n)), device=local)   # defaults = reference behaviour
+            f27 = torch.empty((27, n, n, n), dtype=torch.float32, device="cuda")
+            for i in range(27):
+                f27[i] = float(flow27[i])
+            l3.load_populations(f27)
+            del f27
+            torch.cuda.empty_cache()
+            t_geo = time.perf_counter()
+            l3.insertModel(obj)
+            l3.preProcessModel()
+            l3.sync()
+            t_geo = time.perf_counter() - t_geo
+            l3.setFlowData(lb.FlowData(lb.FlowCriterion.ptestPlaneCriteria, flow27))
+            l3.setReflectionData(lb.ReflectionData())
+            l3.step(3)
+            l3.sync()
+            ms3, _ = l3.step_timed(20)
+            st3 = l3.stats()
+            refmode = {"mlups": n ** 3 * 20 / (ms3 * 1e-3) / 1e6, "ms_per_step": ms3 / 20,
+                       "config": "%d^3 D3Q27, reference arithmetic (fp64 equilibrium, SPLIT moments), zero-inflow edges, table reflection "
+                                 "(%d links), plane source, force accumulator: the --impl reference workload on this library" % (n, st3["links"]),
+                       "geometry_seconds": t_geo, "geometry": "lbm_insert_model + lbm_preprocess_model on the GPU (voxelise %d^3 cells, build tables)" % n}
+            l3.close()
+        except Exception as exc:      # noqa: BLE001
+            refmode = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
+        # ---- BASELINE.json configs[0] on the GPU: 64^3, 1000 steps of the CLI loop in the reference's own mode.
+        # 2.6e5 cells fit the L2: this line is bound by launch latency, not by bandwidth.
+        n1, spacing1, flow1, obj1 = config1_inputs()
+        l5 = lb.Lattice(n1, n1, n1, None, None, lb.FluidData(1.0, 1.0), spacing1, device=local)
+        start = np.zeros(n1 ** 3, dtype=lb.LATTICE_POINT)
+        start["f"] = flow1[None, :]
+        l5.load_data(start)
+        l5.insertModel(obj1)
+        l5.preProcessModel()
+        l5.setFlowData(lb.FlowData(lb.FlowCriterion.ptestPlaneCriteria, flow1))
+        l5.setReflectionData(lb.ReflectionData())
+        l5.step(10)
+        l5.sync()
+        ms5, n5 = l5.step_timed(1000)
+        config1 = {"workload": "BASELINE configs[0]: reference test geometry %d^3 D3Q27, reference mode, 1000 steps" % n1,
+                   "mlups": n1 ** 3 * 1000 / (ms5 * 1e-3) / 1e6, "ms_per_step": ms5 / 1000, "launches_per_step": n5 / 1000,
+                   "note": "launch-latency bound (the lattice fits the L2)"}
+        l5.close()
 
     out = None
     if rank == 0:
@@ -355,27 +421,40 @@ def run_ours(args):
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("d3q%d_%d" % (q, S))
+                traffic = json.load(open(tp)).get("%s_d3q%d_%d" % (args.engine, q, nx if world == 1 else 0))
             except Exception:
                 traffic = None
+        eng_name = ("single-buffer AA streaming (one copy of the populations), classified 32-cell words" if engine == lb.ENGINE_INPLACE
+                    else "two-buffer fused pull, classified 32-cell words")
+        kern = ("aa_odd_kernel<%d> + aa_odd_special_kernel<%d> / aa_even_kernel<%d> + aa_even_special_kernel<%d> (odd / even step)" % (q, q, q, q)
+                if engine == lb.ENGINE_INPLACE else "step_general_kernel<%d> + step_special_kernel<%d> (one step)" % (q, q))
+        if world == 1:
+            wl = ("flow past obstacle (reference test geometry, tapered hexahedron) %dx%dx%d D3Q%d BGK, half-way bounce-back, periodic in x, "
+                  "walls in y/z, initial u=(0.04,0,0), plane source at x=0, force accumulator on" % (gx, gy, gz, q))
+        else:
+            wl = ("flow past obstacles %dx%dx%d D3Q%d BGK (N=8: the 1024^3 domain), %d x-slabs of %dx%dx%d joined by %s; per slab four copies "
+                  "of the reference test geometry (squeezed to %dx%dx%d, tiled 2x2 in y/z), half-way bounce-back, periodic in x, walls in "
+                  "y/z, initial u=(0.04,0,0), plane source at x=0, force accumulator on"
+                  % (gx, gy, gz, q, world, nx, gy, gz,
+                     "peer-memory halos below the C ABI (no communication library in the step)" if args.transport == "peer"
+                     else "NCCL send/recv of the edge planes", nx, gy // 2, gz // 2))
         out = {
-            "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": "MLUPS", "value": mflups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "flow past obstacle (reference test geometry, tapered hexahedron, one per 512-cell box) %dx%dx%d D3Q%d BGK, "
-                                   "half-way bounce-back, periodic in x, walls in y/z, initial u=(0.04,0,0), plane source at x=0; "
-                                   "%d x-slab(s) of %dx%dx%d" % (gx, gy, gz, q, world, nx, gy, gz),
-                       "cells_per_gpu": nx * gy * gz, "tau": tau, "engine": "two-buffer fused pull, classified 32-cell words",
+            "config": {"workload": wl, "cells_per_gpu": nx * gy * gz, "live_cells_per_gpu": live_total // world, "tau": tau,
+                       "engine": eng_name, "transport": (args.transport if world > 1 else None),
+                       "counting": "value counts live (non-solid) cell updates only; mlups_all_cells counts every lattice cell",
                        "l2": "state per GPU %.1f GB >> 126 MB L2, no flush needed" % state_gb},
             "gpu_launches": int(launches),
-            "live_cells": live_total, "mflups": live_total * args.steps / (ms * 1e-3) / 1e6,
+            "live_cells": live_total, "mlups_all_cells": cells_total * args.steps / (ms * 1e-3) / 1e6,
             "hbm_gbs_per_gpu": per_gpu_gbs,
             "roofline": {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_gbs / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_cell": b_alg,
                          "algorithmic_bytes_per_launch": live_total // world * b_alg,
-                         "kernel": "step_general_kernel<%d> + step_special_kernel<%d> (one step)" % (q, q),
-                         "note": "achieved = 2*Q*4 B x live (non-solid) cells per step / CUDA-event time per step; "
+                         "kernel": kern,
+                         "note": "achieved = 2*Q*4 B x live (non-solid) cells per step / CUDA-event time per step, per GPU; "
                                  "solid cells move no bytes and are not counted"},
             "clocks": clk.summary(),
             "state_finite": finite,
@@ -386,10 +465,12 @@ def run_ours(args):
             out["other_engines"] = extra
         if refmode:
             out["reference_mode"] = refmode
+        if config1:
+            out["config1_64cubed"] = config1
     if world > 1:
         dist.barrier()
     if rank == 0 and not args.no_cpu and world == 1:
-        out["cpu_baseline"] = cpu_baseline(q)
+        out["cpu_baseline"] = cpu_baseline()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -402,6 +483,9 @@ def run_ours(args):
 # -------------------------------------------------------------------------------------------------
 
 def run_reference(args):
+    """The reference's own Lattice class and CUDA kernels, compiled unmodified for sm_100a (oracle/Makefile), driven through
+    its CLI loop on the repo arm's lattice size.  The K timed steps are split into three repetitions; `value` is the median
+    repetition (the reference allocates and frees two whole lattices per step, which makes single runs noisy)."""
     rank, world, local = dist_env()
     if rank != 0:
         return
@@ -417,6 +501,7 @@ def run_reference(args):
         n = args.ref_size
         spacing = float(np.float32(1.0 / n))
         flow = source_flow(27)
+        t_setup = time.perf_counter()
         ref = R.RefLattice(n, n, n, tau=0.6, spacing=spacing)
         cells = np.zeros(n * n * n, dtype=O.LATTICE_POINT)
         cells["f"] = flow[None, :]
@@ -427,21 +512,33 @@ def run_reference(args):
         ref.set_flow(2, flow)
         ref.set_reflection_data()
         ref.prime()
+        t_setup = time.perf_counter() - t_setup
         ref.run_cli(args.warmup)
         R.lib().ref_sync()
-        t0 = time.perf_counter()
-        ref.run_cli(args.steps)          # the CLI loop incl. its per-step force read-back; ends with a device sync
-        dt = time.perf_counter() - t0
-        v = n ** 3 * args.steps / dt / 1e6
+        reps = [args.steps // 3 + (1 if r < args.steps % 3 else 0) for r in range(3)]
+        rates, total = [], 0.0
+        for k in reps:
+            if k == 0:
+                continue
+            t0 = time.perf_counter()
+            ref.run_cli(k)                   # the CLI loop incl. its per-step force read-back; ends with a device sync
+            dt = time.perf_counter() - t0
+            total += dt
+            rates.append(n ** 3 * k / dt / 1e6)
+        v = float(np.median(rates))
         base.update({
-            "value": v, "ms_per_step": dt / args.steps * 1e3,
-            "config": {"workload": "flow past obstacle (reference test geometry) D3Q27 BGK, table reflection, plane source at x=0, "
-                                   "zero-inflow edges: the reference's own Lattice class + CUDA kernels compiled unmodified for "
-                                   "sm_100a; bounded sample %d^3 of the 512^3 workload (the reference holds 2 x 144 B/cell on the "
-                                   "device and leaks a 144 B/cell host array per retrieve_data call)" % n},
+            "value": v, "ms_per_step": n ** 3 / v / 1e3,
+            "repetitions": {"steps": [k for k in reps if k], "mlups": rates, "statistic": "median", "seconds_total": total},
+            "setup_seconds": t_setup,
+            "config": {"workload": "flow past obstacle (reference test geometry) %dx%dx%d D3Q27 BGK, table reflection, plane source at x=0, "
+                                   "zero-inflow edges: the reference's own Lattice class + CUDA kernels compiled unmodified for sm_100a, "
+                                   "driven through its CLI loop (LatticeBoltzmannCuda.cpp:85-93); the reference has one velocity set "
+                                   "(D3Q27), one boundary model and one edge rule, so Q / boundary / edges are the reference's, the "
+                                   "lattice size is the repo arm's.  The same workload on this library: `reference_mode` in the "
+                                   "repo arm's line" % (n, n, n)},
             "cpu_baseline": {"value": v, "unit": "MLUPS", "cores": 0, "kind": "reference",
-                             "sample": "%d^3, %d steps; the reference has no CPU path (SURVEY.md D2): this is its GPU path on the "
-                                       "same B200, host loop of LatticeBoltzmannCuda.cpp:85-93" % (n, args.steps)},
+                             "sample": "%d^3, %d steps in 3 repetitions (median); the reference has no CPU path (SURVEY.md D2): this is its "
+                                       "GPU path on the same B200, host loop of LatticeBoltzmannCuda.cpp:85-93" % (n, args.steps)},
             "e2e": {"value": v, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         })
     except Exception as exc:      # noqa: BLE001

@@ -73,6 +73,15 @@ enum lbm_boundary_mode { LBM_BOUNDARY_REFLECT = 0, LBM_BOUNDARY_BOUNCE_BACK = 1 
  * skipped); PHYSICAL uses slot/3 for every slot. */
 enum lbm_force_mode { LBM_FORCE_REFERENCE_SLOT_INDEX = 0, LBM_FORCE_PHYSICAL = 1 };
 
+/* how the force is summed.  F64_PARTIALS: per-warp sums into 128 double slots (order-independent to ~1e-15, the
+ * default).  REFERENCE_FP32: the reference's accumulator -- ONE float triple that every reflected slot adds to
+ * (SimCalcFuncs.cu:181-183) -- in a fixed order: solid cells in host order, slots ascending, one fused multiply-add per
+ * term.  The reference's atomics arrive in no particular order, so its own sum is one of many; this mode fixes the order
+ * the CPU oracle uses (oracle/lbm_oracle.c lbo_reflect) and reproduces that float sum, including the increments a large
+ * fp32 accumulator absorbs.  Table reflection on the two-buffer engine, one handle (not slabs); it adds a short serial
+ * kernel per step. */
+enum lbm_force_accum { LBM_FORCE_ACCUM_F64_PARTIALS = 0, LBM_FORCE_ACCUM_REFERENCE_FP32 = 1 };
+
 /* phases of one reference step, in the CLI's order (LatticeBoltzmannCuda.cpp:89-92) */
 enum lbm_phase {
     LBM_PHASE_STREAM = 1,     /* Lattice::simulateStreaming   -> run_calculate_streaming   */
@@ -108,7 +117,8 @@ typedef struct lbm_config {
     int32_t engine;               /* enum lbm_engine */
     int32_t device;               /* CUDA device ordinal, -1: current device */
     float   wall_u[6][3];         /* wall velocity for LBM_BC_WALL faces, index axis*2 + side(0 low,1 high) */
-    int32_t reserved[8];
+    int32_t force_accum;          /* enum lbm_force_accum */
+    int32_t reserved[7];
 } lbm_config;
 
 /* fills *cfg with the reference's behaviour: q=27, tau=1, zero inflow, SPLIT moments,
@@ -150,7 +160,11 @@ LBM_API int lbm_set_source(lbm_handle h, int kind, const int32_t lo[3], const in
 
 /* Lattice::setReflectionData / retrieve_reflection_data (Lattice.cpp:61-71,438-443) */
 LBM_API int lbm_set_force_accumulator(lbm_handle h, int enable, const float init[3]);
+LBM_API int lbm_set_force_accumulator_f64(lbm_handle h, int enable, const double init[3]);
 LBM_API int lbm_get_force(lbm_handle h, float out[3]);
+/* the same sum before it is narrowed to the reference's float triple (the kernels keep per-warp partial sums in double):
+ * for checkpoints and for adding up the slabs of a decomposed lattice */
+LBM_API int lbm_get_force_f64(lbm_handle h, double out[3]);
 
 /* RunCudaFunctions::run_prime_points (SimCalcFuncs.cu:240-243): coordinates are implicit
  * in this layout, so this only validates the handle. */
@@ -161,6 +175,15 @@ LBM_API int lbm_stream(lbm_handle h);
 LBM_API int lbm_reflect(lbm_handle h);
 LBM_API int lbm_collide(lbm_handle h);
 LBM_API int lbm_source(lbm_handle h);
+
+/* RunCudaFunctions::run_calculate_collision(blocks, threads, lattice, timescale) (SimCalcFuncs.cu:225-228): one collision
+ * phase with the timescale of THIS call; the handle's own tau (FluidData) is unchanged. */
+LBM_API int lbm_collide_tau(lbm_handle h, float timescale);
+/* RunCudaFunctions::run_calculate_reflections_data(blocks, threads, lattice, temp, ReflectionData *) (SimCalcFuncs.cu:
+ * 235-238): one reflect phase whose force is ADDED to the three floats at `xyz` -- the caller's ReflectionData, in device
+ * memory like the reference's d_reflectionData, or in host memory -- whether or not the handle's own accumulator
+ * (lbm_set_force_accumulator) is on.  NULL: a plain lbm_reflect. */
+LBM_API int lbm_reflect_accumulate(lbm_handle h, float *xyz);
 
 /* n fused steps; each equals stream, reflect, collide, source in that order
  * (LatticeBoltzmannCuda.cpp:89-92).  lbm_step_phases runs n fused steps of a subset, e.g.
@@ -209,6 +232,31 @@ LBM_API int lbm_fill_ghosts(lbm_handle h);
  * (c_x = +1 slots of padded plane 0, c_x = -1 slots of padded plane nx+1); this moves them into the edge planes,
  * except where the slot holds this slab's own bounced population (y/z wall, solid neighbour). */
 LBM_API int lbm_inplace_merge_edges(lbm_handle h);
+
+/* ---- slabs with peer-memory halos: the exchange below this interface ---------------------------------------------
+ * The reference runs on one GPU (no cudaSetDevice anywhere); a `Lattice` that spans the GPUs of a box is
+ * a build extension with one requirement: the same answer as one GPU.  One handle per slab (x axis LBM_BC_HALO).  After
+ * lbm_halo_connect a slab's edge cells read (two-buffer engine) or read and write (single-buffer engine) the
+ * neighbouring slab's edge plane where it lies -- peer memory over NVLink, no ghost-plane copies, no communication
+ * library -- and lbm_step / lbm_step_phases order the slabs with one epoch word per face (csrc/lbm_halo.cu).  All slabs
+ * of a domain must take the same steps.  Before reading state back (downloads, moments, mass) synchronise every slab
+ * (lbm_sync on each; across processes also a barrier): on the single-buffer engine after an odd number of steps part of
+ * an edge cell's state sits in the neighbour's memory and is fetched from there.
+ *   one process, several GPUs : create the handles (cfg.device), export + connect them, then lbm_group_step;
+ *   one process per GPU       : export, exchange the blobs (any transport), connect, then lbm_step on every rank. */
+#define LBM_HALO_BLOB_BYTES 320
+/* describes this slab to its neighbours (same-process pointers and CUDA IPC handles of its buffers); resets the epoch,
+ * so every slab exports before any slab connects, and no slab steps between its export and its connect */
+LBM_API int lbm_halo_export(lbm_handle h, void *blob, size_t blob_bytes);
+/* lo_blob / hi_blob: the export of the slab below / above (NULL: none, the domain ends there with zero inflow; the
+ * single-buffer engine needs both).  A ring closes a periodic x axis; one slab may be its own neighbour. */
+LBM_API int lbm_halo_connect(lbm_handle h, const void *lo_blob, const void *hi_blob);
+LBM_API int lbm_halo_disconnect(lbm_handle h);
+/* number of handshakes that gave up waiting for a neighbour (LBM_HALO_TIMEOUT_MS, default 20000); 0 in a healthy run.
+ * lbm_sync returns LBM_ERR_STATE when it is not 0. */
+LBM_API int lbm_halo_timeouts(lbm_handle h, unsigned long long *count);
+/* n steps of all slabs held by ONE process, in lockstep (every slab's "ready" signal is queued before any slab waits) */
+LBM_API int lbm_group_step(lbm_handle *slabs, int count, int n, unsigned phases);
 
 /* layout facts for tools: padded dims and strides in floats */
 typedef struct lbm_layout {

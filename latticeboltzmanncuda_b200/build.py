@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblbm_b200.so")
-SOURCES = ["lbm_kernels.cu", "lbm_capi.cu", "lbm_geometry.cu", "lbm_inplace.cu"]
+SOURCES = ["lbm_kernels.cu", "lbm_capi.cu", "lbm_geometry.cu", "lbm_inplace.cu", "lbm_halo.cu"]
 # per-file extra flags: the geometry predicates must evaluate identically on host and device
 EXTRA = {"lbm_geometry.cu": ["-fmad=false"]}
 HEADERS = ["d3q.h", "lbm_device.h", "lbm_internal.h", "lbm_collide.inl", os.path.join("..", "..", "include", "lbm_b200.h")]

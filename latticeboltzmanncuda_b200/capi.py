@@ -16,9 +16,11 @@ MOMENT_REFERENCE, MOMENT_STANDARD = 0, 1
 EQ_FP32, EQ_FP64 = 0, 1
 BOUNDARY_REFLECT, BOUNDARY_BOUNCE_BACK = 0, 1
 FORCE_REFERENCE_SLOT_INDEX, FORCE_PHYSICAL = 0, 1
+FORCE_ACCUM_F64_PARTIALS, FORCE_ACCUM_REFERENCE_FP32 = 0, 1
 PHASE_STREAM, PHASE_REFLECT, PHASE_COLLIDE, PHASE_SOURCE, PHASE_ALL = 1, 2, 4, 8, 15
 SOURCE_NONE, SOURCE_BOX = 0, 1
 ENGINE_AUTO, ENGINE_PULL2, ENGINE_INPLACE, ENGINE_TMA = range(4)
+HALO_BLOB_BYTES = 320
 
 # simulation/include/LatticePoint.h:9-17 (144 B) and :3-7 (380 B) as numpy record types
 LATTICE_POINT = np.dtype({
@@ -43,7 +45,8 @@ class Config(C.Structure):
         ("engine", C.c_int32),
         ("device", C.c_int32),
         ("wall_u", (C.c_float * 3) * 6),
-        ("reserved", C.c_int32 * 8),
+        ("force_accum", C.c_int32),
+        ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -82,12 +85,16 @@ SYMBOLS = [
     ("lbm_set_reflection_table", _i, [_vp, _vp, _vp, _i]),
     ("lbm_set_source", _i, [_vp, _i, _vp, _vp, _vp]),
     ("lbm_set_force_accumulator", _i, [_vp, _i, _vp]),
+    ("lbm_set_force_accumulator_f64", _i, [_vp, _i, _vp]),
     ("lbm_get_force", _i, [_vp, _vp]),
+    ("lbm_get_force_f64", _i, [_vp, _vp]),
     ("lbm_prime_points", _i, [_vp]),
     ("lbm_stream", _i, [_vp]),
     ("lbm_reflect", _i, [_vp]),
     ("lbm_collide", _i, [_vp]),
     ("lbm_source", _i, [_vp]),
+    ("lbm_collide_tau", _i, [_vp, C.c_float]),
+    ("lbm_reflect_accumulate", _i, [_vp, _vp]),
     ("lbm_step", _i, [_vp, _i]),
     ("lbm_step_phases", _i, [_vp, _i, _u]),
     ("lbm_step_timed", _i, [_vp, _i, _u, C.POINTER(C.c_float), C.POINTER(_i)]),
@@ -106,6 +113,11 @@ SYMBOLS = [
     ("lbm_step_commit", _i, [_vp]),
     ("lbm_fill_ghosts", _i, [_vp]),
     ("lbm_inplace_merge_edges", _i, [_vp]),
+    ("lbm_halo_export", _i, [_vp, _vp, C.c_size_t]),
+    ("lbm_halo_connect", _i, [_vp, _vp, _vp]),
+    ("lbm_halo_disconnect", _i, [_vp]),
+    ("lbm_halo_timeouts", _i, [_vp, C.POINTER(C.c_ulonglong)]),
+    ("lbm_group_step", _i, [C.POINTER(_vp), _i, _i, _u]),
     ("lbm_get_layout", _i, [_vp, C.POINTER(Layout)]),
     ("lbm_get_stats", _i, [_vp, C.POINTER(Stats)]),
     ("lbm_mesh_load", _i, [C.c_char_p, C.POINTER(_vp)]),

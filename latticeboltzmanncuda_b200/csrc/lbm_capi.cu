@@ -134,9 +134,13 @@ int rebuild_special(lbm_handle h)
         // to each other again, so neighbouring warps share sectors and DRAM pages like in the dense kernels,
         // and the entries of a range of planes become a range of the list
         std::vector<uint32_t> list(n);
-        CK(cudaMemcpy(list.data(), h->special_list, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        // (all transfers on the handle's stream: it is a non-blocking stream, so a cudaMemcpy on the legacy default stream
+        // would not be ordered against the kernels that read the list next)
+        CK(cudaMemcpyAsync(list.data(), h->special_list, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
         std::sort(list.begin(), list.end());
-        CK(cudaMemcpy(h->special_list, list.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(h->special_list, list.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));        // `list` is pageable and goes out of scope
         for (int x = 0; x <= g.nx; ++x) {
             const uint64_t first_word = (uint64_t)(x + 1) * g.yp * g.wz;      // mask words of padded plane x + 1 start here
             h->special_start[x] = (uint32_t)(std::lower_bound(list.begin(), list.end(), first_word,
@@ -202,6 +206,10 @@ void fill_params(lbm_handle h, StepParams& p, unsigned phases, int x0, int x1)
     }
     p.force = (h->force_on && (h->nlinks || h->cfg.boundary_mode == LBM_BOUNDARY_BOUNCE_BACK)) ? h->force : nullptr;
     p.force_mode = h->cfg.force_mode;
+    if (p.force && h->force32 && h->n_force_terms) {
+        p.link_rank = h->link_rank;
+        p.force_moved = h->force_moved;
+    }
     p.src_on = h->src_on;
     for (int a = 0; a < 3; ++a) { p.src_lo[a] = h->src_lo[a]; p.src_hi[a] = h->src_hi[a]; p.bc[a] = h->cfg.bc[a]; }
     std::memcpy(p.wall_u, h->cfg.wall_u, sizeof p.wall_u);
@@ -214,6 +222,18 @@ void fill_params(lbm_handle h, StepParams& p, unsigned phases, int x0, int x1)
         p.pop_off[i] = (long long)i * h->g.np;
         p.pull_off[i] = p.pop_off[i] - ((long long)dir_c(i, 0) * h->g.plane + (long long)(dir_c(i, 1) * h->g.zp + dir_c(i, 2)));
     }
+    if (h->halo.connected) {
+        // a pull through a slab face reads the neighbour's current buffer where it lies: ghost plane 0 is the low
+        // neighbour's last plane, ghost plane nx + 1 the high neighbour's first plane
+        p.xdelta_on = 1;
+        for (int side = 0; side < 2; ++side) {
+            if (!h->halo.has[side]) continue;
+            const float* peer = h->halo.peer_buf[side][h->cur ^ h->halo.peer_cur_xor[side]];
+            const long long planes = side == 0 ? (long long)h->halo.peer_nx[0] : -(long long)h->g.nx;
+            const long long apart = (long long)(((intptr_t)peer - (intptr_t)p.fin) / (intptr_t)sizeof(float)) + planes * h->g.plane;
+            for (int i = 0; i < 27; ++i) p.xdelta[side][i] = apart + (long long)i * h->halo.np_diff[side];
+        }
+    }
 }
 
 // is the dense kernel (pull + collide on an all-fluid lattice) enough for these phases?
@@ -222,6 +242,7 @@ bool fast_path_ok(lbm_handle h, unsigned phases)
     if (!(phases & PH_STREAM) || !(phases & PH_COLLIDE)) return false;
     if (h->cfg.bc[2] != LBM_BC_ZERO_INFLOW) return false;     // periodic / wall z edges are resolved by the general kernels
     if (h->any_solid) return false;
+    if (h->halo.connected) return false;                      // the dense kernel knows nothing of neighbouring slabs
     if ((phases & PH_REFLECT) && h->nlinks) return false;
     if ((phases & PH_SOURCE) && h->src_on) return false;
     return true;
@@ -279,7 +300,23 @@ void fill_inplace(lbm_handle h, InplaceParams& ip)
     ip.tau = h->cfg.tau;
     ip.inv_tau = 1.0f / h->cfg.tau;
     ip.parity = h->aa_parity;
+    {
+        // on by default past the reach of the last-level TLB (2 MB pages; measured on B200: 59 GB runs at full speed,
+        // 80 GB does not); LBM_TLB_AHEAD=0 switches it off, another value sets the distance in planes
+        static const int env_ahead = [] { const char* e = getenv("LBM_TLB_AHEAD"); return e ? atoi(e) : -1; }();
+        static const int env_mode = [] { const char* e = getenv("LBM_TLB_MODE"); return e ? atoi(e) : 1; }();
+        const bool big = h->state_bytes() > (size_t(60) << 30);
+        ip.tlb_ahead = env_ahead >= 0 ? env_ahead : (big ? 4 : 0);
+        ip.tlb_mode = env_mode;
+    }
     for (int a = 0; a < 3; ++a) ip.bc[a] = h->cfg.bc[a];
+    if (h->cfg.bc[0] == LBM_BC_HALO) {
+        // x slabs: the neighbouring slab's edge plane in its own allocation (lbm_halo_connect), or this slab's own
+        // ghost plane when the caller moves the planes (no connection)
+        for (int side = 0; side < 2; ++side)
+            for (int i = 0; i < 27; ++i)
+                ip.xshift[side][i] = h->halo.delta_inplace[side] + (long long)i * h->halo.np_diff[side];
+    }
     std::memcpy(ip.wall_u, h->cfg.wall_u, sizeof ip.wall_u);
     if (h->any_solid) {       // obstacles: the mask, the word classes and the special list of rebuild_special
         ip.solid = h->solid;
@@ -301,39 +338,120 @@ int inplace_only(lbm_handle h, const char* what)
     return LBM_OK;
 }
 
-int one_step(lbm_handle h, unsigned phases)
+// LBM_FORCE_ACCUM_REFERENCE_FP32: the links of this step have stored what they moved; add the terms up in the oracle's order
+int force_reference_sum(lbm_handle h, unsigned phases)
+{
+    if (!(phases & PH_REFLECT) || !h->force_on || !h->force32 || !h->n_force_terms) return LBM_OK;
+    CK(launch_force_sequential(h->force_moved, h->force_coef, (long long)h->n_force_terms, h->force32, h->stream));
+    h->launches += 1;
+    return LBM_OK;
+}
+
+// planes [xa, xb) of one in-place step on stream s
+int inplace_range(lbm_handle h, unsigned phases, int xa, int xb, cudaStream_t s)
+{
+    if (xb <= xa) return LBM_OK;
+    InplaceParams ip;
+    fill_inplace(h, ip);
+    if (!(phases & PH_SOURCE)) ip.src_on = 0;
+    ip.x0 = xa; ip.x1 = xb;
+    if (ip.n_special && (int)h->special_start.size() == h->g.nx + 1) {
+        ip.special_k0 = h->special_start[xa];
+        ip.n_special = (long long)h->special_start[xb] - (long long)h->special_start[xa];
+    }
+    int launched = 0;
+    CK(launch_inplace_step(ip, h->cfg.q, h->cfg.moment_mode, h->cfg.eq_precision == LBM_EQ_FP64, s, &launched));
+    h->launches += launched;
+    return LBM_OK;
+}
+
+// First half of a step: everything that needs no neighbour.  On a slab with peer-memory halos it ends with the signal
+// "my previous step is complete, my edge planes are yours to read" to both neighbours.
+int step_a(lbm_handle h, unsigned phases)
 {
     if (h->inplace) {
         if (!(phases & PH_STREAM) || !(phases & PH_COLLIDE))
             return fail(LBM_ERR_UNSUPPORTED, "the in-place engine runs fused stream + collide steps only");
-        InplaceParams ip;
-        fill_inplace(h, ip);
-        if (!(phases & PH_SOURCE)) ip.src_on = 0;
-        int launched = 0;
         if (h->aa_dirty) {
             // first step after the mask or the state was set: solid cells hold zeros from here on
-            if (ip.solid) {
+            if (h->any_solid) {
                 if (h->aa_parity != 0) return fail(LBM_ERR_STATE, "in-place engine: solid cells can only be cleared in the parked form");
+                InplaceParams ip;
+                fill_inplace(h, ip);
                 CK(launch_inplace_zero_solid(ip, h->cfg.q, h->stream));
-                ++launched;
+                h->launches += 1;
             }
             h->aa_dirty = false;
         }
-        CK(launch_inplace_step(ip, h->cfg.q, h->cfg.moment_mode, h->cfg.eq_precision == LBM_EQ_FP64, h->stream, &launched));
-        h->launches += launched;
-        h->aa_parity ^= 1;
-        return LBM_OK;
+    } else {
+        if (h->pending_commit) return fail(LBM_ERR_STATE, "lbm_step_range in flight: call lbm_step_commit first");
+        if (phases & PH_STREAM) {
+            int rc = fill_ghosts(h, true);
+            if (rc) return rc;
+        }
     }
-    if (h->pending_commit) return fail(LBM_ERR_STATE, "lbm_step_range in flight: call lbm_step_commit first");
-    if (phases & PH_STREAM) {
-        int rc = fill_ghosts(h, true);
+    if (h->halo.connected) {
+        CK(cudaEventRecord(h->halo.ev_pre, h->stream));
+        CK(cudaStreamWaitEvent(h->halo.edge, h->halo.ev_pre, 0));
+        int rc = lbm_internal_halo_signal(h);
         if (rc) return rc;
     }
-    int rc = launch_range(h, phases, 0, h->g.nx, h->stream);
-    if (rc) return rc;
-    h->cur ^= 1;
-    note_step_done(h, phases);
     return LBM_OK;
+}
+
+// Second half: (slabs: wait for both neighbours' signal, then) the edge planes on the edge stream next to the interior
+// planes on the main stream, joined at the end.
+int step_b(lbm_handle h, unsigned phases)
+{
+    const int nx = h->g.nx;
+    int rc;
+    if (!h->halo.connected) {
+        if (h->inplace) {
+            if ((rc = inplace_range(h, phases, 0, nx, h->stream))) return rc;
+            h->aa_parity ^= 1;
+            return LBM_OK;
+        }
+        if ((rc = launch_range(h, phases, 0, nx, h->stream))) return rc;
+        if ((rc = force_reference_sum(h, phases))) return rc;
+        h->cur ^= 1;
+        note_step_done(h, phases);
+        return LBM_OK;
+    }
+    if ((rc = lbm_internal_halo_wait(h))) return rc;
+    // table reflection gathers through a solid cell of the neighbouring plane: two planes per face see the neighbour
+    int e = (!h->inplace && h->nlinks) ? 2 : 1;
+    cudaStream_t es = h->halo.edge;
+    if (nx < 2 * e + 1) {
+        // no interior to overlap with: the whole slab runs behind the handshake
+        rc = h->inplace ? inplace_range(h, phases, 0, nx, es) : launch_range(h, phases, 0, nx, es);
+        if (rc) return rc;
+    } else {
+        if (h->inplace) {
+            if ((rc = inplace_range(h, phases, 0, e, es))) return rc;
+            if ((rc = inplace_range(h, phases, nx - e, nx, es))) return rc;
+            if ((rc = inplace_range(h, phases, e, nx - e, h->stream))) return rc;
+        } else {
+            if ((rc = launch_range(h, phases, 0, e, es))) return rc;
+            if ((rc = launch_range(h, phases, nx - e, nx, es))) return rc;
+            if ((rc = launch_range(h, phases, e, nx - e, h->stream))) return rc;
+        }
+    }
+    CK(cudaEventRecord(h->halo.ev_edge, es));
+    CK(cudaStreamWaitEvent(h->stream, h->halo.ev_edge, 0));
+    if (h->inplace) {
+        h->aa_parity ^= 1;
+    } else {
+        h->cur ^= 1;
+        note_step_done(h, phases);
+    }
+    return LBM_OK;
+}
+
+int one_step(lbm_handle h, unsigned phases)
+{
+    int rc = step_a(h, phases);
+    if (rc) return rc;
+    return step_b(h, phases);
 }
 
 }  // namespace
@@ -342,6 +460,8 @@ int one_step(lbm_handle h, unsigned phases)
 int lbm_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
 int lbm_internal_use(lbm_handle h) { return use(h); }
 int lbm_internal_rebuild_mask(lbm_handle h, const uint8_t* dev_bytes, int has_x_ghost) { return rebuild_mask(h, dev_bytes, has_x_ghost); }
+int lbm_internal_step_a(lbm_handle h, unsigned phases) { return step_a(h, phases); }
+int lbm_internal_step_b(lbm_handle h, unsigned phases) { return step_b(h, phases); }
 
 // ---- C ABI -------------------------------------------------------------------------------------
 
@@ -371,7 +491,7 @@ LBM_API int lbm_create(const lbm_config* cfg, lbm_handle* out)
     if (!cfg || !out) return fail(LBM_ERR_INVALID, "null argument");
     *out = nullptr;
     if (cfg->nx < 1 || cfg->ny < 1 || cfg->nz < 1) return fail(LBM_ERR_INVALID, "lattice extents must be >= 1");
-    if (cfg->nx > 65535 || cfg->ny > 65535 * 8) return fail(LBM_ERR_INVALID, "lattice extent too large for one launch");
+    if (cfg->nx > 65535 || cfg->ny > 65535) return fail(LBM_ERR_INVALID, "lattice extent too large for one launch (nx, ny <= 65535)");
     if (cfg->q != 19 && cfg->q != 27) return fail(LBM_ERR_INVALID, "q must be 19 or 27");
     if (!(cfg->tau > 0.0f)) return fail(LBM_ERR_INVALID, "tau must be positive");
     for (int a = 0; a < 3; ++a) {
@@ -380,6 +500,11 @@ LBM_API int lbm_create(const lbm_config* cfg, lbm_handle* out)
     }
     if (cfg->engine != LBM_ENGINE_AUTO && cfg->engine != LBM_ENGINE_PULL2 && cfg->engine != LBM_ENGINE_INPLACE)
         return fail(LBM_ERR_UNSUPPORTED, "engine %d is not built in this version", cfg->engine);
+    if (cfg->force_accum != LBM_FORCE_ACCUM_F64_PARTIALS && cfg->force_accum != LBM_FORCE_ACCUM_REFERENCE_FP32)
+        return fail(LBM_ERR_INVALID, "bad force_accum");
+    if (cfg->force_accum == LBM_FORCE_ACCUM_REFERENCE_FP32 &&
+        (cfg->engine == LBM_ENGINE_INPLACE || cfg->boundary_mode != LBM_BOUNDARY_REFLECT || cfg->bc[0] == LBM_BC_HALO))
+        return fail(LBM_ERR_UNSUPPORTED, "LBM_FORCE_ACCUM_REFERENCE_FP32 restates the reference's accumulator: table reflection on the two-buffer engine, one handle");
     if (cfg->engine == LBM_ENGINE_INPLACE)
         for (int a = 0; a < 3; ++a)
             if (cfg->bc[a] != LBM_BC_PERIODIC && cfg->bc[a] != LBM_BC_WALL && cfg->bc[a] != LBM_BC_HALO)
@@ -429,6 +554,10 @@ LBM_API int lbm_create(const lbm_config* cfg, lbm_handle* out)
     CKB(cudaMalloc(&h->force, 3 * FORCE_SLOTS * sizeof(double)));
     CKB(cudaMemsetAsync(h->force, 0, 3 * FORCE_SLOTS * sizeof(double), h->stream));
     CKB(cudaMalloc(&h->diag, 4 * sizeof(double)));
+    if (cfg->force_accum == LBM_FORCE_ACCUM_REFERENCE_FP32) {
+        CKB(cudaMalloc(&h->force32, 3 * sizeof(float)));
+        CKB(cudaMemsetAsync(h->force32, 0, 3 * sizeof(float), h->stream));
+    }
 #undef CKB
     {
         int rc = rebuild_special(h);      // the word classes exist even without geometry
@@ -446,9 +575,12 @@ LBM_API int lbm_destroy(lbm_handle h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->side) cudaStreamSynchronize(h->side);
+    lbm_internal_halo_release(h);
+    cudaFree(h->moments_scratch);
     for (int b = 0; b < 2; ++b) cudaFree(h->buf[b]);
     cudaFree(h->solid); cudaFree(h->cls); cudaFree(h->cellinfo); cudaFree(h->special_list); cudaFree(h->solid_bytes); cudaFree(h->tmask); cudaFree(h->tprefix); cudaFree(h->toff);
     cudaFree(h->reflected); cudaFree(h->links); cudaFree(h->force); cudaFree(h->diag); cudaFree(h->flag);
+    cudaFree(h->link_rank); cudaFree(h->force_moved); cudaFree(h->force_coef); cudaFree(h->force32);
     cudaFree(h->staging);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -468,7 +600,13 @@ LBM_API int lbm_sync(lbm_handle h)
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->side));
     CK(cudaStreamSynchronize(h->bulk));
+    if (h->halo.edge) CK(cudaStreamSynchronize(h->halo.edge));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->halo.connected) {
+        unsigned long long lost = 0;
+        CK(cudaMemcpy(&lost, h->halo.flags + 2, sizeof lost, cudaMemcpyDeviceToHost));
+        if (lost) return fail(LBM_ERR_STATE, "%llu halo handshake(s) timed out: a neighbouring slab did not take the same steps", lost);
+    }
     return LBM_OK;
 }
 
@@ -600,18 +738,20 @@ LBM_API int lbm_download_f_soa(lbm_handle h, float* f)
     int rc = use(h);
     if (rc) return rc;
     if (!f) return fail(LBM_ERR_INVALID, "null buffer");
-    if ((rc = ensure_staging(h))) return rc;
     const Geom& g = h->g;
-    const size_t per_plane = (size_t)g.ny * g.nz * sizeof(float);
-    if (per_plane > STAGING_BYTES) return fail(LBM_ERR_UNSUPPORTED, "one x-plane exceeds the staging buffer");
-    const int chunk = (int)std::max<size_t>(1, STAGING_BYTES / per_plane);
     CK(cudaStreamSynchronize(h->side));
+    if (h->halo.edge) CK(cudaStreamSynchronize(h->halo.edge));
     if (!h->inplace) {
         for (int q = 0; q < h->cfg.q; ++q)
             CK(copy_population(h, h->buf[h->cur] + (size_t)q * g.np, f + (size_t)q * g.nx * g.ny * g.nz, false, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         return LBM_OK;
     }
+    // single-buffer engine: the state is translated from the storage form through a staging buffer
+    if ((rc = ensure_staging(h))) return rc;
+    const size_t per_plane = (size_t)g.ny * g.nz * sizeof(float);
+    if (per_plane > STAGING_BYTES) return fail(LBM_ERR_UNSUPPORTED, "one x-plane exceeds the staging buffer");
+    const int chunk = (int)std::max<size_t>(1, STAGING_BYTES / per_plane);
     for (int q = 0; q < h->cfg.q; ++q) {
         float* dst = f + (size_t)q * g.nx * g.ny * g.nz;
         for (int x0 = 0; x0 < g.nx; x0 += chunk) {
@@ -734,27 +874,61 @@ LBM_API int lbm_set_reflection_table(lbm_handle h, const void* tables, const int
         }
     }
     toff.push_back((uint32_t)hl.size());
+    // LBM_FORCE_ACCUM_REFERENCE_FP32: the terms of the force sum in the oracle's order (solid cells in host order, slots
+    // ascending = ascending `order`), each with its direction coefficients (SimCalcFuncs.cu:181-183, expression shapes kept)
+    std::vector<uint32_t> rank(hl.size(), 0xffffffffu);
+    std::vector<float> coef;
+    if (h->force32) {
+        std::vector<size_t> by_order;
+        for (size_t i = 0; i < hl.size(); ++i) {
+            const int in_dir = (h->cfg.force_mode == LBM_FORCE_REFERENCE_SLOT_INDEX) ? (int)hl[i].l.slot : (int)hl[i].l.j;
+            if (in_dir < 27) by_order.push_back(i);
+        }
+        std::sort(by_order.begin(), by_order.end(), [&](size_t a, size_t b) { return hl[a].order < hl[b].order; });
+        coef.resize(3 * by_order.size());
+        for (size_t r = 0; r < by_order.size(); ++r) {
+            const Link& L = hl[by_order[r]].l;
+            const int d = L.d, in_dir = (h->cfg.force_mode == LBM_FORCE_REFERENCE_SLOT_INDEX) ? (int)L.slot : (int)L.j;
+            rank[by_order[r]] = (uint32_t)r;
+            for (int a = 0; a < 3; ++a)
+                coef[3 * r + a] = ((float)dir_c(d, a) * dir_split(d)) - ((float)dir_c(in_dir, a) * dir_split(in_dir));
+        }
+    }
     uint32_t run = 0;
     for (size_t wi = 0; wi < words; ++wi) { tprefix[wi] = run; run += (uint32_t)__builtin_popcount(tmask[wi]); }
 
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(h->tmask); cudaFree(h->tprefix); cudaFree(h->toff); cudaFree(h->links); cudaFree(h->reflected);
+    cudaFree(h->link_rank); cudaFree(h->force_moved); cudaFree(h->force_coef);
     h->tmask = h->tprefix = h->toff = h->reflected = nullptr;
+    h->link_rank = nullptr; h->force_moved = h->force_coef = nullptr;
+    h->n_force_terms = 0;
     h->links = nullptr;
     h->nlinks = 0;
     CK(cudaMalloc(&h->reflected, words * sizeof(uint32_t)));
-    CK(cudaMemcpy(h->reflected, refl.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    // uploads on the handle's stream, one synchronisation before the host vectors go away (see rebuild_special)
+    CK(cudaMemcpyAsync(h->reflected, refl.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     if (!links.empty()) {
         CK(cudaMalloc(&h->tmask, words * sizeof(uint32_t)));
         CK(cudaMalloc(&h->tprefix, words * sizeof(uint32_t)));
         CK(cudaMalloc(&h->toff, toff.size() * sizeof(uint32_t)));
         CK(cudaMalloc(&h->links, links.size() * sizeof(Link)));
-        CK(cudaMemcpy(h->tmask, tmask.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->tprefix, tprefix.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->toff, toff.data(), toff.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->links, links.data(), links.size() * sizeof(Link), cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(h->tmask, tmask.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->tprefix, tprefix.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->toff, toff.data(), toff.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->links, links.data(), links.size() * sizeof(Link), cudaMemcpyHostToDevice, h->stream));
         h->nlinks = links.size();
+        if (h->force32 && !coef.empty()) {
+            h->n_force_terms = coef.size() / 3;
+            CK(cudaMalloc(&h->link_rank, rank.size() * sizeof(uint32_t)));
+            CK(cudaMalloc(&h->force_coef, coef.size() * sizeof(float)));
+            CK(cudaMalloc(&h->force_moved, h->n_force_terms * sizeof(float)));
+            CK(cudaMemcpyAsync(h->link_rank, rank.data(), rank.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(h->force_coef, coef.data(), coef.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemsetAsync(h->force_moved, 0, h->n_force_terms * sizeof(float), h->stream));
+        }
     }
+    CK(cudaStreamSynchronize(h->stream));
     return rebuild_special(h);
 }
 
@@ -771,29 +945,58 @@ LBM_API int lbm_set_source(lbm_handle h, int kind, const int32_t lo[3], const in
 
 LBM_API int lbm_set_force_accumulator(lbm_handle h, int enable, const float init[3])
 {
+    if (!init) return lbm_set_force_accumulator_f64(h, enable, nullptr);
+    const double v[3] = {init[0], init[1], init[2]};
+    return lbm_set_force_accumulator_f64(h, enable, v);
+}
+
+LBM_API int lbm_set_force_accumulator_f64(lbm_handle h, int enable, const double init[3])
+{
     int rc = use(h);
     if (rc) return rc;
     h->force_on = enable != 0;
     double v[3 * FORCE_SLOTS] = {0.0};
     if (init) for (int a = 0; a < 3; ++a) v[a] = init[a];
     CK(cudaMemcpyAsync(h->force, v, sizeof v, cudaMemcpyHostToDevice, h->stream));
+    if (h->force32) {
+        const float v32[3] = {init ? (float)init[0] : 0.0f, init ? (float)init[1] : 0.0f, init ? (float)init[2] : 0.0f};
+        CK(cudaMemcpyAsync(h->force32, v32, sizeof v32, cudaMemcpyHostToDevice, h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
     return LBM_OK;
 }
 
-LBM_API int lbm_get_force(lbm_handle h, float out[3])
+LBM_API int lbm_get_force_f64(lbm_handle h, double out[3])
 {
     int rc = use(h);
     if (rc) return rc;
     if (!out) return fail(LBM_ERR_INVALID, "null buffer");
+    if (h->force32) {
+        float v32[3];
+        CK(cudaMemcpyAsync(v32, h->force32, sizeof v32, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int a = 0; a < 3; ++a) out[a] = v32[a];
+        return LBM_OK;
+    }
     double v[3 * FORCE_SLOTS];
+    if (h->halo.edge) CK(cudaStreamSynchronize(h->halo.edge));
     CK(cudaMemcpyAsync(v, h->force, sizeof v, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     for (int a = 0; a < 3; ++a) {
         double t = 0.0;
         for (int k = 0; k < FORCE_SLOTS; ++k) t += v[3 * k + a];
-        out[a] = (float)t;
+        out[a] = t;
     }
+    return LBM_OK;
+}
+
+LBM_API int lbm_get_force(lbm_handle h, float out[3])
+{
+    if (!out) return fail(LBM_ERR_INVALID, "null buffer");
+    double v[3];
+    int rc = lbm_get_force_f64(h, v);
+    if (rc) return rc;
+    for (int a = 0; a < 3; ++a) out[a] = (float)v[a];
     return LBM_OK;
 }
 
@@ -816,6 +1019,74 @@ LBM_API int lbm_stream(lbm_handle h) { return lbm_step_phases(h, 1, LBM_PHASE_ST
 LBM_API int lbm_reflect(lbm_handle h) { return lbm_step_phases(h, 1, LBM_PHASE_REFLECT); }
 LBM_API int lbm_collide(lbm_handle h) { return lbm_step_phases(h, 1, LBM_PHASE_COLLIDE); }
 LBM_API int lbm_source(lbm_handle h) { return lbm_step_phases(h, 1, LBM_PHASE_SOURCE); }
+
+LBM_API int lbm_collide_tau(lbm_handle h, float timescale)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    if (!(timescale > 0.0f)) return fail(LBM_ERR_INVALID, "the timescale must be positive");
+    const float keep = h->cfg.tau;
+    h->cfg.tau = timescale;
+    rc = lbm_step_phases(h, 1, LBM_PHASE_COLLIDE);
+    h->cfg.tau = keep;
+    return rc;
+}
+
+namespace {
+// xyz[a] += (sum of the partial force sums now) - (the sum before the phase)
+__global__ void add_force_delta_kernel(const double* now, const double* before, float* xyz)
+{
+    const int a = threadIdx.x;
+    if (a >= 3) return;
+    double t = 0.0;
+    for (int k = 0; k < FORCE_SLOTS; ++k) t += now[3 * k + a] - before[3 * k + a];
+    xyz[a] += (float)t;
+}
+}  // namespace
+
+LBM_API int lbm_reflect_accumulate(lbm_handle h, float* xyz)
+{
+    int rc = use(h);
+    if (rc) return rc;
+    if (!xyz) return lbm_reflect(h);
+    if (h->force32) return fail(LBM_ERR_UNSUPPORTED, "lbm_reflect_accumulate: not with LBM_FORCE_ACCUM_REFERENCE_FP32 (use the handle's accumulator)");
+    const size_t bytes = 3 * FORCE_SLOTS * sizeof(double);
+    double* before = nullptr;
+    CK(cudaMalloc(&before, bytes));
+    CK(cudaMemcpyAsync(before, h->force, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    const bool was_on = h->force_on;
+    h->force_on = true;
+    rc = lbm_step_phases(h, 1, LBM_PHASE_REFLECT);
+    h->force_on = was_on;
+    if (rc) { cudaFree(before); return rc; }
+    cudaPointerAttributes attr;
+    const bool on_device = cudaPointerGetAttributes(&attr, xyz) == cudaSuccess &&
+                           (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    if (on_device) {
+        add_force_delta_kernel<<<1, 32, 0, h->stream>>>(h->force, before, xyz);
+        rc = cudaGetLastError() == cudaSuccess ? LBM_OK : fail(LBM_ERR_CUDA, "lbm_reflect_accumulate: launch failed");
+    } else {
+        std::vector<double> a(3 * FORCE_SLOTS), b(3 * FORCE_SLOTS);
+        cudaError_t e = cudaMemcpyAsync(a.data(), h->force, bytes, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(b.data(), before, bytes, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(LBM_ERR_CUDA, "lbm_reflect_accumulate: %s", cudaGetErrorString(e));
+        else
+            for (int c = 0; c < 3; ++c) {
+                double t = 0.0;
+                for (int k = 0; k < FORCE_SLOTS; ++k) t += a[3 * k + c] - b[3 * k + c];
+                xyz[c] += (float)t;
+            }
+    }
+    if (!was_on && rc == LBM_OK) {
+        // the handle's own accumulator is off: it keeps what it held
+        if (cudaMemcpyAsync(h->force, before, bytes, cudaMemcpyDeviceToDevice, h->stream) != cudaSuccess) rc = fail(LBM_ERR_CUDA, "lbm_reflect_accumulate: restore failed");
+    }
+    cudaStreamSynchronize(h->stream);
+    cudaFree(before);
+    return rc;
+}
 
 LBM_API int lbm_step_timed(lbm_handle h, int n, unsigned phases, float* ms, int* launches)
 {
@@ -842,8 +1113,9 @@ LBM_API int lbm_moments(lbm_handle h, float* rho, float* ux, float* uy, float* u
     if (rc) return rc;
     const Geom& g = h->g;
     const size_t n = (size_t)g.nx * g.ny * g.nz;
-    float* dev = nullptr;
-    CK(cudaMalloc(&dev, 4 * n * sizeof(float)));
+    if (!h->moments_scratch) CK(cudaMalloc(&h->moments_scratch, 4 * n * sizeof(float)));   // kept for the next call
+    float* dev = h->moments_scratch;
+    if (h->halo.edge) CK(cudaStreamSynchronize(h->halo.edge));
     cudaError_t e;
     if (h->inplace) {
         InplaceParams ip;
@@ -856,7 +1128,6 @@ LBM_API int lbm_moments(lbm_handle h, float* rho, float* ux, float* uy, float* u
     for (int k = 0; k < 4 && e == cudaSuccess; ++k)
         if (outs[k]) e = cudaMemcpyAsync(outs[k], dev + (size_t)k * n, n * sizeof(float), cudaMemcpyDefault, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(dev);
     if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "moments: %s", cudaGetErrorString(e));
     return LBM_OK;
 }
@@ -1002,6 +1273,7 @@ LBM_API int lbm_step_commit(lbm_handle h)
         CK(cudaStreamWaitEvent(h->stream, h->ev_bulk, 0));
         h->bulk_used = false;
     }
+    if ((rc = force_reference_sum(h, h->pending_phases))) return rc;
     h->cur ^= 1;
     h->pending_commit = false;
     note_step_done(h, h->pending_phases);

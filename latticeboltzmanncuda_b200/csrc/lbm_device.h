@@ -15,6 +15,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "d3q.h"
@@ -38,12 +39,21 @@ struct Geom {
     }
 };
 
+// Measurement knobs (profiles/r02_notes.md, the 1024^3 study): LBM_PAD_ROWS extra rows per plane and LBM_PAD_LINES
+// extra 128-byte lines per row, so that plane and row strides stop being powers of two.  The padding is never touched.
+inline int geom_pad(const char* name)
+{
+    const char* e = getenv(name);
+    const int v = e ? atoi(e) : 0;
+    return v > 0 && v <= 64 ? v : 0;
+}
+
 inline Geom make_geom(int nx, int ny, int nz)
 {
     Geom g;
     g.nx = nx; g.ny = ny; g.nz = nz;
-    g.xp = nx + 2; g.yp = ny + 2;
-    g.zp = ((PAD_Z + nz + 1 + 31) / 32) * 32;
+    g.xp = nx + 2; g.yp = ny + 2 + geom_pad("LBM_PAD_ROWS");
+    g.zp = ((PAD_Z + nz + 1 + 31) / 32) * 32 + 32 * geom_pad("LBM_PAD_LINES");
     g.wz = g.zp / 32;
     g.plane = (long long)g.yp * g.zp;
     g.np = (long long)g.xp * g.plane;
@@ -84,6 +94,10 @@ struct StepParams {
     const Link*     links;
     double* force;            // FORCE_SLOTS x 3 partial sums or nullptr
     int   force_mode;
+    // LBM_FORCE_ACCUM_REFERENCE_FP32: instead of summing, every link stores the amount it moved at its rank in the
+    // oracle's order (link_rank, 0xffffffff = contributes nothing); force_sequential_kernel adds them up afterwards
+    const uint32_t* link_rank;
+    float* force_moved;
     int   src_on;
     int   src_lo[3], src_hi[3];
     float src_f[27];
@@ -95,6 +109,13 @@ struct StepParams {
     // pull_off[i] = i * np - (c_ix * plane + c_iy * zp + c_iz) (the slot population i is pulled from)
     long long pop_off[27];
     long long pull_off[27];
+    // x slabs with peer-memory halos (lbm_halo_connect): a pull that leaves the slab through the low / high x face reads
+    // the neighbouring slab's current buffer directly (NVLink): xdelta[side] = element distance from this slab's ghost
+    // plane to the neighbour's edge plane in the neighbour's allocation.  0 = the own ghost plane (zero inflow at the
+    // end of the domain, or planes moved by the caller).
+    // Slabs may differ in thickness, hence in population stride: the distance is kept per population.
+    long long xdelta[2][27];
+    int   xdelta_on;
 };
 
 // single-buffer (AA pattern) engine, lbm_inplace.cu
@@ -124,6 +145,20 @@ struct InplaceParams {
     int   src_on;             // additive box source, applied after the collision
     int   src_lo[3], src_hi[3];
     float src_f[27];
+    int   x0, x1;             // interior planes [x0, x1) this launch covers (the list entries of those planes: special_k0, n_special)
+    long long special_k0;
+    // shift[a][0 / 1]: element offset added to a neighbour address that leaves the lattice through the low / high edge
+    // of axis a under a periodic or halo rule.  Periodic: the far side of the own array (+/- n_a * stride_a).  Halo (x
+    // slabs): the distance from this slab's ghost plane to the neighbouring slab's edge plane IN THE NEIGHBOUR'S
+    // ALLOCATION (peer memory over NVLink, lbm_halo_connect), so that edge cells pull from and push to the neighbour
+    // directly; 0 when the caller moves ghost planes itself (lbm_plane_ptr / lbm_inplace_merge_edges).
+    // The x entries are kept per population slot (xshift[side][slot]; shift[0] is unused): neighbouring slabs may differ
+    // in thickness and therefore in population stride.
+    long long shift[3][2];
+    long long xshift[2][27];
+    // address-translation look-ahead (0 = off): one block per plane touches every 2 MB page of the plane `tlb_ahead`
+    // planes further on, so that the page walk is over when the sweep arrives (lattices beyond ~64 GB, profiles/r02_notes.md)
+    int   tlb_ahead, tlb_mode;
 };
 
 // offsets of the in-place engine for a lattice of geometry g (everything else is left untouched)
@@ -137,6 +172,11 @@ inline void set_inplace_offsets(InplaceParams& ip, const Geom& g)
         ip.push_off[i] = (long long)i * g.np + c;
         ip.park_off[i] = (long long)dir_inv(i) * g.np;
     }
+    const long long span[3] = {(long long)g.nx * g.plane, (long long)g.ny * g.zp, (long long)g.nz};
+    for (int a = 0; a < 3; ++a) { ip.shift[a][0] = span[a]; ip.shift[a][1] = -span[a]; }
+    for (int i = 0; i < 27; ++i) { ip.xshift[0][i] = span[0]; ip.xshift[1][i] = -span[0]; }
+    ip.x0 = 0; ip.x1 = g.nx;
+    ip.special_k0 = 0;
 }
 
 cudaError_t launch_inplace_zero_solid(const InplaceParams& p, int q, cudaStream_t stream);
@@ -158,6 +198,9 @@ struct LaunchCfg {
 // stream_special (optional): the special-word kernel of the general path runs there, concurrently with the rest
 // *launches (optional) is incremented by the number of kernels launched
 cudaError_t launch_step(const LaunchCfg& cfg, const StepParams& p, cudaStream_t stream, cudaStream_t stream_special, int* launches);
+
+// one thread: acc[a] = fma(moved[r], coef[3 r + a], acc[a]) for r = 0 .. n-1, in that order (the reference's single fp32 triple)
+cudaError_t launch_force_sequential(const float* moved, const float* coef, long long n, float* acc3, cudaStream_t stream);
 
 cudaError_t launch_fill_ghosts(float* f, const Geom& g, int q, const int bc[3], const float wall_u[6][3], bool include_x,
                                cudaStream_t stream, int* launches);

@@ -430,6 +430,19 @@ LBM_API int lbm_mesh_load(const char* path, lbm_mesh* out)
     fclose(fp);
     const int nf = (int)m->face_start.size() - 1;
     bool triangles = true;
+    // a face that names a vertex the file does not have (`f 0 ...`, an index beyond the vertex list) makes the mesh
+    // invalid -- nothing is inside, like any mesh CGAL's reader rejects -- instead of an out-of-range read later
+    bool indices_ok = true;
+    const int nv_all = (int)(m->v.size() / 3);
+    for (int id : m->face_idx)
+        if (id < 0 || id >= nv_all) indices_ok = false;
+    if (!indices_ok) {
+        m->face_idx.clear();
+        m->face_start.assign(1, 0);
+        m->closed = false;
+        m->valid = false;
+        return LBM_OK;
+    }
     std::map<std::pair<int, int>, int> edges;
     for (int f = 0; f < nf; ++f) {
         const int b = m->face_start[f], e = m->face_start[f + 1];

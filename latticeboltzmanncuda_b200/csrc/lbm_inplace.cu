@@ -44,14 +44,16 @@ namespace {
 #include "lbm_collide.inl"
 
 struct Edge {          // where population i of cell (x,y,z) comes from / goes to
-    long long off;     // element offset of the neighbour cell relative to the cell (valid when kind == 0)
-    int kind;          // 0 neighbour inside (possibly wrapped), 1 wall
+    long long off;     // complete element offset from the cell: population slot + neighbour cell (valid when kind == 0)
+    int kind;          // 0 neighbour inside (possibly wrapped, possibly in the neighbouring slab), 1 wall
     float term;        // moving-wall term for the bounced population
 };
 
-// neighbour of (x,y,z) in direction (dx,dy,dz) under the per-axis edge rules; `sign` = +1 for the push target
-// x + c_i, -1 for the pull source x - c_i.  For a wall the returned term is 6 w_i (c_b . u) where c_b is the
-// direction of the population after the bounce.
+// neighbour of (x,y,z) in direction c_i under the per-axis edge rules; `sign` = +1 for the push target
+// x + c_i (slot i), -1 for the pull source x - c_i (slot inv(i)).  The plain address is the precomputed
+// pull_off / push_off; an axis on which the neighbour leaves the lattice adds shift[a][side] (periodic: the far side
+// of the array, halo: the neighbouring slab's edge plane) or turns the access into the cell's own slot (wall).
+// For a wall the returned term is 6 w_i (c_b . u) where c_b is the direction of the population after the bounce.
 // AXES: bit a set = the cell may sit on an edge of axis a (the others are known to be interior).
 template <int Q, int AXES = 7>
 __device__ __forceinline__ Edge edge_lookup(const InplaceParams& p, int i, int x, int y, int z, int sign)
@@ -60,17 +62,14 @@ __device__ __forceinline__ Edge edge_lookup(const InplaceParams& p, int i, int x
     const int c[3] = {sign * dir_c(i, 0), sign * dir_c(i, 1), sign * dir_c(i, 2)};
     const int n[3] = {g.nx, g.ny, g.nz};
     const int pos[3] = {x, y, z};
-    const long long stride[3] = {g.plane, (long long)g.zp, 1};
     Edge e;
-    e.off = 0; e.kind = 0; e.term = 0.0f;
+    e.off = sign < 0 ? p.pull_off[i] : p.push_off[i];
+    e.kind = 0; e.term = 0.0f;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
+        if (!((AXES >> a) & 1) || c[a] == 0) continue;
         const int t = pos[a] + c[a];
-        if (!((AXES >> a) & 1) || (t >= 0 && t < n[a])) { e.off += (long long)c[a] * stride[a]; continue; }
-        if (p.bc[a] == 3) {          // halo (x slabs): the ghost plane is an ordinary neighbour, filled from / returned to the next slab
-            e.off += (long long)c[a] * stride[a];
-            continue;
-        }
+        if (t >= 0 && t < n[a]) continue;
         if (p.bc[a] == 2) {
             if (e.kind == 0) {       // the wall named first in x, y, z order supplies the velocity
                 const float* u = p.wall_u[a * 2 + (t < 0 ? 0 : 1)];
@@ -81,7 +80,9 @@ __device__ __forceinline__ Edge edge_lookup(const InplaceParams& p, int i, int x
             }
             e.kind = 1;
         } else {
-            e.off += (long long)(c[a] - (t < 0 ? -n[a] : n[a])) * stride[a];     // periodic wrap
+            // periodic wrap / neighbouring slab (x: per slot, the slot being inv(i) for a pull and i for a push)
+            if (a == 0) e.off += p.xshift[t < 0 ? 0 : 1][sign < 0 ? dir_inv(i) : i];
+            else        e.off += p.shift[a][t < 0 ? 0 : 1];
         }
     }
     return e;
@@ -107,6 +108,32 @@ __device__ __forceinline__ void add_source(const InplaceParams& p, float (&f)[Q]
 
 enum : unsigned { AA_ORDINARY = 0, AA_DEAD = 1, AA_SPECIAL = 2 };      // word classes, as in lbm_kernels.cu
 
+// Lattices of more than ~64 GB lose a third of their speed although they move the same bytes per cell (ncu: same DRAM
+// traffic, twice the lg_throttle / long_scoreboard stalls, independent of shape and padding -- profiles/r02_notes.md): the
+// sweep touches every 2 MB page once per step, and past the reach of the last-level TLB every first touch is a page walk
+// that all SMs entering the page wait for together.  One block per plane therefore touches every page of every
+// population `ahead` planes further on (one request per 2 MB), so that the walk overlaps with the work on the planes in
+// between.  mode 1: prefetch.global.L2, mode 2: a load whose value is dropped.
+template <int Q>
+__device__ __forceinline__ void touch_pages_ahead(const InplaceParams& p, int x, unsigned t)
+{
+#if defined(__CUDACC__)
+    const Geom& g = p.g;
+    const int xa = x + p.tlb_ahead;
+    if (t >= (unsigned)Q || xa > g.nx) return;
+    const float* base = p.f + (long long)t * g.np + (long long)(xa + 1) * g.plane;
+    constexpr long long PAGE = (2ll << 20) / (long long)sizeof(float);
+    for (long long off = 0; off < g.plane; off += PAGE) {
+        if (p.tlb_mode == 2) {
+            float v;
+            asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(base + off));
+        } else {
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(base + off));
+        }
+    }
+#endif
+}
+
 // EXTRA: the lattice has a solid mask and / or a source (kept out of the all-fluid instantiation)
 template <int Q, int MOMENT, bool EQ64, bool EXTRA>
 __global__ void __launch_bounds__(256, (Q == 19 && !EQ64) ? 6 : 4) aa_even_kernel(const __grid_constant__ InplaceParams p)
@@ -114,7 +141,8 @@ __global__ void __launch_bounds__(256, (Q == 19 && !EQ64) ? 6 : 4) aa_even_kerne
     const Geom& g = p.g;
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int x = blockIdx.z;
+    const int x = p.x0 + blockIdx.z;                 // the launch covers the planes [x0, x1)
+    if (p.tlb_ahead && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.y == 0) touch_pages_ahead<Q>(p, x, threadIdx.x);
     if (z >= g.nz || y >= g.ny) return;
     if (EXTRA && p.solid) {
         // a warp is 32 consecutive z of one row = one 32-cell word (blockDim.x is a multiple of 32)
@@ -143,12 +171,11 @@ __global__ void __launch_bounds__(256, (Q == 19 && !EQ64) ? 6 : 4) aa_even_kerne
 template <int Q, int MOMENT, bool EQ64, int AXES, bool EXTRA>
 __device__ __forceinline__ void aa_odd_edge_cell(const InplaceParams& p, float* a, int x, int y, int z)
 {
-    const Geom& g = p.g;
     float f[Q];
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
         const Edge e = edge_lookup<Q, AXES>(p, i, x, y, z, -1);
-        f[i] = (e.kind == 0) ? a[(long long)dir_inv(i) * g.np + e.off] : a[(long long)i * g.np] + e.term;
+        f[i] = (e.kind == 0) ? a[e.off] : a[p.pop_off[i]] + e.term;
     }
     if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
     else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
@@ -157,8 +184,8 @@ __device__ __forceinline__ void aa_odd_edge_cell(const InplaceParams& p, float* 
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
         const Edge e = edge_lookup<Q, AXES>(p, i, x, y, z, +1);
-        if (e.kind == 0) a[(long long)i * g.np + e.off] = f[i];
-        else             a[(long long)dir_inv(i) * g.np] = f[i] + e.term;
+        if (e.kind == 0) a[e.off] = f[i];
+        else             a[p.park_off[i]] = f[i] + e.term;
     }
 }
 
@@ -216,46 +243,50 @@ __device__ __forceinline__ void aa_odd_zedge_cell(const InplaceParams& p, float*
     }
 }
 
-// Two launches cover the lattice, each thread touching only its own slots (no ordering between them):
-//   MODE 0  the interior box, rows 1..ny-2 of planes 1..nx-2: a block owns 4 consecutive z-words of a row.  Words
+// Three launches cover the planes [x0, x1) of the lattice, each thread touching only its own slots (no ordering
+// between them):
+//   MODE 0  the interior box, rows 1..ny-2 of the planes 1..nx-2: a block owns 4 consecutive z-words of a row.  Words
 //           away from the z edge run plain offsets (lean code); the first and last word of the row take the z rule
 //           (periodic wrap / wall) for the populations with c_z != 0 of their first / last lane -- in the same
 //           launch, next to the rest of their row, so that the row is still one contiguous run in DRAM;
-//   MODE 2  the x and y faces, with the per-direction rules of all three axes.
-// With geometry (EXTRA and a class array) both launches take the ordinary words only: all-solid words are
+//   MODE 2  the x faces (planes 0 and nx-1, every row), with the per-direction rules of all three axes: on x slabs
+//           these are the cells that pull from and push to the neighbouring slab's memory;
+//   MODE 3  the y faces (rows 0 and ny-1) of the planes 1..nx-2, with the y and z rules.
+// With geometry (EXTRA and a class array) all launches take the ordinary words only: all-solid words are
 // skipped and the special words are left to aa_odd_special_kernel.
 template <int Q, int MOMENT, bool EQ64, int MODE, bool EXTRA>
 __global__ void __launch_bounds__(128, (MODE == 0 && Q == 19 && !EQ64) ? (EXTRA ? LBM_AA_ODD_MINB : 12) : 8) aa_odd_kernel(const __grid_constant__ InplaceParams p)
 {
     const Geom& g = p.g;
     const int wcount = (g.nz + 31) >> 5;
+    // (MODE 0 and 3 are launched with [x0, x1) already clipped to the interior planes 1..nx-2, see launch_t)
     int x, y, w;
     if constexpr (MODE == 0) {
         w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
         if (w >= wcount) return;
         y = 1 + blockIdx.y;
-        x = 1 + blockIdx.z;
+        x = p.x0 + blockIdx.z;
+        if (p.tlb_ahead && blockIdx.x == 0 && blockIdx.y == 0) touch_pages_ahead<Q>(p, x + 1, threadIdx.x);
+    } else if constexpr (MODE == 2) {
+        // face planes of the range: plane 0 if x0 == 0, plane nx-1 if x1 == nx (one plane when nx == 1)
+        const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const long long per = (long long)g.ny * wcount;
+        const bool lo = p.x0 == 0, hi = p.x1 == g.nx && g.nx > 1;
+        if (k >= per * ((lo ? 1 : 0) + (hi ? 1 : 0))) return;
+        const int plane = (int)(k / per);
+        const int rem = (int)(k - (long long)plane * per);
+        x = (plane == 0 && lo) ? 0 : g.nx - 1;
+        y = rem / wcount;
+        w = rem - y * wcount;
     } else {
-        long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        const int x2 = min(g.nx, 2), y2 = min(g.ny, 2);
-        const int xi = g.nx - x2;
-        const long long na = (long long)x2 * g.ny * wcount, nb = (long long)xi * y2 * wcount;
-        if (k < na) {
-            const int plane = (int)(k / ((long long)g.ny * wcount));
-            const int rem = (int)(k - (long long)plane * g.ny * wcount);
-            x = plane == 0 ? 0 : g.nx - 1;
-            y = rem / wcount;
-            w = rem - y * wcount;
-        } else if (k < na + nb) {
-            k -= na;
-            const int xs = (int)(k / (y2 * wcount));
-            const int rem = (int)(k - (long long)xs * (y2 * wcount));
-            x = 1 + xs;
-            y = (rem / wcount) == 0 ? 0 : g.ny - 1;
-            w = rem % wcount;
-        } else {
-            return;
-        }
+        const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const int y2 = min(g.ny, 2);
+        if (k >= (long long)(p.x1 - p.x0) * y2 * wcount) return;
+        const int xs = (int)(k / (y2 * wcount));
+        const int rem = (int)(k - (long long)xs * (y2 * wcount));
+        x = p.x0 + xs;
+        y = (rem / wcount) == 0 ? 0 : g.ny - 1;
+        w = rem % wcount;
     }
     const int z = w * 32 + (int)(threadIdx.x & 31u);
     if (z >= g.nz) return;
@@ -281,8 +312,10 @@ __global__ void __launch_bounds__(128, (MODE == 0 && Q == 19 && !EQ64) ? (EXTRA 
         asm volatile("" : "+l"(a));
 #pragma unroll
         for (int i = 0; i < Q; ++i) a[p.push_off[i]] = f[i];
-    } else {
+    } else if constexpr (MODE == 2) {
         aa_odd_edge_cell<Q, MOMENT, EQ64, 7, EXTRA>(p, a, x, y, z);
+    } else {
+        aa_odd_edge_cell<Q, MOMENT, EQ64, 6, EXTRA>(p, a, x, y, z);
     }
 }
 
@@ -330,7 +363,6 @@ template <int Q, int MOMENT, bool EQ64, int AXES, bool FORCE>
 __device__ __forceinline__ void aa_odd_geo_cell(const InplaceParams& p, float* a, int x, int y, int z, uint32_t nb,
                                                 float& fx, float& fy, float& fz)
 {
-    const Geom& g = p.g;
     float f[Q];
     f[0] = a[p.pop_off[0]];
 #pragma unroll
@@ -341,7 +373,7 @@ __device__ __forceinline__ void aa_odd_geo_cell(const InplaceParams& p, float* a
         } else {
             const Edge e = edge_lookup<Q, AXES>(p, i, x, y, z, -1);
             const bool self = own || e.kind != 0;
-            const float v = a[self ? p.pop_off[i] : (long long)dir_inv(i) * g.np + e.off];
+            const float v = a[self ? p.pop_off[i] : e.off];
             f[i] = (!own && e.kind != 0) ? v + e.term : v;
         }
     }
@@ -359,7 +391,7 @@ __device__ __forceinline__ void aa_odd_geo_cell(const InplaceParams& p, float* a
         } else {
             const Edge e = edge_lookup<Q, AXES>(p, i, x, y, z, +1);
             const bool self = own || e.kind != 0;
-            a[self ? p.pop_off[dir_inv(i)] : (long long)i * g.np + e.off] = (!own && e.kind != 0) ? f[i] + e.term : f[i];
+            a[self ? p.pop_off[dir_inv(i)] : e.off] = (!own && e.kind != 0) ? f[i] + e.term : f[i];
         }
     }
 }
@@ -373,8 +405,9 @@ __global__ void __launch_bounds__(128, Q == 19 ? 8 : 6) aa_odd_special_kernel(co
 {
     const Geom& g = p.g;
     const unsigned lane = threadIdx.x & 31u;
-    const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (k >= p.n_special) return;
+    const long long kl = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (kl >= p.n_special) return;
+    const long long k = p.special_k0 + kl;                    // the launch covers the entries [special_k0, special_k0 + n_special)
     const uint32_t widx = __ldg(p.special_list + k);          // mask-word index = padded cell index / 32
     const uint32_t nb = __ldg(p.cellinfo + k * 32 + lane);
     const int wpad = (int)(widx % (uint32_t)g.wz);
@@ -403,8 +436,9 @@ __global__ void __launch_bounds__(128, 8) aa_even_special_kernel(const __grid_co
 {
     const Geom& g = p.g;
     const unsigned lane = threadIdx.x & 31u;
-    const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (k >= p.n_special) return;
+    const long long kl = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (kl >= p.n_special) return;
+    const long long k = p.special_k0 + kl;
     const uint32_t widx = __ldg(p.special_list + k);
     const uint32_t nb = __ldg(p.cellinfo + k * 32 + lane);
     const int wpad = (int)(widx % (uint32_t)g.wz);
@@ -487,7 +521,7 @@ __device__ __forceinline__ float aa_fetch(const InplaceParams& p, int i, int x, 
     }
     const Edge e = edge_lookup<Q>(p, i, x, y, z, +1);
     // a population that bounced off a wall is parked in the opposite slot with the wall term already added
-    return (e.kind == 0) ? a[(long long)i * g.np + e.off] : a[(long long)dir_inv(i) * g.np] - e.term;
+    return (e.kind == 0) ? a[e.off] : a[(long long)dir_inv(i) * g.np] - e.term;
 }
 
 template <int Q>
@@ -572,25 +606,36 @@ __global__ void __launch_bounds__(256) aa_mass_kernel(const __grid_constant__ In
     }
 }
 
+// one step of the planes [p.x0, p.x1) (and of the special-list entries [p.special_k0, p.special_k0 + p.n_special),
+// which the caller sets to the entries of those planes)
 template <int Q, int MOMENT, bool EQ64, bool EXTRA>
 cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, int* launches)
 {
     const Geom& g = p.g;
     int n = 0;
+    if (p.x1 <= p.x0) return cudaSuccess;
     const unsigned special_blocks = (unsigned)((p.n_special + 3) / 4);
     if (p.parity == 0) {        // parked form -> pull / push
         const int wcount = (g.nz + 31) / 32;
-        if (g.nx > 2 && g.ny > 2) {
-            dim3 grid((wcount + 3) / 4, g.ny - 2, g.nx - 2);
-            aa_odd_kernel<Q, MOMENT, EQ64, 0, EXTRA><<<grid, 128, 0, stream>>>(p);
+        const int xi0 = p.x0 > 1 ? p.x0 : 1, xi1 = p.x1 < g.nx - 1 ? p.x1 : g.nx - 1;
+        if (xi1 > xi0) {
+            InplaceParams pi = p;          // the interior planes of the range
+            pi.x0 = xi0; pi.x1 = xi1;
+            if (g.ny > 2) {
+                dim3 grid((wcount + 3) / 4, g.ny - 2, xi1 - xi0);
+                aa_odd_kernel<Q, MOMENT, EQ64, 0, EXTRA><<<grid, 128, 0, stream>>>(pi);
+                ++n;
+            }
+            const long long warps = (long long)(xi1 - xi0) * (g.ny < 2 ? g.ny : 2) * wcount;
+            aa_odd_kernel<Q, MOMENT, EQ64, 3, EXTRA><<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(pi);
             ++n;
         }
-        const long long x2 = g.nx < 2 ? g.nx : 2, y2 = g.ny < 2 ? g.ny : 2;
-        const long long xi = g.nx - x2;
-        // when there is no interior box (nx or ny <= 2) the faces are the whole lattice
-        const long long warps = x2 * g.ny * wcount + xi * y2 * wcount;
-        aa_odd_kernel<Q, MOMENT, EQ64, 2, EXTRA><<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(p);
-        ++n;
+        const int faces = (p.x0 == 0 ? 1 : 0) + ((p.x1 == g.nx && g.nx > 1) ? 1 : 0);
+        if (faces) {
+            const long long warps = (long long)faces * g.ny * wcount;
+            aa_odd_kernel<Q, MOMENT, EQ64, 2, EXTRA><<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(p);
+            ++n;
+        }
         if (EXTRA && p.cls && p.n_special > 0) {
             if (p.force) aa_odd_special_kernel<Q, MOMENT, EQ64, true><<<special_blocks, 128, 0, stream>>>(p);
             else         aa_odd_special_kernel<Q, MOMENT, EQ64, false><<<special_blocks, 128, 0, stream>>>(p);
@@ -601,7 +646,7 @@ cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, int* launches)
         if (bz > 128) bz = 128;
         int by = 128 / bz;
         if (by > g.ny) by = g.ny;
-        dim3 block(bz, by, 1), grid((g.nz + bz - 1) / bz, (g.ny + by - 1) / by, g.nx);
+        dim3 block(bz, by, 1), grid((g.nz + bz - 1) / bz, (g.ny + by - 1) / by, p.x1 - p.x0);
         aa_even_kernel<Q, MOMENT, EQ64, EXTRA><<<grid, block, 0, stream>>>(p);
         ++n;
         if (EXTRA && p.cls && p.force && p.n_special > 0) {

@@ -6,6 +6,26 @@
 
 #include <vector>
 
+// x slabs with peer-memory halos (lbm_halo_export / lbm_halo_connect, lbm_halo.cu): what a slab knows about its two
+// neighbours.  Side 0 = the slab below (lower x), side 1 = the slab above.
+struct lbm_halo_state {
+    bool connected = false;
+    bool has[2] = {false, false};            // there is a neighbour on that side (a missing one = end of a zero-inflow domain)
+    bool ipc[2] = {false, false};            // its memory was opened through CUDA IPC (another process) and must be closed
+    float* peer_buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [side][buffer]: the neighbour's population buffers
+    unsigned long long* peer_flag[2] = {nullptr, nullptr};   // the word of the NEIGHBOUR's flag block that this slab writes
+    int peer_nx[2] = {0, 0};
+    int peer_cur_xor[2] = {0, 0};            // two-buffer engine: (neighbour's current buffer) ^ (mine), constant in lockstep
+    long long delta_inplace[2] = {0, 0};     // single-buffer engine: element distance ghost plane -> neighbour's edge plane (slot 0)
+    long long np_diff[2] = {0, 0};           // neighbour's population stride - mine (slabs may differ in thickness)
+    // own flag block (device memory, written by the neighbours through peer stores): [0] the low neighbour's epoch,
+    // [1] the high neighbour's epoch, [2] number of handshakes that timed out, [3] spare
+    unsigned long long* flags = nullptr;
+    unsigned long long epoch = 0;            // handshakes issued so far; all slabs of a group step in lockstep
+    cudaStream_t edge = nullptr;             // highest priority: handshake + the edge planes
+    cudaEvent_t ev_pre = nullptr, ev_edge = nullptr;
+};
+
 struct lbm_lattice_s {
     // (all members are plain data; the C ABI functions in lbm_capi.cu own the logic)
     lbm_config cfg;
@@ -36,7 +56,14 @@ struct lbm_lattice_s {
     uint32_t *tmask = nullptr, *tprefix = nullptr, *toff = nullptr, *reflected = nullptr;
     lbm::Link* links = nullptr;
     size_t nlinks = 0;
-    double* force = nullptr;         // 3 doubles
+    // LBM_FORCE_ACCUM_REFERENCE_FP32: rank of every link in the oracle's order, the amounts moved this step, the
+    // direction coefficients of every term, and the float triple itself
+    uint32_t* link_rank = nullptr;
+    float* force_moved = nullptr;
+    float* force_coef = nullptr;
+    float* force32 = nullptr;
+    size_t n_force_terms = 0;
+    double* force = nullptr;         // FORCE_SLOTS x 3 doubles
     bool force_on = false;
     int src_on = 0;
     int src_lo[3] = {0, 0, 0}, src_hi[3] = {0, 0, 0};
@@ -45,6 +72,9 @@ struct lbm_lattice_s {
     unsigned* flag = nullptr;
     void* staging = nullptr;
     long long launches = 0;
+    lbm_halo_state halo;
+    float* moments_scratch = nullptr;   // 4 n floats, lbm_moments
+    int slab_x0 = 0, slab_gx = 0;     // lbm_set_slab_origin: first global plane of this slab and the global x extent (0 = not a slab)
     // host copy of the reflection tables currently set (380-byte records) and their owning cells
     std::vector<unsigned char> host_tables;
     std::vector<int64_t> host_table_cells;
@@ -58,3 +88,12 @@ struct lbm_lattice_s {
 int lbm_internal_fail(int code, const char* msg);
 int lbm_internal_use(lbm_handle h);
 int lbm_internal_rebuild_mask(lbm_handle h, const uint8_t* dev_bytes, int has_x_ghost);
+// one step of a handle in two halves (lbm_capi.cu): a = everything that needs no neighbour (ghost fills, the
+// "my previous step is complete" signal to the neighbouring slabs), b = wait for the neighbours, edge planes,
+// interior planes, join.  lbm_step_phases runs a then b; lbm_group_step runs a on every slab of a group first.
+int lbm_internal_step_a(lbm_handle h, unsigned phases);
+int lbm_internal_step_b(lbm_handle h, unsigned phases);
+// lbm_halo.cu
+int lbm_internal_halo_signal(lbm_handle h);       // epoch + 1 -> the neighbours' flag blocks (edge stream)
+int lbm_internal_halo_wait(lbm_handle h);         // until both neighbours have signalled epoch + 1 (edge stream); epoch += 1
+void lbm_internal_halo_release(lbm_handle h);

@@ -121,9 +121,17 @@ __device__ __forceinline__ bool boundary_path(const StepParams& p, float (&f)[Q]
                                 if (sz < 0) src += g.nz; else if (sz >= g.nz) src -= g.nz;
                             }
                         }
+                        if (p.xdelta_on) {
+                            // the value may sit in the neighbouring slab (source plane below 1 or above nx): read it there
+                            const int sp = (int)(L.src_cell / (uint32_t)g.plane) - (do_stream ? c_dir[L.j][0] : 0);
+                            if (sp < 1) src += p.xdelta[0][L.j]; else if (sp > g.nx) src += p.xdelta[1][L.j];
+                        }
                         const float moved = p.fin[src] * L.w;
                         f[i] += moved;
-                        if (p.force) {
+                        if (p.force_moved) {
+                            const uint32_t r = __ldg(p.link_rank + e);
+                            if (r != 0xffffffffu) p.force_moved[r] = moved;
+                        } else if (p.force) {
                             // SimCalcFuncs.cu:181-183; incoming direction from the slot index (reference) or slot/3
                             const int in_dir = (p.force_mode == 0) ? (int)L.slot : (int)L.j;
                             if (in_dir < 27) {
@@ -234,34 +242,70 @@ __device__ __forceinline__ void st_pop(float* a, float v)
 //   wall       : half-way bounce-back, the lane reads its own cell's opposite population and adds
 //                6 w_i (c_i . u_wall) for a moving wall (rho_wall = 1).
 // edge_word is warp-uniform: only the first and last word of a row take the second branch.
+// XE: the launch covers x edge planes of a slab with peer-memory halos; on_lo / on_hi = this cell's plane is the first /
+// last of the slab, so a pull through that face reads the neighbouring slab's memory (xdelta, 0 without a neighbour).
+// One exception: beyond a y WALL the value would be the wall ghost of the neighbour's plane, which only this slab can
+// produce (it is this very cell's bounced-back population, launch_fill_ghosts / fill_axis_kernel): the lane takes it
+// from its own opposite slot, like a z wall.
 template <int Q>
+__device__ __forceinline__ bool through_face(int i, bool on_lo, bool on_hi)
+{
+    return dir_c(i, 0) != 0 && (dir_c(i, 0) > 0 ? on_lo : on_hi);
+}
+template <int Q>
+__device__ __forceinline__ bool beyond_y_wall(const StepParams& p, int i, int y)
+{
+    return p.bc[1] == 2 && dir_c(i, 1) != 0 && (dir_c(i, 1) > 0 ? y == 0 : y == p.g.ny - 1);
+}
+
+template <int Q, bool XE = false>
 __device__ __forceinline__ void pull_populations(const StepParams& p, const float* __restrict__ fin, int x, int y, int z,
-                                                 bool edge_word, float (&f)[Q])
+                                                 bool edge_word, float (&f)[Q], bool on_lo = false, bool on_hi = false)
 {
     const Geom& g = p.g;
+    uint32_t ywalls = 0;                         // (XE) populations that bounced off a y wall next to a slab face
     if (!edge_word || p.bc[2] == 0) {
 #pragma unroll
-        for (int i = 0; i < Q; ++i)
-            f[i] = ld_pop(fin + p.pull_off[i]);
-        return;
-    }
-    const bool lo = (z == 0), hi = (z == g.nz - 1);
-    const bool wall = p.bc[2] == 2;
-    // all Q loads first, as one batch (only the address differs on the edge lane) ...
-#pragma unroll
-    for (int i = 0; i < Q; ++i) {
-        long long a = p.pull_off[i];
-        if (dir_c(i, 2) != 0) {
-            const bool outside = dir_c(i, 2) > 0 ? lo : hi;          // the cell this population comes from is beyond the z edge
-            if (outside) a = wall ? p.pop_off[dir_inv(i)] : a + (dir_c(i, 2) > 0 ? g.nz : -g.nz);
+        for (int i = 0; i < Q; ++i) {
+            long long a = p.pull_off[i];
+            if (XE && through_face<Q>(i, on_lo, on_hi)) {
+                if (beyond_y_wall<Q>(p, i, y)) { a = p.pop_off[dir_inv(i)]; ywalls |= 1u << i; }
+                else a += p.xdelta[dir_c(i, 0) > 0 ? 0 : 1][i];
+            }
+            f[i] = ld_pop(fin + a);
         }
-        f[i] = ld_pop(fin + a);
+    } else {
+        const bool lo = (z == 0), hi = (z == g.nz - 1);
+        const bool wall = p.bc[2] == 2;
+        // all Q loads first, as one batch (only the address differs on the edge lane) ...
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            long long a = p.pull_off[i];
+            bool own = false;
+            if (dir_c(i, 2) != 0) {
+                const bool outside = dir_c(i, 2) > 0 ? lo : hi;          // the cell this population comes from is beyond the z edge
+                if (outside) {
+                    if (wall) { a = p.pop_off[dir_inv(i)]; own = true; }
+                    else a += (dir_c(i, 2) > 0 ? g.nz : -g.nz);
+                }
+            }
+            if (XE && through_face<Q>(i, on_lo, on_hi)) {
+                if (beyond_y_wall<Q>(p, i, y)) { a = p.pop_off[dir_inv(i)]; ywalls |= 1u << i; }
+                else if (!own) a += p.xdelta[dir_c(i, 0) > 0 ? 0 : 1][i];
+            }
+            f[i] = ld_pop(fin + a);
+        }
+        // ... then the moving-wall terms of the populations that bounced (edge lanes of moving-wall set-ups only)
+        if (wall && p.wall_moving && (lo || hi)) {
+#pragma unroll
+            for (int i = 1; i < Q; ++i)
+                if (dir_c(i, 2) != 0 && (dir_c(i, 2) > 0 ? lo : hi) && !((ywalls >> i) & 1u)) f[i] += moving_wall_term<Q>(p, i, x, y);
+        }
     }
-    // ... then the moving-wall terms of the populations that bounced (edge lanes of moving-wall set-ups only)
-    if (wall && p.wall_moving && (lo || hi)) {
+    if (XE && p.wall_moving && ywalls) {
 #pragma unroll
         for (int i = 1; i < Q; ++i)
-            if (dir_c(i, 2) != 0 && (dir_c(i, 2) > 0 ? lo : hi)) f[i] += moving_wall_term<Q>(p, i, x, y);
+            if ((ywalls >> i) & 1u) f[i] += moving_wall_term<Q>(p, i, x, y);
     }
 }
 
@@ -363,7 +407,11 @@ __global__ void __launch_bounds__(32 * LBM_GEN_WARPS, LBM_GEN_MINB) step_general
         } else {
             const float* __restrict__ fin = p.fin + idx;
             if (do_stream) {
-                pull_populations<Q>(p, fin, x, y, z, wi == 0 || wi == wcount - 1, f);
+                if (SRC) {          // (the variant for the planes that need more: source box, slab faces next to peer memory)
+                    pull_populations<Q, true>(p, fin, x, y, z, wi == 0 || wi == wcount - 1, f, p.xdelta_on && x == 0, p.xdelta_on && x == g.nx - 1);
+                } else {
+                    pull_populations<Q>(p, fin, x, y, z, wi == 0 || wi == wcount - 1, f);
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < Q; ++i) f[i] = fin[p.pop_off[i]];
@@ -375,9 +423,9 @@ __global__ void __launch_bounds__(32 * LBM_GEN_WARPS, LBM_GEN_MINB) step_general
             }
         }
         // ---- additive source on the selected cells (SimCalcFuncs.cu:200-215); bounce-back solids take none
-        // (SRC is set for the launch that covers the planes the source box intersects, see launch_step_general_r)
-        if (SRC && !(dead && p.boundary_mode == 1)) {
-            if (y >= p.src_lo[1] && y <= p.src_hi[1] && z >= p.src_lo[2] && z <= p.src_hi[2]) {
+        // (SRC is set for the launches that cover the planes the source box intersects, see launch_step_general_r)
+        if (SRC && (p.phases & PH_SOURCE) && p.src_on && !(dead && p.boundary_mode == 1)) {
+            if (x >= p.src_lo[0] && x <= p.src_hi[0] && y >= p.src_lo[1] && y <= p.src_hi[1] && z >= p.src_lo[2] && z <= p.src_hi[2]) {
 #pragma unroll
                 for (int i = 0; i < Q; ++i) f[i] += p.src_f[i];
             }
@@ -396,10 +444,10 @@ __global__ void __launch_bounds__(32 * LBM_GEN_WARPS, LBM_GEN_MINB) step_general
 // lanes load nothing at all.  Momentum exchange with obstacle cells is summed into (fx, fy, fz).
 // ZEDGE (warp-uniform) = the word holds a z edge that is periodic or a wall; kept out of the common path so
 // that its Q loads stay one uninterrupted batch.
-template <int Q, bool ZEDGE>
+template <int Q, bool ZEDGE, bool XE>
 __device__ __forceinline__ void pull_bounce_back(const StepParams& p, const float* __restrict__ fin, int x, int y, int z,
                                                  uint32_t nb, bool live, float (&f)[Q],
-                                                 float& fx, float& fy, float& fz, bool& has_force)
+                                                 float& fx, float& fy, float& fz, bool& has_force, bool on_lo, bool on_hi)
 {
     const Geom& g = p.g;
     const bool lo = ZEDGE && (z == 0), hi = ZEDGE && (z == g.nz - 1);
@@ -417,6 +465,11 @@ __device__ __forceinline__ void pull_bounce_back(const StepParams& p, const floa
                 else a += (dir_c(i, 2) > 0 ? g.nz : -g.nz);
             }
         }
+        if (XE && !own && through_face<Q>(i, on_lo, on_hi)) {
+            // through a slab face: the neighbour's memory, or (beyond a y wall) the cell's own bounced population
+            if (beyond_y_wall<Q>(p, i, y)) { own = true; zwalls |= 1u << i; }
+            else a += p.xdelta[dir_c(i, 0) > 0 ? 0 : 1][i];
+        }
         if (own) a = p.pop_off[dir_inv(i)];
         f[i] = live ? ld_pop(fin + a) : 0.0f;
     }
@@ -432,17 +485,18 @@ __device__ __forceinline__ void pull_bounce_back(const StepParams& p, const floa
             }
         }
     }
-    if (ZEDGE && p.wall_moving && live && zwalls) {
+    if ((ZEDGE || XE) && p.wall_moving && live && zwalls) {
 #pragma unroll
         for (int i = 1; i < Q; ++i)
-            if (dir_c(i, 2) != 0 && ((zwalls >> i) & 1u)) f[i] += moving_wall_term<Q>(p, i, x, y);
+            if ((zwalls >> i) & 1u) f[i] += moving_wall_term<Q>(p, i, x, y);
     }
 }
 
 // Special words (touching a solid cell, a wall ghost or a reflection target): one warp per entry of the
 // compact list built with the classification; cellinfo holds one neighbourhood word per cell of each entry,
 // in list order.  Same step as everywhere else plus the boundary treatment.
-template <int Q, int MOMENT, bool EQ64>
+// XE: the launch covers the first and / or last plane of a slab with peer-memory halos (lbm_halo_connect)
+template <int Q, int MOMENT, bool EQ64, bool XE>
 __global__ void __launch_bounds__(128, LBM_SPC_MINB) step_special_kernel(const __grid_constant__ StepParams p)
 {
     const Geom& g = p.g;
@@ -492,6 +546,7 @@ __global__ void __launch_bounds__(128, LBM_SPC_MINB) step_special_kernel(const _
     const bool edge_word = w == PAD_Z / 32 || w == PAD_Z / 32 + ((g.nz + 31) >> 5) - 1;
     const long long idx = (long long)widx * 32 + lane;
     const float* __restrict__ fin = p.fin + idx;
+    const bool on_lo = XE && x == 0, on_hi = XE && x == g.nx - 1;
     float f[Q];
     bool dead, skip_store = false;
     if (p.boundary_mode == 1 && do_stream) {
@@ -499,8 +554,8 @@ __global__ void __launch_bounds__(128, LBM_SPC_MINB) step_special_kernel(const _
         const bool solid_here = (nb >> nb_bit(0, 0, 0)) & 1u;
         float fx = 0.0f, fy = 0.0f, fz = 0.0f;
         bool has_force = false;
-        if (edge_word && p.bc[2] != 0) pull_bounce_back<Q, true>(p, fin, x, y, z, nb, active && !solid_here, f, fx, fy, fz, has_force);
-        else                           pull_bounce_back<Q, false>(p, fin, x, y, z, nb, active && !solid_here, f, fx, fy, fz, has_force);
+        if (edge_word && p.bc[2] != 0) pull_bounce_back<Q, true, XE>(p, fin, x, y, z, nb, active && !solid_here, f, fx, fy, fz, has_force, on_lo, on_hi);
+        else                           pull_bounce_back<Q, false, XE>(p, fin, x, y, z, nb, active && !solid_here, f, fx, fy, fz, has_force, on_lo, on_hi);
         dead = solid_here;
         // both buffers already hold zeros in the solid cells: leave out the 32-byte sectors (8 lanes) that
         // are solid throughout; a sector with a live cell is written whole, a partial one would cost a read
@@ -522,7 +577,7 @@ __global__ void __launch_bounds__(128, LBM_SPC_MINB) step_special_kernel(const _
         }
     } else {
         if (do_stream) {
-            pull_populations<Q>(p, fin, x, y, z, edge_word, f);
+            pull_populations<Q, XE>(p, fin, x, y, z, edge_word, f, on_lo, on_hi);
         } else {
 #pragma unroll
             for (int i = 0; i < Q; ++i) f[i] = fin[p.pop_off[i]];
@@ -593,22 +648,39 @@ cudaError_t launch_step_general_x(const StepParams& p, int xa, int xb, cudaStrea
     return cudaGetLastError();
 }
 
-// The additive source touches the planes src_lo[0]..src_hi[0] only (the reference's plane x == 0 or one cell):
-// those planes get their own launch of the variant that carries the source code, every other plane runs the
-// variant without it.
+// The additive source touches the planes src_lo[0]..src_hi[0] only (the reference's plane x == 0 or one cell), and
+// only the first and last plane of a slab pull from the neighbouring slab's memory: runs of such planes get their own
+// launch of the variant that carries that code, every other plane runs the lean variant.
 template <int Q, int MOMENT, bool EQ64, int ROWS>
 cudaError_t launch_step_general_r(const StepParams& p, cudaStream_t stream, int* launches)
 {
+    const Geom& g = p.g;
     int sa = p.x0, sb = p.x0;      // [sa, sb) = planes of this launch the source box intersects
     if ((p.phases & PH_SOURCE) && p.src_on) {
         sa = p.src_lo[0] > p.x0 ? p.src_lo[0] : p.x0;
         sb = (p.src_hi[0] + 1) < p.x1 ? (p.src_hi[0] + 1) : p.x1;
         if (sb <= sa) sa = sb = p.x0;
     }
-    cudaError_t e = launch_step_general_x<Q, MOMENT, EQ64, ROWS, false>(p, p.x0, sa, stream);
-    if (e == cudaSuccess) e = launch_step_general_x<Q, MOMENT, EQ64, ROWS, true>(p, sa, sb, stream);
-    if (e == cudaSuccess) e = launch_step_general_x<Q, MOMENT, EQ64, ROWS, false>(p, sb, p.x1, stream);
-    if (launches) *launches += (sa > p.x0) + (sb > sa) + (p.x1 > sb);
+    const bool peer = p.xdelta_on && (p.phases & PH_STREAM);
+    auto extra = [&](int x) { return (x >= sa && x < sb) || (peer && (x == 0 || x == g.nx - 1)); };
+    cudaError_t e = cudaSuccess;
+    int x = p.x0;
+    while (x < p.x1 && e == cudaSuccess) {        // maximal runs of planes of one kind (at most five)
+        const bool ex = extra(x);
+        int xe = x + 1;
+        if (!ex) {
+            // the next plane that needs the extra variant: sa, nx - 1, or the end of the range
+            xe = p.x1;
+            if (sb > sa && sa > x && sa < xe) xe = sa;
+            if (peer && g.nx - 1 > x && g.nx - 1 < xe) xe = g.nx - 1;
+        } else {
+            while (xe < p.x1 && extra(xe)) ++xe;
+        }
+        e = ex ? launch_step_general_x<Q, MOMENT, EQ64, ROWS, true>(p, x, xe, stream)
+               : launch_step_general_x<Q, MOMENT, EQ64, ROWS, false>(p, x, xe, stream);
+        if (launches) *launches += 1;
+        x = xe;
+    }
     return e;
 }
 
@@ -622,7 +694,9 @@ cudaError_t launch_step_tasks(const StepParams& p, cudaStream_t stream, cudaStre
     if (p.n_special > 0) {
         const long long blocks = (p.n_special + 4 * LBM_SPC_ENTRIES - 1) / (4 * LBM_SPC_ENTRIES);
         cudaStream_t ss = stream_special ? stream_special : stream;
-        step_special_kernel<Q, MOMENT, EQ64><<<(unsigned)blocks, 128, 0, ss>>>(p);
+        const bool xe = p.xdelta_on && (p.phases & PH_STREAM) && (p.x0 == 0 || p.x1 == p.g.nx);
+        if (xe) step_special_kernel<Q, MOMENT, EQ64, true><<<(unsigned)blocks, 128, 0, ss>>>(p);
+        else    step_special_kernel<Q, MOMENT, EQ64, false><<<(unsigned)blocks, 128, 0, ss>>>(p);
         if (launches) *launches += 1;
     }
     return cudaGetLastError();
@@ -954,6 +1028,30 @@ __global__ void __launch_bounds__(256) mass_momentum_kernel(const float* __restr
 }  // namespace
 
 // ---- launch wrappers ---------------------------------------------------------------------------
+
+namespace {
+// The reference keeps the force in one float triple that every reflected slot adds to with an atomic
+// (SimCalcFuncs.cu:181-183).  This restates that accumulator with the order fixed: one thread, terms in the oracle's order,
+// one fused multiply-add each -- slow by design (a serial chain), it exists for parity (LBM_FORCE_ACCUM_REFERENCE_FP32).
+__global__ void force_sequential_kernel(const float* __restrict__ moved, const float* __restrict__ coef, long long n, float* acc3)
+{
+    float fx = acc3[0], fy = acc3[1], fz = acc3[2];
+    for (long long r = 0; r < n; ++r) {
+        const float m = moved[r];
+        fx = fmaf(m, coef[3 * r + 0], fx);
+        fy = fmaf(m, coef[3 * r + 1], fy);
+        fz = fmaf(m, coef[3 * r + 2], fz);
+    }
+    acc3[0] = fx; acc3[1] = fy; acc3[2] = fz;
+}
+}  // namespace
+
+cudaError_t launch_force_sequential(const float* moved, const float* coef, long long n, float* acc3, cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    force_sequential_kernel<<<1, 1, 0, stream>>>(moved, coef, n, acc3);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_step(const LaunchCfg& cfg, const StepParams& p, cudaStream_t stream, cudaStream_t stream_special, int* launches)
 {

@@ -3,6 +3,9 @@
 // Host code only: every line of device work sits behind the C ABI.
 #include "lbm_reference_api.hpp"
 
+#include <mutex>
+#include <unordered_map>
+
 #include "../../include/lbm_b200.h"
 
 #include <cstdio>
@@ -102,6 +105,25 @@ Point_3 Model::reflectionVector(Point_3 point_1, Point_3 point_2)
 
 // ---- Lattice -------------------------------------------------------------------------------------------------
 
+// RunCudaFunctions::* receive a LatticeData by value (the handle travels in its pointer field), not the Lattice that
+// owns it: phases that Lattice queued for fusion must run before a direct kernel-wrapper call, so every Lattice is
+// findable from its handle.
+namespace {
+std::mutex& owners_mutex() { static std::mutex m; return m; }
+std::unordered_map<lbm_lattice_s*, Lattice*>& owners() { static std::unordered_map<lbm_lattice_s*, Lattice*> m; return m; }
+}  // namespace
+
+void Lattice::flush_owner_of(lbm_lattice_s* h)
+{
+    Lattice* owner = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(owners_mutex());
+        auto it = owners().find(h);
+        if (it != owners().end()) owner = it->second;
+    }
+    if (owner) owner->flush();
+}
+
 bool Lattice::check(int rc, const char* what)
 {
     if (rc == LBM_OK) return true;
@@ -121,10 +143,18 @@ Lattice::Lattice(int x, int y, int z, dim3 blocks, dim3 threads, FluidData fluid
     cfg.nx = x; cfg.ny = y; cfg.nz = z;
     cfg.tau = fluid.m_characteristicTimescale;
     check(lbm_create(&cfg, &handle_), "Lattice");
+    if (handle_) {
+        std::lock_guard<std::mutex> lock(owners_mutex());
+        owners()[handle_] = this;
+    }
 }
 
 Lattice::~Lattice()
 {
+    if (handle_) {
+        std::lock_guard<std::mutex> lock(owners_mutex());
+        owners().erase(handle_);
+    }
     lbm_destroy(handle_);
     delete model_;
 }
@@ -317,18 +347,34 @@ namespace RunCudaFunctions
         if (rc != LBM_OK) printf("RunCudaFunctions::%s failed: %s\n", what, lbm_last_error());
     }
 
-    void run_calculate_streaming(dim3, dim3, LatticeData lattice, LatticeData) { report(lbm_stream(of(lattice)), "run_calculate_streaming"); }
-
-    void run_calculate_collision(dim3, dim3, LatticeData lattice, float) { report(lbm_collide(of(lattice)), "run_calculate_collision"); }
-
-    void run_calculate_reflections(dim3, dim3, LatticeData lattice, LatticeData) { report(lbm_reflect(of(lattice)), "run_calculate_reflections"); }
-
-    void run_calculate_reflections_data(dim3, dim3, LatticeData lattice, LatticeData, ReflectionData*)
+    // The reference's wrappers take a second lattice (the copy the host made before the launch, Lattice.cpp:115-210):
+    // this library keeps both buffers inside the handle, so `templattice` carries nothing and is not looked at.
+    // Phases the owning Lattice has queued for fusion run first, so that calls cannot overtake each other.
+    static lbm_handle ready(const LatticeData& d)
     {
-        report(lbm_reflect(of(lattice)), "run_calculate_reflections_data");
+        lbm_handle h = of(d);
+        Lattice::flush_owner_of(h);
+        return h;
     }
 
-    void run_prime_points(dim3, dim3, LatticeData lattice) { report(lbm_prime_points(of(lattice)), "run_prime_points"); }
+    void run_calculate_streaming(dim3, dim3, LatticeData lattice, LatticeData) { report(lbm_stream(ready(lattice)), "run_calculate_streaming"); }
 
-    void run_generate_flow(dim3, dim3, LatticeData lattice, FlowData*) { report(lbm_source(of(lattice)), "run_generate_flow"); }
+    // the timescale of THIS call (the reference kernel divides by its argument, SimCalcFuncs.cu:98-156), not the FluidData's
+    void run_calculate_collision(dim3, dim3, LatticeData lattice, float timescale)
+    {
+        report(lbm_collide_tau(ready(lattice), timescale), "run_calculate_collision");
+    }
+
+    void run_calculate_reflections(dim3, dim3, LatticeData lattice, LatticeData) { report(lbm_reflect(ready(lattice)), "run_calculate_reflections"); }
+
+    // the force of this call is added to the caller's ReflectionData (device memory in the reference, Lattice.cpp:190-193;
+    // host memory works too), whether or not Lattice::setReflectionData was called
+    void run_calculate_reflections_data(dim3, dim3, LatticeData lattice, LatticeData, ReflectionData* reflectionData)
+    {
+        report(lbm_reflect_accumulate(ready(lattice), reflectionData ? &reflectionData->x : nullptr), "run_calculate_reflections_data");
+    }
+
+    void run_prime_points(dim3, dim3, LatticeData lattice) { report(lbm_prime_points(ready(lattice)), "run_prime_points"); }
+
+    void run_generate_flow(dim3, dim3, LatticeData lattice, FlowData*) { report(lbm_source(ready(lattice)), "run_generate_flow"); }
 }

@@ -182,6 +182,7 @@ public:
     void simulateSteps(int n);                       // n fused steps: stream, reflect, collide, source
     void synchronize();
     lbm_lattice_s* handle() { flush(); return handle_; }
+    static void flush_owner_of(lbm_lattice_s* h);   // runs the phases the Lattice that owns `h` has queued (RunCudaFunctions)
     const std::string& lastError() const { return last_error_; }
 
 private:

@@ -60,7 +60,7 @@ class Lattice:
     def __init__(self, x, y, z, blocks=None, threads=None, fluid=None, spacing=1.0, *, q=27,
                  bc=(capi.BC_ZERO_INFLOW,) * 3, moment_mode=capi.MOMENT_REFERENCE, eq_precision=capi.EQ_FP64,
                  boundary_mode=capi.BOUNDARY_REFLECT, force_mode=capi.FORCE_REFERENCE_SLOT_INDEX,
-                 wall_u=None, device=-1, engine=capi.ENGINE_AUTO):
+                 wall_u=None, device=-1, engine=capi.ENGINE_AUTO, force_accum=capi.FORCE_ACCUM_F64_PARTIALS):
         self._lib = capi.load()
         self._h = C.c_void_p()
         fluid = fluid or FluidData()
@@ -72,6 +72,7 @@ class Lattice:
         cfg.moment_mode, cfg.eq_precision = int(moment_mode), int(eq_precision)
         cfg.boundary_mode, cfg.force_mode = int(boundary_mode), int(force_mode)
         cfg.device, cfg.engine = int(device), int(engine)
+        cfg.force_accum = int(force_accum)
         if wall_u is not None:
             wu = np.asarray(wall_u, np.float32).reshape(6, 3)
             for i in range(6):
@@ -141,10 +142,24 @@ class Lattice:
             raise ValueError("expected shape %r" % (shape,))
         capi.check(self._lib.lbm_upload_f_soa(self._h, capi.ptr(a)))
 
+    @staticmethod
+    def _check_out(a, count, what):
+        """a caller-supplied output buffer goes to C as a bare pointer: it must be float32, contiguous and large enough"""
+        if isinstance(a, np.ndarray):
+            ok = a.dtype == np.float32 and a.flags.c_contiguous and a.flags.writeable and a.size >= count
+        elif hasattr(a, "data_ptr"):
+            ok = str(a.dtype) == "torch.float32" and a.is_contiguous() and a.numel() >= count
+        else:
+            ok = False
+        if not ok:
+            raise ValueError("%s: expected a writable contiguous float32 buffer (numpy array or torch tensor) of at least %d elements" % (what, count))
+
     def retrieve_populations(self, out=None):
         if out is None:
             out = np.empty((self.q, self.nx, self.ny, self.nz), np.float32)
-        capi.check(self._lib.lbm_download_f_soa(self._h, capi.ptr(out)))
+        else:
+            self._check_out(out, self.q * self.n_cells, "retrieve_populations(out=)")
+        capi.check(self._lib.lbm_download_f_soa(self._h, capi.ptr(out.data_ptr() if hasattr(out, "data_ptr") else out)))
         return out
 
     # -- geometry side inputs ----------------------------------------------------------------
@@ -215,11 +230,18 @@ class Lattice:
         f = np.ascontiguousarray(flowData.inducedFlow, np.float32)
         capi.check(self._lib.lbm_set_source(self._h, capi.SOURCE_BOX, capi.ptr(lo), capi.ptr(hi), capi.ptr(f)))
 
-    def setReflectionData(self, reflection):
-        """Lattice.cpp:61-71"""
+    def setReflectionData(self, reflection, exact=None):
+        """Lattice.cpp:61-71.  `exact`: three doubles to start the accumulator from instead of the float members of
+        `reflection` (checkpoint restore: the kernels keep the sum in double)"""
         self.m_reflectionData = reflection
         if reflection is None:
             capi.check(self._lib.lbm_set_force_accumulator(self._h, 0, None))
+            return
+        if exact is not None:
+            init64 = np.ascontiguousarray(exact, np.float64)
+            if init64.shape != (3,):
+                raise ValueError("exact: three doubles")
+            capi.check(self._lib.lbm_set_force_accumulator_f64(self._h, 1, capi.ptr(init64)))
             return
         init = np.array([reflection.x, reflection.y, reflection.z], np.float32)
         capi.check(self._lib.lbm_set_force_accumulator(self._h, 1, capi.ptr(init)))
@@ -232,6 +254,12 @@ class Lattice:
             self.m_reflectionData.x, self.m_reflectionData.y, self.m_reflectionData.z = map(float, out)
             return self.m_reflectionData
         return ReflectionData(*out)
+
+    def force_f64(self):
+        """the accumulated force before it is narrowed to the reference's float triple"""
+        out = np.zeros(3, np.float64)
+        capi.check(self._lib.lbm_get_force_f64(self._h, capi.ptr(out)))
+        return out
 
     # -- the per-timestep path (Lattice.cpp:115-226) ------------------------------------------
     def prime_points(self):
@@ -273,7 +301,12 @@ class Lattice:
         arrays or torch tensors, host or CUDA) to fill instead of allocating host arrays"""
         n = self.n_cells
         if out is not None:
-            ptrs = [capi.ptr(o.data_ptr() if hasattr(o, "data_ptr") else o) for o in out]
+            if len(out) != 4:
+                raise ValueError("moments(out=): four buffers (rho, ux, uy, uz)")
+            for o in out:
+                if o is not None:
+                    self._check_out(o, n, "moments(out=)")
+            ptrs = [None if o is None else capi.ptr(o.data_ptr() if hasattr(o, "data_ptr") else o) for o in out]
             capi.check(self._lib.lbm_moments(self._h, *ptrs))
             return out
         rho, ux, uy, uz = (np.empty(n, np.float32) for _ in range(4))

@@ -101,10 +101,14 @@ class SlabLattice:
     """one x-slab of a gx x gy x gz lattice, driven like a `Lattice`"""
 
     def __init__(self, gx, gy, gz, fluid, rank, world, device, bc_x=capi.BC_PERIODIC, bc_yz=(capi.BC_PERIODIC,) * 2,
-                 overlap=True, **kw):
+                 overlap=True, transport="nccl", **kw):
+        """transport: "nccl" = this module posts the edge planes with torch.distributed P2P every step (any backend, also
+        gloo); "peer" = the library's own peer-memory halos (lbm_halo_connect: the edge cells address the neighbouring
+        slab's memory over NVLink, nothing is copied and nothing runs between the steps; CUDA only, one box)."""
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
+        self.transport = transport
         if bc_x not in (capi.BC_PERIODIC, capi.BC_ZERO_INFLOW):
             raise ValueError("the global x edge must be periodic or zero-inflow in slab mode")
         self.rank, self.world = rank, world
@@ -128,6 +132,22 @@ class SlabLattice:
         self.stream = torch.cuda.Stream(device=device)
         capi.check(self._lib.lbm_set_stream(self.lattice.handle, C.c_void_p(self.stream.cuda_stream)))
         self._ghosts_current = False
+        if transport == "peer":
+            self._connect_peers()
+        elif transport != "nccl":
+            raise ValueError("transport must be 'nccl' or 'peer'")
+
+    def _connect_peers(self):
+        """every rank exports its slab (CUDA IPC handles), the blobs travel once through the process group, and each rank
+        connects to the slab below and above; from then on lbm_step does the whole step"""
+        blob = (C.c_ubyte * capi.HALO_BLOB_BYTES)()
+        capi.check(self._lib.lbm_halo_export(self.lattice.handle, blob, capi.HALO_BLOB_BYTES))
+        blobs = [None] * self.world
+        self.dist.all_gather_object(blobs, bytes(blob))
+        lo = None if self.halo.left is None else (C.c_ubyte * capi.HALO_BLOB_BYTES).from_buffer_copy(blobs[self.halo.left])
+        hi = None if self.halo.right is None else (C.c_ubyte * capi.HALO_BLOB_BYTES).from_buffer_copy(blobs[self.halo.right])
+        capi.check(self._lib.lbm_halo_connect(self.lattice.handle, lo, hi))
+        self.dist.barrier()              # nobody steps before everybody is connected
 
     # ---- plane views ----------------------------------------------------------------------------
     def _plane(self, q, xp, nxt):
@@ -207,6 +227,9 @@ class SlabLattice:
 
     def step(self, n=1, phases=capi.PHASE_ALL):
         lib, h = self._lib, self.lattice.handle
+        if self.transport == "peer":
+            capi.check(lib.lbm_step_phases(h, int(n), int(phases)))      # handshake, edge planes and interior: all below the C ABI
+            return
         if self.inplace:
             return self._step_inplace(n, phases)
         if not self._ghosts_current:
@@ -231,7 +254,7 @@ class SlabLattice:
         torch = self.torch
         st0 = self.lattice.stats()["kernel_launches"]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if not self._ghosts_current and not self.inplace:
+        if not self._ghosts_current and not self.inplace and self.transport != "peer":
             self.prime()
         self.stream.synchronize()
         e0.record(self.stream)
@@ -239,6 +262,13 @@ class SlabLattice:
         e1.record(self.stream)
         e1.synchronize()
         return e0.elapsed_time(e1), self.lattice.stats()["kernel_launches"] - st0
+
+    def sync(self):
+        """this slab's streams have drained and (peer transport) so have the neighbours': part of an edge cell's state may
+        sit in a neighbouring slab's memory, so nothing is read back before every rank is here"""
+        self.lattice.sync()
+        if self.transport == "peer":
+            self.dist.barrier()
 
     # ---- inputs in global coordinates ---------------------------------------------------------------
     def load_populations(self, f_local):
@@ -264,15 +294,14 @@ class SlabLattice:
         """{"mass": sum rho, "momentum": sum rho u [3], "force": obstacle force [3]} of the global lattice: every
         rank reduces its own slab on the device (lbm_mass / lbm_momentum / lbm_get_force), then one fp64
         all-reduce of 7 numbers"""
-        self.stream.synchronize()
+        self.sync()
         lat = self.lattice
         loc = np.zeros(7, np.float64)
         loc[0] = lat.mass()
         loc[1:4] = lat.momentum()
         if lat.m_reflectionData is not None:
-            r = lat.retrieve_reflection_data()
-            loc[4:7] = (r.x, r.y, r.z)
-        tot = allreduce_sum(loc, self.dist, self._dev())
+            loc[4:7] = lat.force_f64()
+        tot = allreduce_sum(loc, self.dist, self._dev() if self.dist.get_backend() == "nccl" else None)
         return {"mass": float(tot[0]), "momentum": tot[1:4].copy(), "force": tot[4:7].copy()}
 
     def mass(self):
@@ -280,3 +309,90 @@ class SlabLattice:
 
     def momentum(self):
         return self.diagnostics()["momentum"]
+
+
+class SlabGroup:
+    """All x slabs of a gx x gy x gz lattice in ONE process, one per device in `devices` (repeating a device is fine:
+    the slabs then share it) -- what a single-process caller such as the C++ `Lattice` drop-in does.  The slabs are
+    connected through lbm_halo_connect and stepped in lockstep by lbm_group_step; inputs and outputs are global arrays."""
+
+    def __init__(self, gx, gy, gz, fluid, devices, bc_x=capi.BC_PERIODIC, bc_yz=(capi.BC_PERIODIC,) * 2, **kw):
+        if bc_x not in (capi.BC_PERIODIC, capi.BC_ZERO_INFLOW):
+            raise ValueError("the global x edge must be periodic or zero-inflow in slab mode")
+        self.gx, self.gy, self.gz = gx, gy, gz
+        self.world = len(devices)
+        self.periodic = bc_x == capi.BC_PERIODIC
+        self.ranges = [slab_range(gx, r, self.world) for r in range(self.world)]
+        self._lib = capi.load()
+        self.slabs = [Lattice(x1 - x0, gy, gz, None, None, fluid, 1.0, bc=(capi.BC_HALO, bc_yz[0], bc_yz[1]), device=dev, **kw)
+                      for (x0, x1), dev in zip(self.ranges, devices)]
+        self.q = self.slabs[0].q
+        blobs = []
+        for s in self.slabs:
+            b = (C.c_ubyte * capi.HALO_BLOB_BYTES)()
+            capi.check(self._lib.lbm_halo_export(s.handle, b, capi.HALO_BLOB_BYTES))
+            blobs.append(b)
+        for r, s in enumerate(self.slabs):
+            lo = blobs[(r - 1) % self.world] if (self.periodic or r > 0) else None
+            hi = blobs[(r + 1) % self.world] if (self.periodic or r + 1 < self.world) else None
+            capi.check(self._lib.lbm_halo_connect(s.handle, lo, hi))
+        self._handles = (C.c_void_p * self.world)(*[s.handle for s in self.slabs])
+
+    def close(self):
+        for s in self.slabs:
+            capi.check(self._lib.lbm_halo_disconnect(s.handle))
+        for s in self.slabs:
+            s.close()
+
+    def step(self, n=1, phases=capi.PHASE_ALL):
+        capi.check(self._lib.lbm_group_step(self._handles, self.world, int(n), int(phases)))
+
+    def sync(self):
+        for s in self.slabs:
+            s.sync()
+
+    def load_populations(self, f):
+        f = np.ascontiguousarray(f, np.float32)
+        for (x0, x1), s in zip(self.ranges, self.slabs):
+            s.load_populations(np.ascontiguousarray(f[:, x0:x1]))
+
+    def retrieve_populations(self):
+        self.sync()
+        return np.concatenate([s.retrieve_populations() for s in self.slabs], axis=1)
+
+    def set_solid_mask(self, solid):
+        """global uint8 [gx, gy, gz]: every slab gets its planes plus its neighbours' edge planes (periodic images at the
+        ends of a periodic axis, fluid beyond a zero-inflow end)"""
+        solid = np.ascontiguousarray(solid, np.uint8).reshape(self.gx, self.gy, self.gz)
+        for (x0, x1), s in zip(self.ranges, self.slabs):
+            lo = solid[(x0 - 1) % self.gx] if (self.periodic or x0 > 0) else np.zeros_like(solid[0])
+            hi = solid[x1 % self.gx] if (self.periodic or x1 < self.gx) else np.zeros_like(solid[0])
+            s.set_solid_mask(np.concatenate([lo[None], solid[x0:x1], hi[None]], axis=0), x_ghost_planes=True)
+
+    def set_source_global(self, lo, hi, flow):
+        gl = 0 if lo[0] is None else lo[0]
+        gh = self.gx - 1 if hi[0] is None else hi[0]
+        for (x0, x1), s in zip(self.ranges, self.slabs):
+            a, b = max(gl, x0) - x0, min(gh, x1 - 1) - x0
+            s.setFlowData(None if a > b else FlowData(((a, lo[1], lo[2]), (b, hi[1], hi[2])), flow))
+
+    def enable_force(self):
+        from .lattice import ReflectionData
+        for s in self.slabs:
+            s.setReflectionData(ReflectionData())
+
+    def force(self):
+        self.sync()
+        tot = np.zeros(3, np.float64)
+        for s in self.slabs:
+            tot += s.force_f64()
+        return tot
+
+    def mass(self):
+        self.sync()
+        return float(sum(s.mass() for s in self.slabs))
+
+    def moments(self):
+        self.sync()
+        parts = [s.moments() for s in self.slabs]
+        return tuple(np.concatenate([p[k] for p in parts], axis=0) for k in range(4))

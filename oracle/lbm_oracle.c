@@ -31,6 +31,11 @@ const float LBO_SPLIT[27] = {0.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0,
                              0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5,
                              1.0/3.0, 1.0/3.0, 1.0/3.0, 1.0/3.0, 1.0/3.0, 1.0/3.0, 1.0/3.0, 1.0/3.0};
 
+void lbo_set_num_threads(int n)
+{
+    omp_set_num_threads(n > 0 ? n : 1);
+}
+
 int lbo_num_threads(void)
 {
 #ifdef _OPENMP

@@ -114,6 +114,7 @@ int  lbo_get_reflection_direction(const lbo_reflection_values *t, int slot);
 unsigned lbo_compress_ints(const int *array, int num, int bit_length);
 
 int lbo_num_threads(void);
+void lbo_set_num_threads(int n);
 
 /* ---- geometry side input (geom_oracle.c) ---------------------------------------- */
 

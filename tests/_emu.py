@@ -124,7 +124,7 @@ def full_library():
     SIMT executor of tests/emu/: returns the path of tests/emu/_build/liblbm_b200_emu.so"""
     os.makedirs(BUILD, exist_ok=True)
     so = os.path.join(BUILD, "liblbm_b200_emu.so")
-    units = ["lbm_kernels.cu", "lbm_capi.cu", "lbm_geometry.cu", "lbm_inplace.cu"]
+    units = ["lbm_kernels.cu", "lbm_capi.cu", "lbm_geometry.cu", "lbm_inplace.cu", "lbm_halo.cu"]
     import fcntl
     with open(os.path.join(BUILD, ".lock"), "w") as lock:          # spawned test workers may all arrive here at once
         fcntl.flock(lock, fcntl.LOCK_EX)

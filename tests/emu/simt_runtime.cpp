@@ -270,6 +270,13 @@ cudaError_t cudaMalloc3D(struct cudaPitchedPtr* out, struct cudaExtent e)
     return rc;
 }
 cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+// slabs in one process share the host's address space; nothing here ever crosses a process
+cudaError_t cudaPointerGetAttributes(struct cudaPointerAttributes* a, const void*) { std::memset(a, 0, sizeof *a); a->type = cudaMemoryTypeDevice; return cudaSuccess; }
+cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return cudaSuccess; }
+cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void*) { std::memset(h, 0, sizeof *h); return cudaSuccess; }
+cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 // (the reference fetches a device function pointer through the address of a __device__ variable; on this executor
 // that variable is an ordinary global, initialised with the function's address)
 cudaError_t cudaMemcpyFromSymbol(void* dst, const void* symbol, size_t count, size_t offset, enum cudaMemcpyKind)

@@ -25,7 +25,7 @@ SELECTION = [
     (TP, "test_collision_known_answer", 1), (TP, "test_full_known_answer", 1), (TP, "test_reflections_known_answer", 1),
     (TP, "test_flow_generation_known_answer", 1), (TP, "test_plane_flow_generation_known_answer", 1),
     (TP, "test_stream_bit_exact", 1), (TP, "test_collide_parity", 1), (TP, "test_reflect_parity_16", 1),
-    (TP, "test_cli_steps_parity_with_geometry", 2), (TP, "test_unfused_phases_equal_fused_step", 1),
+    (TP, "test_cli_steps_parity_with_geometry", 2), (TP, "test_force_accumulator_in_the_reference_arithmetic", 1), (TP, "test_unfused_phases_equal_fused_step", 1),
     (TP, "test_soa_engine_parity", 1), (TP, "test_bounce_back_obstacle_parity", 1), (TP, "test_lid_driven_cavity_parity", 1),
     (TP, "test_bad_arguments_are_reported", 1), (TP, "test_inplace_engine_equals_two_buffer_engine", 9),
     (TP, "test_inplace_engine_with_obstacles", 5), (TP, "test_inplace_engine_refuses_what_it_cannot_do", 1),

@@ -111,25 +111,44 @@ def test_mask_and_tables_bit_exact(shape, name):
     assert np.array_equal(out["is_reflected"], cells["is_reflected"])
 
 
+_CONFIG1 = {}
+
+
+def _config1_oracle(n, tau, steps):
+    """the oracle's run of BASELINE.json configs[0], computed once per session (about a minute of CPU time)"""
+    key = (n, tau, steps)
+    if key not in _CONFIG1:
+        spacing = np.float32(1.0 / n)
+        flow = np.full(27, 0.001, np.float32); flow[6] = 0.002
+        cells = O.new_cells(n, n, n)
+        cells["f"] = flow[None, :]
+        mesh = O.Mesh(obj("cube_angled.obj"))
+        assert mesh.insert(cells, n, n, n, spacing) == 1
+        tables, tindex = mesh.preprocess(cells, n, n, n, spacing)
+        force = np.zeros(3, np.float32)
+        want = O.step_cli(cells, n, n, n, tau, tables, tindex, force, O.SRC_PLANE_X0, flow, steps=steps)
+        _CONFIG1[key] = (want, force, flow, spacing)
+    return _CONFIG1[key]
+
+
+CONFIG1_STEPS = int(os.environ.get("LBM_CONFIG1_STEPS", "1000"))
+
+
 @pytest.mark.parametrize("eq", [lb.EQ_FP64, lb.EQ_FP32])
 def test_config1_reference_geometry_64_cubed(eq):
     """BASELINE.json configs[0]: the reference test geometry on a 64^3 grid driven exactly like the CLI
-    (LatticeBoltzmannCuda.cpp:29-93): all f = 0.001, f[6] = 0.002, plane source at x == 0, force accumulator,
-    stream/reflect/collide/source.  Everything on our side comes from the drop-in interface; the oracle runs its
-    own voxeliser, table builder and four phases.  The open (zero-inflow) box drains towards rho -> 0 where
-    u = m / rho amplifies any rounding difference, so the comparison stops at 150 steps (rel 1e-5)."""
-    n, tau, steps = 64, 1.0, 150
-    spacing = np.float32(1.0 / n)
-    flow = np.full(27, 0.001, np.float32); flow[6] = 0.002
-    cells = O.new_cells(n, n, n)
-    cells["f"] = flow[None, :]
-    mesh = O.Mesh(obj("cube_angled.obj"))
-    assert mesh.insert(cells, n, n, n, spacing) == 1
-    tables, tindex = mesh.preprocess(cells, n, n, n, spacing)
-    force = np.zeros(3, np.float32)
-    want = O.step_cli(cells, n, n, n, tau, tables, tindex, force, O.SRC_PLANE_X0, flow, steps=steps)
+    (LatticeBoltzmannCuda.cpp:29-93) for the full 1000 steps: all f = 0.001, f[6] = 0.002, plane source at x == 0, force
+    accumulator, stream/reflect/collide/source.  Everything on our side comes from the drop-in interface; the oracle runs
+    its own voxeliser, table builder and four phases.  Measured on B200 (profiles/r02a_config1_curve_1000_steps.jsonl):
+    the distributions stay within 4e-7 (fp64 equilibrium; bit-identical to the reference's own kernels at every one of
+    the 20 checkpoints) and 1.2e-6 (fp32) of the oracle over all 1000 steps although the open box drains to rho ~ 2e-7."""
+    n, tau, steps = 64, 1.0, CONFIG1_STEPS
+    want, force, flow, spacing = _config1_oracle(n, tau, steps)
 
-    lat = make(n, n, n, float(spacing), tau=tau, eq_precision=eq)
+    # fp64 equilibrium: with the reference's own accumulator (one float triple, the oracle's order); fp32: the default
+    ref_accum = eq == lb.EQ_FP64
+    lat = make(n, n, n, float(spacing), tau=tau, eq_precision=eq,
+               force_accum=lb.FORCE_ACCUM_REFERENCE_FP32 if ref_accum else lb.FORCE_ACCUM_F64_PARTIALS)
     start = O.new_cells(n, n, n)
     start["f"] = flow[None, :]
     lat.load_data(start)
@@ -143,12 +162,16 @@ def test_config1_reference_geometry_64_cubed(eq):
     got = lat.retrieve_data()
     scale = float(np.abs(want["f"]).max())
     assert float(np.abs(got["f"].astype(np.float64) - want["f"]).max()) / scale <= 1e-5
-    # The reference keeps the force in three fp32 atomics that are never reset: once the sum is ~1e3 an increment
-    # below half an ulp (3e-5) is absorbed, and the small contributions of the weakly loaded faces are lost one by
-    # one.  The oracle restates that; the kernel sums per-warp partials in double.  The two agree to 2e-4 while
-    # the accumulator is small (tests/test_gpu_parity.py, 40 steps at 16^3) and drift apart by a few 1e-3 here.
     r = lat.retrieve_reflection_data()
-    assert np.allclose([r.x, r.y, r.z], force, rtol=1e-2, atol=1e-6)
+    if ref_accum:
+        # 1e-5 on the force, in the reference's own accumulator arithmetic
+        assert np.allclose([r.x, r.y, r.z], force, rtol=1e-5, atol=0), ([r.x, r.y, r.z], force)
+    else:
+        # The reference keeps the force in three fp32 atomics that are never reset: once the sum is ~1e4 an increment
+        # below half an ulp (5e-4) is absorbed, and the small contributions of the weakly loaded faces are lost one by
+        # one.  The oracle restates that; the default accumulator sums per-warp partials in double, i.e. exactly, and the
+        # two drift apart by the lost increments: 3 % after 1000 steps (the curve in profiles/r02a_*).
+        assert np.allclose([r.x, r.y, r.z], force, rtol=5e-2, atol=1e-6)
     assert np.array_equal(got["is_internal"], want["is_internal"])
     # the fused path gives the same state as the four separate phases
     lat2 = make(n, n, n, float(spacing), tau=tau, eq_precision=eq)

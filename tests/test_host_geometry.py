@@ -86,3 +86,20 @@ def test_host_helpers_bit_equal_to_oracle():
         for _ in range(200):
             a, b = rng.uniform(lo - 0.5, hi + 0.5, 3).astype(np.float32), rng.uniform(lo, hi, 3).astype(np.float32)
             assert np.array_equal(m.reflectionVector(a, b), mo.reflection_vector(a, b))
+
+
+def test_obj_with_out_of_range_face_indices_is_an_invalid_mesh(tmp_path):
+    """`f 0 ...`, an index past the vertex list or a too-negative relative index must give an invalid (empty) model, as a
+    reader that rejects the file would, not an out-of-range read in the mesh queries"""
+    verts = "v 0 0 0\nv 1 0 0\nv 0 1 0\nv 0 0 1\n"
+    good = "f 1 2 3\nf 1 2 4\nf 2 3 4\nf 1 3 4\n"
+    for bad in ("f 0 1 2\n", "f 1 2 9\n", "f -7 1 2\n"):
+        p = tmp_path / "bad.obj"
+        p.write_text(verts + good + bad)
+        m = lb.Model(str(p))
+        assert m.checkError() and not m.isModelClosed()
+        assert not m.isPointInsideModel((0.1, 0.1, 0.1))
+        assert tuple(m.reflectionVector((0.1, 0.1, -1.0), (0.1, 0.1, 1.0))) == (0.0, 0.0, 0.0)
+    p = tmp_path / "good.obj"
+    p.write_text(verts + good)
+    assert lb.Model(str(p)).isPointInsideModel((0.1, 0.1, 0.1))

@@ -107,14 +107,14 @@ def test_sparse_obstacle_all_word_classes(q, bc):
                            steps=1, force=force)
         assert rel_err(lat.retrieve(), state) <= REL, "step %d" % step
         assert np.allclose(lat.total_force(), force, rtol=1e-4, atol=1e-4)
-    assert lat.launches.value == 3 * 3 + 2 * 2      # odd: interior, faces, special words; even: ordinary words, special words
+    assert lat.launches.value == 3 * 4 + 2 * 2      # odd: interior, y faces, x faces, special words; even: ordinary words, special words
     # without the force sum the even step is one launch and the solid lanes of the special kernel leave at once: same state
     quiet = _emu.Lattice(X, Y, Z, q, 0.7, bc, WALL_U)
     quiet.set_solid_mask(solid)
     quiet.load(f)
     quiet.step(5)
     assert np.array_equal(quiet.retrieve(), lat.retrieve())
-    assert quiet.launches.value == 3 * 3 + 2 * 1
+    assert quiet.launches.value == 3 * 4 + 2 * 1
 
 
 def test_obstacle_tables_layout():

@@ -50,17 +50,27 @@ def test_checkpoint_round_trip_continues_bit_for_bit(tmp_path):
     a.setFlowData(lb.FlowData(lb.FlowCriterion.ptestPlaneCriteria, flow))
     a.setReflectionData(lb.ReflectionData())
     a.step(7)
-    ck = str(tmp_path / "state.npz")
-    lio.save_checkpoint(a, ck)
+    ck = str(tmp_path / "state")                         # no suffix: both calls complete it the same way
+    assert lio.save_checkpoint(a, ck) == ck + ".npz"
     a.step(9)
     want = a.retrieve_populations()
     wf = a.retrieve_reflection_data()
+    wf64 = a.force_f64()
     b = fresh()
+    # stale state on the restoring side must not survive: another body, a source and a force accumulator
+    b.set_solid_mask(np.ones((n, n, n), np.uint8))
+    b.setFlowData(lb.FlowData(lb.FlowCriterion.ptestCriteria, flow * 3))
+    b.setReflectionData(lb.ReflectionData(5.0, 6.0, 7.0))
     lio.load_checkpoint(b, ck)
     b.step(9)
     assert np.array_equal(b.retrieve_populations(), want)
     bf = b.retrieve_reflection_data()
     assert np.allclose([bf.x, bf.y, bf.z], [wf.x, wf.y, wf.z], rtol=1e-6)
+    assert np.allclose(b.force_f64(), wf64, rtol=1e-12)      # the accumulator is restored as the double it is (order of the warp sums aside)
+    with pytest.raises(ValueError):
+        b.retrieve_populations(out=np.zeros((27, n, n, n), np.float64))
+    with pytest.raises(ValueError):
+        b.moments(out=[np.zeros(n ** 3 - 1, np.float32)] * 4)
     rho, ux, uy, uz = b.moments()
     lio.write_vti(str(tmp_path / "field.vti"), rho, ux, uy, uz, 1.0 / n, b.get_solid_mask())
     assert os.path.getsize(str(tmp_path / "field.vti")) > 16 * n ** 3
