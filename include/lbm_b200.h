@@ -153,6 +153,15 @@ LBM_API int lbm_get_solid_mask(lbm_handle h, uint8_t *solid);
  * cell that owns it.  Replaces LatticePoint::d_reflections / isReflected. */
 LBM_API int lbm_set_reflection_table(lbm_handle h, const void *tables, const int64_t *cell_index, int n);
 
+/* the same for a slab (x axis LBM_BC_HALO): the cell indices count nx + 2 planes, the neighbouring slabs' edge planes first
+ * and last (index = z + y*nz + (x+1)*nz*ny), like lbm_set_solid_mask with x_ghost_planes.  A boundary-solid cell in a
+ * neighbour's edge plane reflects into this slab too, so its table is needed here as well. */
+LBM_API int lbm_set_reflection_table_slab(lbm_handle h, const void *tables, const int64_t *cell_index, int n);
+/* where this slab sits in the whole lattice: its first plane is global plane x0 of gx.  lbm_insert_model and
+ * lbm_preprocess_model then work in global coordinates (lattice point = global index * spacing) and produce the
+ * neighbours' edge planes as well; the ends of the x axis are the reference's zero-inflow edges. */
+LBM_API int lbm_set_slab_origin(lbm_handle h, int x0, int gx);
+
 /* Lattice::setFlowData (Lattice.cpp:428-436) with the criterion as data instead of a device
  * function pointer: every cell with lo[a] <= coord[a] <= hi[a] gets f_i += f[i] each step.
  * FlowCriterion::testCriteria is the box (1,1,1)-(1,1,1); testPlaneCriteria is x in [0,0]. */

@@ -83,6 +83,8 @@ SYMBOLS = [
     ("lbm_set_solid_mask", _i, [_vp, _vp, _i]),
     ("lbm_get_solid_mask", _i, [_vp, _vp]),
     ("lbm_set_reflection_table", _i, [_vp, _vp, _vp, _i]),
+    ("lbm_set_reflection_table_slab", _i, [_vp, _vp, _vp, _i]),
+    ("lbm_set_slab_origin", _i, [_vp, _i, _i]),
     ("lbm_set_source", _i, [_vp, _i, _vp, _vp, _vp]),
     ("lbm_set_force_accumulator", _i, [_vp, _i, _vp]),
     ("lbm_set_force_accumulator_f64", _i, [_vp, _i, _vp]),

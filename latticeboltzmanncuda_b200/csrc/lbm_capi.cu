@@ -300,15 +300,6 @@ void fill_inplace(lbm_handle h, InplaceParams& ip)
     ip.tau = h->cfg.tau;
     ip.inv_tau = 1.0f / h->cfg.tau;
     ip.parity = h->aa_parity;
-    {
-        // on by default past the reach of the last-level TLB (2 MB pages; measured on B200: 59 GB runs at full speed,
-        // 80 GB does not); LBM_TLB_AHEAD=0 switches it off, another value sets the distance in planes
-        static const int env_ahead = [] { const char* e = getenv("LBM_TLB_AHEAD"); return e ? atoi(e) : -1; }();
-        static const int env_mode = [] { const char* e = getenv("LBM_TLB_MODE"); return e ? atoi(e) : 1; }();
-        const bool big = h->state_bytes() > (size_t(60) << 30);
-        ip.tlb_ahead = env_ahead >= 0 ? env_ahead : (big ? 4 : 0);
-        ip.tlb_mode = env_mode;
-    }
     for (int a = 0; a < 3; ++a) ip.bc[a] = h->cfg.bc[a];
     if (h->cfg.bc[0] == LBM_BC_HALO) {
         // x slabs: the neighbouring slab's edge plane in its own allocation (lbm_halo_connect), or this slab's own
@@ -326,6 +317,8 @@ void fill_inplace(lbm_handle h, InplaceParams& ip)
         ip.n_special = (long long)h->n_special;
         ip.cellinfo = h->cellinfo;
         ip.force = h->force_on ? h->force : nullptr;
+        static const bool split_even = [] { const char* e = getenv("LBM_AA_FORCE_SPLIT"); return e ? atoi(e) != 0 : false; }();
+        ip.force_pending = (ip.force && !split_even) ? h->force + 3 * FORCE_SLOTS : nullptr;
     }
     ip.src_on = h->src_on;
     for (int a = 0; a < 3; ++a) { ip.src_lo[a] = h->src_lo[a]; ip.src_hi[a] = h->src_hi[a]; }
@@ -359,8 +352,20 @@ int inplace_range(lbm_handle h, unsigned phases, int xa, int xb, cudaStream_t s)
         ip.special_k0 = h->special_start[xa];
         ip.n_special = (long long)h->special_start[xb] - (long long)h->special_start[xa];
     }
+    // on the handle's main stream the face and special-word kernels of an odd step run next to the interior launch (on
+    // the high-priority side stream): they touch disjoint slots, and the tail of one launch overlaps the other
+    static const bool concurrent = [] { const char* e = getenv("LBM_AA_CONCURRENT"); return e ? atoi(e) != 0 : true; }();
+    const bool fork = concurrent && s == h->stream && h->aa_parity == 0;
+    if (fork) {
+        CK(cudaEventRecord(h->ev_main, h->stream));
+        CK(cudaStreamWaitEvent(h->side, h->ev_main, 0));
+    }
     int launched = 0;
-    CK(launch_inplace_step(ip, h->cfg.q, h->cfg.moment_mode, h->cfg.eq_precision == LBM_EQ_FP64, s, &launched));
+    CK(launch_inplace_step(ip, h->cfg.q, h->cfg.moment_mode, h->cfg.eq_precision == LBM_EQ_FP64, s, fork ? h->side : nullptr, &launched));
+    if (fork) {
+        CK(cudaEventRecord(h->ev_side, h->side));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_side, 0));
+    }
     h->launches += launched;
     return LBM_OK;
 }
@@ -382,6 +387,11 @@ int step_a(lbm_handle h, unsigned phases)
                 h->launches += 1;
             }
             h->aa_dirty = false;
+        }
+        if (h->aa_parity == 0 && h->force_on && h->any_solid) {
+            // the momentum the previous odd step summed ahead of time belongs to the even step that has run since
+            CK(launch_inplace_fold_pending(h->force, h->force + 3 * FORCE_SLOTS, h->stream));
+            h->launches += 1;
         }
     } else {
         if (h->pending_commit) return fail(LBM_ERR_STATE, "lbm_step_range in flight: call lbm_step_commit first");
@@ -551,8 +561,9 @@ LBM_API int lbm_create(const lbm_config* cfg, lbm_handle* out)
         CKB(cudaMalloc(&h->buf[b], h->state_bytes()));
         CKB(cudaMemsetAsync(h->buf[b], 0, h->state_bytes(), h->stream));
     }
-    CKB(cudaMalloc(&h->force, 3 * FORCE_SLOTS * sizeof(double)));
-    CKB(cudaMemsetAsync(h->force, 0, 3 * FORCE_SLOTS * sizeof(double), h->stream));
+    // (two sets of partial sums: the second holds what the single-buffer engine sums ahead of time, see InplaceParams)
+    CKB(cudaMalloc(&h->force, 2 * 3 * FORCE_SLOTS * sizeof(double)));
+    CKB(cudaMemsetAsync(h->force, 0, 2 * 3 * FORCE_SLOTS * sizeof(double), h->stream));
     CKB(cudaMalloc(&h->diag, 4 * sizeof(double)));
     if (cfg->force_accum == LBM_FORCE_ACCUM_REFERENCE_FP32) {
         CKB(cudaMalloc(&h->force32, 3 * sizeof(float)));
@@ -726,6 +737,8 @@ LBM_API int lbm_upload_f_soa(lbm_handle h, const float* f)
         float* dst = h->inplace ? h->buf[0] + (size_t)dir_inv(q) * g.np : h->buf[h->cur] + (size_t)q * g.np;
         CK(copy_population(h, dst, src, true, h->stream));
     }
+    if (h->inplace && h->aa_parity == 1)      // momentum summed ahead of time for an even step that the replaced state will never take
+        CK(cudaMemsetAsync(h->force + 3 * FORCE_SLOTS, 0, 3 * FORCE_SLOTS * sizeof(double), h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->dead_dirty = 2;
     h->aa_parity = 0;
@@ -812,25 +825,30 @@ LBM_API int lbm_get_solid_mask(lbm_handle h, uint8_t* solid)
     return LBM_OK;
 }
 
-// Turns the reference's per-solid-cell scatter tables into per-fluid-cell gather lists.
-LBM_API int lbm_set_reflection_table(lbm_handle h, const void* tables, const int64_t* cell_index, int n)
+// Turns the reference's per-solid-cell scatter tables into per-fluid-cell gather lists.  `ghost` = the cell indices
+// count nx + 2 planes (the neighbouring slabs' edge planes first and last, like lbm_set_solid_mask with ghost planes):
+// a table of a ghost-plane cell feeds the cells of this slab it reflects into, a table of an edge cell feeds only the
+// targets inside this slab -- the neighbour holds the same table for the others.
+static int set_reflection_table(lbm_handle h, const void* tables, const int64_t* cell_index, int n, bool ghost)
 {
     int rc = use(h);
     if (rc) return rc;
     if ((rc = inplace_only(h, "lbm_set_reflection_table"))) return rc;
     if (n < 0 || (n > 0 && (!tables || !cell_index))) return fail(LBM_ERR_INVALID, "bad reflection table arguments");
-    if (h->cfg.bc[0] == LBM_BC_HALO && n > 0)
-        return fail(LBM_ERR_UNSUPPORTED, "table reflection is not available on halo (slab) handles yet");
+    if (h->cfg.bc[0] == LBM_BC_HALO && n > 0 && !ghost)
+        return fail(LBM_ERR_UNSUPPORTED, "slab handles take their tables with the neighbours' edge planes: lbm_set_reflection_table_slab");
     const Geom& g = h->g;
-    const long long ncell = (long long)g.nx * g.ny * g.nz;
+    const int xlo = ghost ? -1 : 0;
+    const long long ncell = (long long)(g.nx + (ghost ? 2 : 0)) * g.ny * g.nz;
     struct HostLink { uint32_t tgt; Link l; long long order; };
     std::vector<HostLink> hl;
     const size_t words = h->mask_words();
     std::vector<uint32_t> refl(words, 0u);
+    std::vector<int> interior;              // tables of cells inside the slab (what lbm_get_reflection_tables reports)
     for (int t = 0; t < n; ++t) {
         const long long k = cell_index[t];
         if (k < 0 || k >= ncell) return fail(LBM_ERR_INVALID, "reflection table %d: cell index out of range", t);
-        const int sx = (int)(k / ((long long)g.ny * g.nz));
+        const int sx = (int)(k / ((long long)g.ny * g.nz)) + xlo;
         const int rem = (int)(k % ((long long)g.ny * g.nz));
         const int sy = rem / g.nz, sz = rem % g.nz;
         const unsigned char* rec = (const unsigned char*)tables + (size_t)t * TABLE_BYTES;
@@ -839,7 +857,10 @@ LBM_API int lbm_set_reflection_table(lbm_handle h, const void* tables, const int
         std::memcpy(dirs, rec, sizeof dirs);
         std::memcpy(w, rec + sizeof dirs, sizeof w);
         const long long scell = g.cell(sx, sy, sz);
-        refl[(size_t)(scell >> 5)] |= 1u << (scell & 31);
+        if (sx >= 0 && sx < g.nx) {
+            refl[(size_t)(scell >> 5)] |= 1u << (scell & 31);
+            interior.push_back(t);
+        }
         for (int s = 1; s < 81; ++s) {      // slot 0 is never read (SimCalcFuncs.cu:164)
             const int d = (int)(((uint32_t)dirs[s / 6] >> (5 * (s % 6))) & 0x1Fu);   // SimCalcFuncs.cu:18-30
             if (d == 0) continue;
@@ -847,7 +868,7 @@ LBM_API int lbm_set_reflection_table(lbm_handle h, const void* tables, const int
             const int j = s / 3;
             if (d >= h->cfg.q || j >= h->cfg.q) continue;
             const int tx = sx + dir_c(d, 0), ty = sy + dir_c(d, 1), tz = sz + dir_c(d, 2);
-            if (tx < 0 || ty < 0 || tz < 0 || tx >= g.nx || ty >= g.ny || tz >= g.nz) continue;   // SimCalcFuncs.cu:175
+            if (tx < 0 || ty < 0 || tz < 0 || tx >= g.nx || ty >= g.ny || tz >= g.nz) continue;   // SimCalcFuncs.cu:175 (slabs: the neighbour's target)
             HostLink e;
             e.tgt = (uint32_t)g.cell(tx, ty, tz);
             e.l.src_cell = (uint32_t)scell;
@@ -857,8 +878,13 @@ LBM_API int lbm_set_reflection_table(lbm_handle h, const void* tables, const int
             hl.push_back(e);
         }
     }
-    h->host_tables.assign((const unsigned char*)tables, (const unsigned char*)tables + (size_t)n * TABLE_BYTES);
-    h->host_table_cells.assign(cell_index, cell_index + n);
+    h->host_tables.clear();
+    h->host_table_cells.clear();
+    for (int t : interior) {
+        const unsigned char* rec = (const unsigned char*)tables + (size_t)t * TABLE_BYTES;
+        h->host_tables.insert(h->host_tables.end(), rec, rec + TABLE_BYTES);
+        h->host_table_cells.push_back(cell_index[t] - (ghost ? (int64_t)g.ny * g.nz : 0));      // slab-local host index
+    }
     std::sort(hl.begin(), hl.end(), [](const HostLink& a, const HostLink& b) {
         if (a.tgt != b.tgt) return a.tgt < b.tgt;
         if (a.l.d != b.l.d) return a.l.d < b.l.d;      // the kernel walks a target's links population by population
@@ -932,6 +958,25 @@ LBM_API int lbm_set_reflection_table(lbm_handle h, const void* tables, const int
     return rebuild_special(h);
 }
 
+LBM_API int lbm_set_reflection_table(lbm_handle h, const void* tables, const int64_t* cell_index, int n)
+{
+    return set_reflection_table(h, tables, cell_index, n, false);
+}
+
+LBM_API int lbm_set_reflection_table_slab(lbm_handle h, const void* tables, const int64_t* cell_index, int n)
+{
+    return set_reflection_table(h, tables, cell_index, n, true);
+}
+
+LBM_API int lbm_set_slab_origin(lbm_handle h, int x0, int gx)
+{
+    if (!h) return fail(LBM_ERR_INVALID, "null handle");
+    if (x0 < 0 || gx < x0 + h->g.nx) return fail(LBM_ERR_INVALID, "lbm_set_slab_origin: the slab [%d, %d) does not fit a domain of %d planes", x0, x0 + h->g.nx, gx);
+    h->slab_x0 = x0;
+    h->slab_gx = gx;
+    return LBM_OK;
+}
+
 LBM_API int lbm_set_source(lbm_handle h, int kind, const int32_t lo[3], const int32_t hi[3], const float f[27])
 {
     if (!h) return fail(LBM_ERR_INVALID, "null handle");
@@ -955,7 +1000,7 @@ LBM_API int lbm_set_force_accumulator_f64(lbm_handle h, int enable, const double
     int rc = use(h);
     if (rc) return rc;
     h->force_on = enable != 0;
-    double v[3 * FORCE_SLOTS] = {0.0};
+    double v[2 * 3 * FORCE_SLOTS] = {0.0};
     if (init) for (int a = 0; a < 3; ++a) v[a] = init[a];
     CK(cudaMemcpyAsync(h->force, v, sizeof v, cudaMemcpyHostToDevice, h->stream));
     if (h->force32) {
@@ -978,13 +1023,15 @@ LBM_API int lbm_get_force_f64(lbm_handle h, double out[3])
         for (int a = 0; a < 3; ++a) out[a] = v32[a];
         return LBM_OK;
     }
-    double v[3 * FORCE_SLOTS];
+    double v[2 * 3 * FORCE_SLOTS];
     if (h->halo.edge) CK(cudaStreamSynchronize(h->halo.edge));
     CK(cudaMemcpyAsync(v, h->force, sizeof v, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    // single-buffer engine: the sums made ahead of time count once the even step they belong to has run
+    const int sets = (h->inplace && h->aa_parity == 0) ? 2 : 1;
     for (int a = 0; a < 3; ++a) {
         double t = 0.0;
-        for (int k = 0; k < FORCE_SLOTS; ++k) t += v[3 * k + a];
+        for (int k = 0; k < sets * FORCE_SLOTS; ++k) t += v[3 * k + a];
         out[a] = t;
     }
     return LBM_OK;

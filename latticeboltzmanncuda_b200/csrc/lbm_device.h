@@ -142,6 +142,11 @@ struct InplaceParams {
     long long n_special;
     const uint32_t* cellinfo;
     double* force;            // FORCE_SLOTS x 3 partial sums of the momentum exchange, or nullptr
+    // The momentum a cell hands to an obstacle in an EVEN step is carried by the populations the preceding odd step
+    // parked in the cell's own slots: the odd step's special-word kernel sums it ahead of time into force_pending
+    // (counted once the even step has run, lbm_get_force), so that the even step needs no special-word pass.
+    // nullptr: the even step sums it itself (aa_even_special_kernel; LBM_AA_FORCE_SPLIT=1, kept for comparison).
+    double* force_pending;
     int   src_on;             // additive box source, applied after the collision
     int   src_lo[3], src_hi[3];
     float src_f[27];
@@ -156,9 +161,6 @@ struct InplaceParams {
     // in thickness and therefore in population stride.
     long long shift[3][2];
     long long xshift[2][27];
-    // address-translation look-ahead (0 = off): one block per plane touches every 2 MB page of the plane `tlb_ahead`
-    // planes further on, so that the page walk is over when the sweep arrives (lattices beyond ~64 GB, profiles/r02_notes.md)
-    int   tlb_ahead, tlb_mode;
 };
 
 // offsets of the in-place engine for a lattice of geometry g (everything else is left untouched)
@@ -181,7 +183,10 @@ inline void set_inplace_offsets(InplaceParams& ip, const Geom& g)
 
 cudaError_t launch_inplace_zero_solid(const InplaceParams& p, int q, cudaStream_t stream);
 cudaError_t launch_inplace_merge_edges(const InplaceParams& p, int q, cudaStream_t stream);
-cudaError_t launch_inplace_step(const InplaceParams& p, int q, int moment, int eq64, cudaStream_t stream, int* launches);
+// `side` (optional): the face and special-word kernels of an odd step run there, next to the interior launch on `stream`
+// (they touch disjoint slots); the caller orders the two streams before and after
+cudaError_t launch_inplace_step(const InplaceParams& p, int q, int moment, int eq64, cudaStream_t stream, cudaStream_t side, int* launches);
+cudaError_t launch_inplace_fold_pending(double* force, double* pending, cudaStream_t stream);
 cudaError_t launch_inplace_scatter(const float* dense, float* f, const Geom& g, int q_index, int x0, int nxc, cudaStream_t stream);
 cudaError_t launch_inplace_gather(const InplaceParams& p, int q, float* dense, int q_index, int x0, int nxc, cudaStream_t stream);
 cudaError_t launch_inplace_moments(const InplaceParams& p, int q, int moment_mode, float* rho, float* ux, float* uy, float* uz, cudaStream_t stream);

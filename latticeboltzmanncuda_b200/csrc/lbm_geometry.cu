@@ -253,15 +253,16 @@ LBM_HD void distribute_vector(const float v[3], float scores[27], int dirs[27])
 // ---- kernels ----------------------------------------------------------------------------------------------
 
 // Lattice::insertModel's triple loop (Lattice.cpp:248-257), one thread per cell, host cell order
-__global__ void voxelise_kernel(MeshView m, uint8_t* __restrict__ solid, int nx, int ny, int nz, float spacing)
+// (slabs: plane 0 of the array is global plane x_origin of gx; planes outside the lattice are fluid)
+__global__ void voxelise_kernel(MeshView m, uint8_t* __restrict__ solid, int nx, int ny, int nz, float spacing, int x_origin, int gx)
 {
     const long long n = (long long)nx * ny * nz;
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int z = (int)(k % nz);
     const int y = (int)((k / nz) % ny);
-    const int x = (int)(k / ((long long)nz * ny));
-    solid[k] = point_inside(m, x * spacing, y * spacing, z * spacing) ? 1 : 0;
+    const int x = (int)(k / ((long long)nz * ny)) + x_origin;
+    solid[k] = (x >= 0 && x < gx && point_inside(m, x * spacing, y * spacing, z * spacing)) ? 1 : 0;
 }
 
 // solid cells with at least one in-domain fluid neighbour: the only cells that can own a table
@@ -289,9 +290,10 @@ struct TableRecord {       // ReflectionValues, simulation/include/LatticePoint.
 
 // Lattice::preProcessModel's per-cell body (Lattice.cpp:342-411), one thread per candidate cell.
 // An out-of-domain neighbour is treated as unavailable where the reference indexes without a check (:369).
+// (slabs: the array holds the planes x_origin .. x_origin + nx - 1 of the lattice; positions use the global index)
 __global__ void table_kernel(MeshView m, const uint8_t* __restrict__ solid, const long long* __restrict__ cells, int ncells,
                              TableRecord* __restrict__ tables, uint8_t* __restrict__ reflected, int nx, int ny, int nz,
-                             float spacing, HalfTurn ht)
+                             float spacing, HalfTurn ht, int x_origin)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
@@ -305,8 +307,8 @@ __global__ void table_kernel(MeshView m, const uint8_t* __restrict__ solid, cons
         const int nxp = x + dir_c(d, 0), nyp = y + dir_c(d, 1), nzp = z + dir_c(d, 2);
         if (nxp < 0 || nyp < 0 || nzp < 0 || nxp >= nx || nyp >= ny || nzp >= nz) continue;
         if (solid[((long long)nxp * ny + nyp) * nz + nzp]) continue;
-        const float p1[3] = {spacing * nxp, spacing * nyp, spacing * nzp};
-        const float p2[3] = {spacing * x, spacing * y, spacing * z};
+        const float p1[3] = {spacing * (nxp + x_origin), spacing * nyp, spacing * nzp};
+        const float p2[3] = {spacing * (x + x_origin), spacing * y, spacing * z};
         float r[3], scores[27];
         int dirs[27];
         reflection_vector(m, p1, p2, ht, r);
@@ -539,7 +541,8 @@ LBM_API unsigned lbm_compress_ints(const int* array, int num, int bit_length)
     return out;
 }
 
-// Lattice::insertModel (Lattice.cpp:228-260): voxelise the mesh on the lattice points index*spacing
+// Lattice::insertModel (Lattice.cpp:228-260): voxelise the mesh on the lattice points index*spacing.
+// On a slab (lbm_set_slab_origin) the index is the global one and the neighbours' edge planes are voxelised too.
 LBM_API int lbm_insert_model(lbm_handle h, lbm_mesh m, float spacing, int* accepted)
 {
     int rc = lbm_internal_use(h);
@@ -548,70 +551,116 @@ LBM_API int lbm_insert_model(lbm_handle h, lbm_mesh m, float spacing, int* accep
     if (accepted) *accepted = 0;
     const Geom& g = h->g;
     if (!m->loaded || m->v.empty()) return LBM_OK;
+    const bool slab = h->cfg.bc[0] == LBM_BC_HALO;
+    if (slab && h->slab_gx <= 0) return lbm_internal_fail(LBM_ERR_STATE, "insert_model on a slab handle: call lbm_set_slab_origin first (or set the mask planes)");
+    const int gx = slab ? h->slab_gx : g.nx;
     // the bounding-box guard: a mesh that leaves the box is silently ignored (Lattice.cpp:236-244)
-    if (m->lo[0] < 0.0 || m->lo[1] < 0.0 || m->lo[2] < 0.0 || m->hi[0] > g.nx * spacing || m->hi[1] > g.ny * spacing ||
+    if (m->lo[0] < 0.0 || m->lo[1] < 0.0 || m->lo[2] < 0.0 || m->hi[0] > gx * spacing || m->hi[1] > g.ny * spacing ||
         m->hi[2] > g.nz * spacing)
         return LBM_OK;
-    if (h->cfg.bc[0] == LBM_BC_HALO) return lbm_internal_fail(LBM_ERR_UNSUPPORTED, "insert_model on a slab handle: set the mask planes instead");
     MeshView v;
     if ((rc = device_view(m, h->device, &v))) return rc;
-    const size_t n = (size_t)g.nx * g.ny * g.nz;
-    if (!h->solid_bytes) GCK(cudaMalloc(&h->solid_bytes, n + 2 * (size_t)g.ny * g.nz));
-    voxelise_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(v, h->solid_bytes, g.nx, g.ny, g.nz, spacing);
+    const size_t per = (size_t)g.ny * g.nz;
+    const size_t n = (size_t)g.nx * per;
+    if (!h->solid_bytes) GCK(cudaMalloc(&h->solid_bytes, n + 2 * per));
+    if (slab) {
+        voxelise_kernel<<<(unsigned)((n + 2 * per + 127) / 128), 128, 0, h->stream>>>(v, h->solid_bytes, g.nx + 2, g.ny, g.nz, spacing,
+                                                                                  h->slab_x0 - 1, gx);
+    } else {
+        voxelise_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(v, h->solid_bytes, g.nx, g.ny, g.nz, spacing, 0, g.nx);
+    }
     GCK(cudaGetLastError());
     if (accepted) *accepted = 1;
-    return lbm_internal_rebuild_mask(h, h->solid_bytes, 0);
+    return lbm_internal_rebuild_mask(h, h->solid_bytes, slab ? 1 : 0);
 }
 
-// Lattice::preProcessModel (Lattice.cpp:323-426): build the reflection tables of the boundary-solid cells
+// Lattice::preProcessModel (Lattice.cpp:323-426): build the reflection tables of the boundary-solid cells.
+// On a slab the tables are built for its own planes and the neighbours' edge planes (a boundary-solid cell there
+// reflects into this slab as well); the cells they look at reach one plane further, so the box that is voxelised for
+// this spans two planes beyond each face (clipped to the lattice).
 LBM_API int lbm_preprocess_model(lbm_handle h, lbm_mesh m, float spacing)
 {
     int rc = lbm_internal_use(h);
     if (rc) return rc;
     if (!m) return lbm_internal_fail(LBM_ERR_INVALID, "null mesh");
     const Geom& g = h->g;
-    const size_t n = (size_t)g.nx * g.ny * g.nz;
-    if (!h->solid || !h->any_solid) return lbm_set_reflection_table(h, nullptr, nullptr, 0);
+    const bool slab = h->cfg.bc[0] == LBM_BC_HALO;
+    if (slab && h->slab_gx <= 0) return lbm_internal_fail(LBM_ERR_STATE, "preprocess_model on a slab handle: call lbm_set_slab_origin first");
+    auto install = [&](const void* t, const int64_t* c, int cnt) {
+        return slab ? lbm_set_reflection_table_slab(h, t, c, cnt) : lbm_set_reflection_table(h, t, c, cnt);
+    };
+    if (!h->solid || !h->any_solid) return install(nullptr, nullptr, 0);
     MeshView v;
     if ((rc = device_view(m, h->device, &v))) return rc;
     if (!m->loaded) v.nf = 0;
-    if (!h->solid_bytes) GCK(cudaMalloc(&h->solid_bytes, n + 2 * (size_t)g.ny * g.nz));
-    GCK(launch_mask_to_bytes(h->solid, h->solid_bytes, g, h->stream));
+    // the box the tables are built on: the lattice itself, or the slab and two planes beyond each face
+    const int xa = slab ? std::max(0, h->slab_x0 - 2) : 0;
+    const int xb = slab ? std::min(h->slab_gx, h->slab_x0 + g.nx + 2) : g.nx;
+    const int bx = xb - xa;
+    const size_t per = (size_t)g.ny * g.nz;
+    const size_t n = (size_t)bx * per;
+    uint8_t* box = nullptr;          // solid flags of the box
+    if (slab) {
+        GCK(cudaMalloc(&box, n));
+        MeshView vv = v;
+        if (!m->loaded) vv.nf = 0;
+        voxelise_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(vv, box, bx, g.ny, g.nz, spacing, xa, h->slab_gx);
+    } else {
+        if (!h->solid_bytes) GCK(cudaMalloc(&h->solid_bytes, n + 2 * per));
+        GCK(launch_mask_to_bytes(h->solid, h->solid_bytes, g, h->stream));
+        box = h->solid_bytes;
+    }
+    auto drop_box = [&] { if (slab) cudaFree(box); };
     uint8_t* d_cand = nullptr;
-    GCK(cudaMalloc(&d_cand, n));
-    candidate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->solid_bytes, d_cand, g.nx, g.ny, g.nz);
+    cudaError_t e = cudaMalloc(&d_cand, n);
+    if (e != cudaSuccess) { drop_box(); return lbm_internal_fail(LBM_ERR_NOMEM, cudaGetErrorString(e)); }
+    candidate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(box, d_cand, bx, g.ny, g.nz);
     std::vector<uint8_t> cand(n);
-    cudaError_t e = cudaMemcpyAsync(cand.data(), d_cand, n, cudaMemcpyDeviceToHost, h->stream);
+    e = cudaMemcpyAsync(cand.data(), d_cand, n, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(d_cand);
-    if (e != cudaSuccess) return lbm_internal_fail(LBM_ERR_CUDA, cudaGetErrorString(e));
+    if (e != cudaSuccess) { drop_box(); return lbm_internal_fail(LBM_ERR_CUDA, cudaGetErrorString(e)); }
+    // candidates in host order = the order the reference discovers them in; a slab keeps those of its own planes and of
+    // the neighbours' edge planes
+    const int keep_lo = slab ? h->slab_x0 - 1 : 0, keep_hi = slab ? h->slab_x0 + g.nx : g.nx - 1;      // global planes, inclusive
     std::vector<long long> cells;
-    for (size_t k = 0; k < n; ++k)
-        if (cand[k]) cells.push_back((long long)k);          // host order = the order the reference discovers them in
-    if (cells.empty()) return lbm_set_reflection_table(h, nullptr, nullptr, 0);
+    for (size_t k = 0; k < n; ++k) {
+        if (!cand[k]) continue;
+        const int xg = (int)(k / per) + xa;
+        if (xg >= keep_lo && xg <= keep_hi) cells.push_back((long long)k);
+    }
+    if (cells.empty()) { drop_box(); return install(nullptr, nullptr, 0); }
     long long* d_cells = nullptr;
     TableRecord* d_tables = nullptr;
     uint8_t* d_refl = nullptr;
     const int nc = (int)cells.size();
-    GCK(cudaMalloc(&d_cells, nc * sizeof(long long)));
-    GCK(cudaMalloc(&d_tables, nc * sizeof(TableRecord)));
-    GCK(cudaMalloc(&d_refl, nc));
-    GCK(cudaMemcpyAsync(d_cells, cells.data(), nc * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
-    table_kernel<<<(nc + 63) / 64, 64, 0, h->stream>>>(v, h->solid_bytes, d_cells, nc, d_tables, d_refl, g.nx, g.ny, g.nz, spacing, half_turn());
+    e = cudaMalloc(&d_cells, nc * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc(&d_tables, nc * sizeof(TableRecord));
+    if (e == cudaSuccess) e = cudaMalloc(&d_refl, nc);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_cells, cells.data(), nc * sizeof(long long), cudaMemcpyHostToDevice, h->stream);
     std::vector<TableRecord> tables(nc);
     std::vector<uint8_t> refl(nc);
-    e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        table_kernel<<<(nc + 63) / 64, 64, 0, h->stream>>>(v, box, d_cells, nc, d_tables, d_refl, bx, g.ny, g.nz, spacing, half_turn(), xa);
+        e = cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(tables.data(), d_tables, nc * sizeof(TableRecord), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(refl.data(), d_refl, nc, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(d_cells); cudaFree(d_tables); cudaFree(d_refl);
+    drop_box();
     if (e != cudaSuccess) return lbm_internal_fail(LBM_ERR_CUDA, cudaGetErrorString(e));
     std::vector<TableRecord> keep;
     std::vector<int64_t> keep_cells;
-    for (int c = 0; c < nc; ++c)
-        if (refl[c]) { keep.push_back(tables[c]); keep_cells.push_back(cells[c]); }
+    for (int c = 0; c < nc; ++c) {
+        if (!refl[c]) continue;
+        keep.push_back(tables[c]);
+        // box index -> the handle's index space (a slab counts its planes from the low neighbour's edge plane)
+        const long long shift = slab ? (long long)(xa - (h->slab_x0 - 1)) * (long long)per : 0;
+        keep_cells.push_back(cells[c] + shift);
+    }
     static_assert(sizeof(TableRecord) == 380, "ReflectionValues is 380 bytes");
-    return lbm_set_reflection_table(h, keep.data(), keep_cells.data(), (int)keep.size());
+    return install(keep.data(), keep_cells.data(), (int)keep.size());
 }
 
 // the tables currently set on the handle (by lbm_preprocess_model or lbm_set_reflection_table)

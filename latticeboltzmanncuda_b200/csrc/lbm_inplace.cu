@@ -43,6 +43,12 @@ namespace {
 // the collision operators are shared with lbm_kernels.cu through this header-like include
 #include "lbm_collide.inl"
 
+// Moving-wall terms are formed and added with explicitly rounded operations: the same cell goes through different code
+// (interior kernel, face kernel, special-word kernel) depending on where a slab boundary falls, and a product that one
+// of them contracted into the following add would differ in the last bit from the others.
+__device__ __forceinline__ float wall_term(float w6, float sgn, float cu) { return __fmul_rn(__fmul_rn(w6, sgn), cu); }
+__device__ __forceinline__ float plus_term(float v, float t) { return __fadd_rn(v, t); }
+
 struct Edge {          // where population i of cell (x,y,z) comes from / goes to
     long long off;     // complete element offset from the cell: population slot + neighbour cell (valid when kind == 0)
     int kind;          // 0 neighbour inside (possibly wrapped, possibly in the neighbouring slab), 1 wall
@@ -75,8 +81,8 @@ __device__ __forceinline__ Edge edge_lookup(const InplaceParams& p, int i, int x
                 const float* u = p.wall_u[a * 2 + (t < 0 ? 0 : 1)];
                 // pull (sign -1): the population arriving is i itself; push (sign +1): it comes back as inv(i) = -c_i
                 const float s = (sign < 0) ? 1.0f : -1.0f;
-                e.term = 6.0f * (float)dir_weight<Q>(i) * s *
-                         ((float)dir_c(i, 0) * u[0] + (float)dir_c(i, 1) * u[1] + (float)dir_c(i, 2) * u[2]);
+                e.term = wall_term(6.0f * (float)dir_weight<Q>(i), s,
+                                   (float)dir_c(i, 0) * u[0] + (float)dir_c(i, 1) * u[1] + (float)dir_c(i, 2) * u[2]);
             }
             e.kind = 1;
         } else {
@@ -108,32 +114,6 @@ __device__ __forceinline__ void add_source(const InplaceParams& p, float (&f)[Q]
 
 enum : unsigned { AA_ORDINARY = 0, AA_DEAD = 1, AA_SPECIAL = 2 };      // word classes, as in lbm_kernels.cu
 
-// Lattices of more than ~64 GB lose a third of their speed although they move the same bytes per cell (ncu: same DRAM
-// traffic, twice the lg_throttle / long_scoreboard stalls, independent of shape and padding -- profiles/r02_notes.md): the
-// sweep touches every 2 MB page once per step, and past the reach of the last-level TLB every first touch is a page walk
-// that all SMs entering the page wait for together.  One block per plane therefore touches every page of every
-// population `ahead` planes further on (one request per 2 MB), so that the walk overlaps with the work on the planes in
-// between.  mode 1: prefetch.global.L2, mode 2: a load whose value is dropped.
-template <int Q>
-__device__ __forceinline__ void touch_pages_ahead(const InplaceParams& p, int x, unsigned t)
-{
-#if defined(__CUDACC__)
-    const Geom& g = p.g;
-    const int xa = x + p.tlb_ahead;
-    if (t >= (unsigned)Q || xa > g.nx) return;
-    const float* base = p.f + (long long)t * g.np + (long long)(xa + 1) * g.plane;
-    constexpr long long PAGE = (2ll << 20) / (long long)sizeof(float);
-    for (long long off = 0; off < g.plane; off += PAGE) {
-        if (p.tlb_mode == 2) {
-            float v;
-            asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(base + off));
-        } else {
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(base + off));
-        }
-    }
-#endif
-}
-
 // EXTRA: the lattice has a solid mask and / or a source (kept out of the all-fluid instantiation)
 template <int Q, int MOMENT, bool EQ64, bool EXTRA>
 __global__ void __launch_bounds__(256, (Q == 19 && !EQ64) ? 6 : 4) aa_even_kernel(const __grid_constant__ InplaceParams p)
@@ -142,11 +122,10 @@ __global__ void __launch_bounds__(256, (Q == 19 && !EQ64) ? 6 : 4) aa_even_kerne
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int x = p.x0 + blockIdx.z;                 // the launch covers the planes [x0, x1)
-    if (p.tlb_ahead && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.y == 0) touch_pages_ahead<Q>(p, x, threadIdx.x);
     if (z >= g.nz || y >= g.ny) return;
     if (EXTRA && p.solid) {
         // a warp is 32 consecutive z of one row = one 32-cell word (blockDim.x is a multiple of 32)
-        if (p.force) {
+        if (p.force && !p.force_pending) {
             // the momentum exchange is summed by aa_even_special_kernel, which takes the special words: ordinary words only
             if (__ldg(p.cls + ((long long)x * ((g.nz + 31) >> 5) + (z >> 5)) * p.cls_pitch + y) != AA_ORDINARY) return;
         } else {
@@ -175,7 +154,7 @@ __device__ __forceinline__ void aa_odd_edge_cell(const InplaceParams& p, float* 
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
         const Edge e = edge_lookup<Q, AXES>(p, i, x, y, z, -1);
-        f[i] = (e.kind == 0) ? a[e.off] : a[p.pop_off[i]] + e.term;
+        f[i] = (e.kind == 0) ? a[e.off] : plus_term(a[p.pop_off[i]], e.term);
     }
     if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
     else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
@@ -185,7 +164,7 @@ __device__ __forceinline__ void aa_odd_edge_cell(const InplaceParams& p, float* 
     for (int i = 0; i < Q; ++i) {
         const Edge e = edge_lookup<Q, AXES>(p, i, x, y, z, +1);
         if (e.kind == 0) a[e.off] = f[i];
-        else             a[p.park_off[i]] = f[i] + e.term;
+        else             a[p.park_off[i]] = plus_term(f[i], e.term);
     }
 }
 
@@ -214,8 +193,8 @@ __device__ __forceinline__ void aa_odd_zedge_cell(const InplaceParams& p, float*
         for (int i = 1; i < Q; ++i) {
             if (dir_c(i, 2) != 0 && (dir_c(i, 2) > 0 ? lo : hi)) {
                 const float* u = p.wall_u[dir_c(i, 2) > 0 ? 4 : 5];
-                f[i] += 6.0f * (float)dir_weight<Q>(i) * 1.0f *
-                        ((float)dir_c(i, 0) * u[0] + (float)dir_c(i, 1) * u[1] + (float)dir_c(i, 2) * u[2]);
+                f[i] = plus_term(f[i], wall_term(6.0f * (float)dir_weight<Q>(i), 1.0f,
+                                                 (float)dir_c(i, 0) * u[0] + (float)dir_c(i, 1) * u[1] + (float)dir_c(i, 2) * u[2]));
             }
         }
     }
@@ -234,8 +213,8 @@ __device__ __forceinline__ void aa_odd_zedge_cell(const InplaceParams& p, float*
                 off = wall ? p.park_off[i] : off + (dir_c(i, 2) < 0 ? g.nz : -g.nz);
                 if (wall) {
                     const float* u = p.wall_u[dir_c(i, 2) < 0 ? 4 : 5];
-                    v += 6.0f * (float)dir_weight<Q>(i) * -1.0f *
-                         ((float)dir_c(i, 0) * u[0] + (float)dir_c(i, 1) * u[1] + (float)dir_c(i, 2) * u[2]);
+                    v = plus_term(v, wall_term(6.0f * (float)dir_weight<Q>(i), -1.0f,
+                                               (float)dir_c(i, 0) * u[0] + (float)dir_c(i, 1) * u[1] + (float)dir_c(i, 2) * u[2]));
                 }
             }
         }
@@ -266,7 +245,6 @@ __global__ void __launch_bounds__(128, (MODE == 0 && Q == 19 && !EQ64) ? (EXTRA 
         if (w >= wcount) return;
         y = 1 + blockIdx.y;
         x = p.x0 + blockIdx.z;
-        if (p.tlb_ahead && blockIdx.x == 0 && blockIdx.y == 0) touch_pages_ahead<Q>(p, x + 1, threadIdx.x);
     } else if constexpr (MODE == 2) {
         // face planes of the range: plane 0 if x0 == 0, plane nx-1 if x1 == nx (one plane when nx == 1)
         const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -338,9 +316,9 @@ __device__ __forceinline__ void bounce_momentum(const float (&f)[Q], uint32_t nb
 }
 
 // one atomic triple per warp into one of FORCE_SLOTS partial sums (all 32 lanes of the warp arrive here)
-__device__ __forceinline__ void warp_force_add(const InplaceParams& p, uint32_t widx, float fx, float fy, float fz)
+__device__ __forceinline__ void warp_force_add(double* sums, uint32_t widx, float fx, float fy, float fz)
 {
-    double* slot = p.force + 3 * ((unsigned)(widx >> 2) % FORCE_SLOTS);
+    double* slot = sums + 3 * ((unsigned)(widx >> 2) % FORCE_SLOTS);
     if (!__any_sync(0xffffffffu, fx != 0.0f || fy != 0.0f || fz != 0.0f)) return;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -361,7 +339,7 @@ __device__ __forceinline__ void warp_force_add(const InplaceParams& p, uint32_t 
 // periodic: wrapped neighbour); AXES = 0 is the word away from every edge, with constant-bank offsets only.
 template <int Q, int MOMENT, bool EQ64, int AXES, bool FORCE>
 __device__ __forceinline__ void aa_odd_geo_cell(const InplaceParams& p, float* a, int x, int y, int z, uint32_t nb,
-                                                float& fx, float& fy, float& fz)
+                                                float& fx, float& fy, float& fz, float& gx, float& gy, float& gz)
 {
     float f[Q];
     f[0] = a[p.pop_off[0]];
@@ -374,7 +352,7 @@ __device__ __forceinline__ void aa_odd_geo_cell(const InplaceParams& p, float* a
             const Edge e = edge_lookup<Q, AXES>(p, i, x, y, z, -1);
             const bool self = own || e.kind != 0;
             const float v = a[self ? p.pop_off[i] : e.off];
-            f[i] = (!own && e.kind != 0) ? v + e.term : v;
+            f[i] = (!own && e.kind != 0) ? plus_term(v, e.term) : v;
         }
     }
     if (FORCE) bounce_momentum<Q>(f, nb, fx, fy, fz);
@@ -386,12 +364,20 @@ __device__ __forceinline__ void aa_odd_geo_cell(const InplaceParams& p, float* a
 #pragma unroll
     for (int i = 1; i < Q; ++i) {
         const bool own = (nb >> nb_bit(dir_c(i, 0), dir_c(i, 1), dir_c(i, 2))) & 1u;         // x + c_i is solid
+        if (FORCE && own && p.force_pending) {
+            // parked for the next (even) step, where it arrives as population inv(i) with the obstacle upstream: the
+            // momentum that step hands over, -c_inv(i) * 2 f = +c_i * 2 f (bounce_momentum), summed here ahead of time
+            const float m = f[i] + f[i];
+            gx += (float)dir_c(i, 0) * m;
+            gy += (float)dir_c(i, 1) * m;
+            gz += (float)dir_c(i, 2) * m;
+        }
         if constexpr (AXES == 0) {
             a[own ? p.pop_off[dir_inv(i)] : p.push_off[i]] = f[i];
         } else {
             const Edge e = edge_lookup<Q, AXES>(p, i, x, y, z, +1);
             const bool self = own || e.kind != 0;
-            a[self ? p.pop_off[dir_inv(i)] : e.off] = (!own && e.kind != 0) ? f[i] + e.term : f[i];
+            a[self ? p.pop_off[dir_inv(i)] : e.off] = (!own && e.kind != 0) ? plus_term(f[i], e.term) : f[i];
         }
     }
 }
@@ -417,15 +403,18 @@ __global__ void __launch_bounds__(128, Q == 19 ? 8 : 6) aa_odd_special_kernel(co
     const int z = w * 32 + (int)lane;
     const bool live = z < g.nz && !((nb >> nb_bit(0, 0, 0)) & 1u);
     if (!FORCE && !live) return;
-    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+    float fx = 0.0f, fy = 0.0f, fz = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
     if (live) {
         float* a = p.f + (long long)widx * 32 + lane;
         const int wcount = (g.nz + 31) >> 5;
-        if (x == 0 || x == g.nx - 1 || y == 0 || y == g.ny - 1) aa_odd_geo_cell<Q, MOMENT, EQ64, 7, FORCE>(p, a, x, y, z, nb, fx, fy, fz);
-        else if (w == 0 || w == wcount - 1)                     aa_odd_geo_cell<Q, MOMENT, EQ64, 4, FORCE>(p, a, x, y, z, nb, fx, fy, fz);
-        else                                                    aa_odd_geo_cell<Q, MOMENT, EQ64, 0, FORCE>(p, a, x, y, z, nb, fx, fy, fz);
+        if (x == 0 || x == g.nx - 1 || y == 0 || y == g.ny - 1) aa_odd_geo_cell<Q, MOMENT, EQ64, 7, FORCE>(p, a, x, y, z, nb, fx, fy, fz, gx, gy, gz);
+        else if (w == 0 || w == wcount - 1)                     aa_odd_geo_cell<Q, MOMENT, EQ64, 4, FORCE>(p, a, x, y, z, nb, fx, fy, fz, gx, gy, gz);
+        else                                                    aa_odd_geo_cell<Q, MOMENT, EQ64, 0, FORCE>(p, a, x, y, z, nb, fx, fy, fz, gx, gy, gz);
     }
-    if (FORCE) warp_force_add(p, widx, fx, fy, fz);
+    if (FORCE) {
+        warp_force_add(p.force, widx, fx, fy, fz);
+        if (p.force_pending) warp_force_add(p.force_pending, widx, gx, gy, gz);
+    }
 }
 
 // even step of the special words when the momentum exchange is summed (otherwise aa_even_kernel takes them too):
@@ -460,7 +449,7 @@ __global__ void __launch_bounds__(128, 8) aa_even_special_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < Q; ++i) a[p.park_off[i]] = f[i];
     }
-    warp_force_add(p, widx, fx, fy, fz);
+    warp_force_add(p.force, widx, fx, fy, fz);
 }
 
 // x slabs, after an odd step.  The neighbouring slab pushed populations across the shared face into its ghost copy
@@ -521,7 +510,7 @@ __device__ __forceinline__ float aa_fetch(const InplaceParams& p, int i, int x, 
     }
     const Edge e = edge_lookup<Q>(p, i, x, y, z, +1);
     // a population that bounced off a wall is parked in the opposite slot with the wall term already added
-    return (e.kind == 0) ? a[e.off] : a[(long long)dir_inv(i) * g.np] - e.term;
+    return (e.kind == 0) ? a[e.off] : plus_term(a[(long long)dir_inv(i) * g.np], -e.term);
 }
 
 template <int Q>
@@ -609,11 +598,12 @@ __global__ void __launch_bounds__(256) aa_mass_kernel(const __grid_constant__ In
 // one step of the planes [p.x0, p.x1) (and of the special-list entries [p.special_k0, p.special_k0 + p.n_special),
 // which the caller sets to the entries of those planes)
 template <int Q, int MOMENT, bool EQ64, bool EXTRA>
-cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, int* launches)
+cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, cudaStream_t side, int* launches)
 {
     const Geom& g = p.g;
     int n = 0;
     if (p.x1 <= p.x0) return cudaSuccess;
+    if (!side) side = stream;
     const unsigned special_blocks = (unsigned)((p.n_special + 3) / 4);
     if (p.parity == 0) {        // parked form -> pull / push
         const int wcount = (g.nz + 31) / 32;
@@ -627,18 +617,18 @@ cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, int* launches)
                 ++n;
             }
             const long long warps = (long long)(xi1 - xi0) * (g.ny < 2 ? g.ny : 2) * wcount;
-            aa_odd_kernel<Q, MOMENT, EQ64, 3, EXTRA><<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(pi);
+            aa_odd_kernel<Q, MOMENT, EQ64, 3, EXTRA><<<(unsigned)((warps + 3) / 4), 128, 0, side>>>(pi);
             ++n;
         }
         const int faces = (p.x0 == 0 ? 1 : 0) + ((p.x1 == g.nx && g.nx > 1) ? 1 : 0);
         if (faces) {
             const long long warps = (long long)faces * g.ny * wcount;
-            aa_odd_kernel<Q, MOMENT, EQ64, 2, EXTRA><<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(p);
+            aa_odd_kernel<Q, MOMENT, EQ64, 2, EXTRA><<<(unsigned)((warps + 3) / 4), 128, 0, side>>>(p);
             ++n;
         }
         if (EXTRA && p.cls && p.n_special > 0) {
-            if (p.force) aa_odd_special_kernel<Q, MOMENT, EQ64, true><<<special_blocks, 128, 0, stream>>>(p);
-            else         aa_odd_special_kernel<Q, MOMENT, EQ64, false><<<special_blocks, 128, 0, stream>>>(p);
+            if (p.force) aa_odd_special_kernel<Q, MOMENT, EQ64, true><<<special_blocks, 128, 0, side>>>(p);
+            else         aa_odd_special_kernel<Q, MOMENT, EQ64, false><<<special_blocks, 128, 0, side>>>(p);
             ++n;
         }
     } else {                    // arrived form -> local
@@ -649,8 +639,8 @@ cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, int* launches)
         dim3 block(bz, by, 1), grid((g.nz + bz - 1) / bz, (g.ny + by - 1) / by, p.x1 - p.x0);
         aa_even_kernel<Q, MOMENT, EQ64, EXTRA><<<grid, block, 0, stream>>>(p);
         ++n;
-        if (EXTRA && p.cls && p.force && p.n_special > 0) {
-            aa_even_special_kernel<Q, MOMENT, EQ64><<<special_blocks, 128, 0, stream>>>(p);
+        if (EXTRA && p.cls && p.force && !p.force_pending && p.n_special > 0) {
+            aa_even_special_kernel<Q, MOMENT, EQ64><<<special_blocks, 128, 0, side>>>(p);
             ++n;
         }
     }
@@ -659,23 +649,41 @@ cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, int* launches)
 }
 
 template <int Q>
-cudaError_t launch_q(const InplaceParams& p, int moment, int eq64, cudaStream_t s, int* n)
+cudaError_t launch_q(const InplaceParams& p, int moment, int eq64, cudaStream_t s, cudaStream_t s2, int* n)
 {
     // the all-fluid, source-free lattice keeps its own instantiation (no class or mask look-ups at all)
     const bool extra = p.solid != nullptr || p.src_on;
     if (extra) {
-        if (moment == 0) return eq64 ? launch_t<Q, 0, true, true>(p, s, n) : launch_t<Q, 0, false, true>(p, s, n);
-        return eq64 ? launch_t<Q, 1, true, true>(p, s, n) : launch_t<Q, 1, false, true>(p, s, n);
+        if (moment == 0) return eq64 ? launch_t<Q, 0, true, true>(p, s, s2, n) : launch_t<Q, 0, false, true>(p, s, s2, n);
+        return eq64 ? launch_t<Q, 1, true, true>(p, s, s2, n) : launch_t<Q, 1, false, true>(p, s, s2, n);
     }
-    if (moment == 0) return eq64 ? launch_t<Q, 0, true, false>(p, s, n) : launch_t<Q, 0, false, false>(p, s, n);
-    return eq64 ? launch_t<Q, 1, true, false>(p, s, n) : launch_t<Q, 1, false, false>(p, s, n);
+    if (moment == 0) return eq64 ? launch_t<Q, 0, true, false>(p, s, s2, n) : launch_t<Q, 0, false, false>(p, s, s2, n);
+    return eq64 ? launch_t<Q, 1, true, false>(p, s, s2, n) : launch_t<Q, 1, false, false>(p, s, s2, n);
 }
 
 }  // namespace
 
-cudaError_t launch_inplace_step(const InplaceParams& p, int q, int moment, int eq64, cudaStream_t stream, int* launches)
+cudaError_t launch_inplace_step(const InplaceParams& p, int q, int moment, int eq64, cudaStream_t stream, cudaStream_t side, int* launches)
 {
-    return q == 27 ? launch_q<27>(p, moment, eq64, stream, launches) : launch_q<19>(p, moment, eq64, stream, launches);
+    return q == 27 ? launch_q<27>(p, moment, eq64, stream, side, launches) : launch_q<19>(p, moment, eq64, stream, side, launches);
+}
+
+namespace {
+// before an odd step: what the previous odd step summed ahead of time has been earned by the even step in between
+__global__ void fold_pending_kernel(double* force, double* pending)
+{
+    const int k = threadIdx.x;
+    if (k < 3 * FORCE_SLOTS) {
+        force[k] += pending[k];
+        pending[k] = 0.0;
+    }
+}
+}  // namespace
+
+cudaError_t launch_inplace_fold_pending(double* force, double* pending, cudaStream_t stream)
+{
+    fold_pending_kernel<<<1, 3 * FORCE_SLOTS, 0, stream>>>(force, pending);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_inplace_zero_solid(const InplaceParams& p, int q, cudaStream_t stream)

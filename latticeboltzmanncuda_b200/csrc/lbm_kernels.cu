@@ -185,7 +185,7 @@ __device__ __noinline__ float moving_wall_term(const StepParams& p, int i, int x
     else if (p.bc[1] == 2 && (sy < 0 || sy >= g.ny)) u = p.wall_u[2 + (sy < 0 ? 0 : 1)];
     const float w = (Q == 27) ? (i < 7 ? (float)(2.0 / 27.0) : (i < 19 ? (float)(1.0 / 54.0) : (float)(1.0 / 216.0)))
                               : (i < 7 ? (float)(1.0 / 18.0) : (float)(1.0 / 36.0));
-    return 6.0f * w * ((float)c_dir[i][0] * u[0] + (float)c_dir[i][1] * u[1] + (float)c_dir[i][2] * u[2]);
+    return __fmul_rn(6.0f * w, (float)c_dir[i][0] * u[0] + (float)c_dir[i][1] * u[1] + (float)c_dir[i][2] * u[2]);
 }
 
 // Launch shape of the general and special kernels; the defaults are the values measured best on B200 at 512^3
@@ -772,8 +772,10 @@ __global__ void fill_axis_kernel(const __grid_constant__ FillParams p)
             if (t[0] < 0 || t[0] >= n[0] || t[1] < 0 || t[1] >= n[1] || t[2] < 0 || t[2] >= n[2]) continue;
             const float* u = p.wall_u[side];
             const float cu = (float)dir_c(i, 0) * u[0] + (float)dir_c(i, 1) * u[1] + (float)dir_c(i, 2) * u[2];
+            // (explicitly rounded: on a slab face the same value is formed by moving_wall_term() at pull time, and a product
+            // contracted into the add here would differ from it in the last bit)
             p.f[(long long)i * g.np + gidx] =
-                p.f[(long long)dir_inv(i) * g.np + g.cell(t[0], t[1], t[2])] + 6.0f * (float)dir_weight<Q>(i) * cu;
+                __fadd_rn(p.f[(long long)dir_inv(i) * g.np + g.cell(t[0], t[1], t[2])], __fmul_rn(6.0f * (float)dir_weight<Q>(i), cu));
         }
     }
 }

@@ -337,6 +337,9 @@ class SlabGroup:
             hi = blobs[(r + 1) % self.world] if (self.periodic or r + 1 < self.world) else None
             capi.check(self._lib.lbm_halo_connect(s.handle, lo, hi))
         self._handles = (C.c_void_p * self.world)(*[s.handle for s in self.slabs])
+        for (x0, _), s in zip(self.ranges, self.slabs):
+            capi.check(self._lib.lbm_set_slab_origin(s.handle, x0, gx))
+        self.m_simModel = None
 
     def close(self):
         for s in self.slabs:
@@ -368,6 +371,46 @@ class SlabGroup:
             lo = solid[(x0 - 1) % self.gx] if (self.periodic or x0 > 0) else np.zeros_like(solid[0])
             hi = solid[x1 % self.gx] if (self.periodic or x1 < self.gx) else np.zeros_like(solid[0])
             s.set_solid_mask(np.concatenate([lo[None], solid[x0:x1], hi[None]], axis=0), x_ghost_planes=True)
+
+    def insertModel(self, filename, spacing):
+        """Lattice::insertModel on every slab, in global coordinates (lbm_set_slab_origin): each slab voxelises its own
+        planes and its neighbours' edge planes"""
+        from .model import Model
+        self.m_simModel = Model(filename)
+        self._spacing = float(spacing)
+        ok = True
+        for s in self.slabs:
+            accepted = C.c_int()
+            capi.check(self._lib.lbm_insert_model(s.handle, self.m_simModel.handle, self._spacing, C.byref(accepted)))
+            ok = ok and bool(accepted.value)
+        return ok
+
+    def preProcessModel(self):
+        """Lattice::preProcessModel on every slab: the tables of its own boundary-solid cells and of those in the
+        neighbours' edge planes"""
+        if self.m_simModel is None:
+            return
+        for s in self.slabs:
+            capi.check(self._lib.lbm_preprocess_model(s.handle, self.m_simModel.handle, self._spacing))
+
+    def load_data(self, cells):
+        """the reference's AoS records (144 bytes, host order: x slabs are contiguous runs)"""
+        per = self.gy * self.gz
+        cells = np.ascontiguousarray(cells, dtype=capi.LATTICE_POINT)
+        for (x0, x1), s in zip(self.ranges, self.slabs):
+            s.load_data(cells[x0 * per:x1 * per])
+        solid = cells["is_internal"].reshape(self.gx, self.gy, self.gz)
+        if solid.any():
+            self.set_solid_mask(solid)          # load_data alone knows nothing of the neighbours' edge planes
+
+    def retrieve_data(self):
+        self.sync()
+        parts = []
+        for (x0, _), s in zip(self.ranges, self.slabs):
+            p = s.retrieve_data()
+            p["x"] += x0
+            parts.append(p)
+        return np.concatenate(parts)
 
     def set_source_global(self, lo, hi, flow):
         gl = 0 if lo[0] is None else lo[0]

@@ -117,6 +117,64 @@ def run_case(name, devices):
         grp.close()
 
 
+def run_reference_mode_case(world, devices, n=16, steps=12, fused=True):
+    """The reference's own mode (D3Q27, table reflection, fp64 equilibrium, SPLIT moments, zero-inflow edges, plane source,
+    force) on slabs: geometry and tables built per slab in global coordinates, a body that crosses the cuts.  Against one
+    handle on the whole lattice (bit for bit) and the oracle's CLI loop."""
+    import os
+    obj = os.path.join(O.GOLDEN_DIR, "obj", "cube_angled.obj")
+    spacing = float(np.float32(1.0 / n))
+    flow = np.full(27, 0.001, np.float32)
+    flow[6] = 0.002
+    start = O.new_cells(n, n, n)
+    start["f"] = flow[None, :]
+    one = lb.Lattice(n, n, n, None, None, lb.FluidData(1.0, 0.9), spacing)
+    grp = SlabGroup(n, n, n, lb.FluidData(1.0, 0.9), devices(world), bc_x=Z0, bc_yz=(Z0, Z0))
+    try:
+        one.load_data(start)
+        grp.load_data(start)
+        assert one.insertModel(obj) and grp.insertModel(obj, spacing)
+        assert np.array_equal(np.concatenate([s.get_solid_mask() for s in grp.slabs], axis=0), one.get_solid_mask())
+        one.preProcessModel()
+        grp.preProcessModel()
+        t1, k1 = one.reflection_tables()
+        per = n * n
+        tg = [s.reflection_tables() for s in grp.slabs]
+        kg = np.concatenate([k + x0 * per for (t, k), (x0, _) in zip(tg, grp.ranges)])
+        assert np.array_equal(kg, k1)                                   # the same boundary-solid cells, each owned by one slab
+        assert np.array_equal(np.concatenate([t for t, _ in tg])["w"], t1["w"])
+        one.setFlowData(lb.FlowData(lb.FlowCriterion.ptestPlaneCriteria, flow))
+        grp.set_source_global((0, None, None), (0, None, None), flow)
+        one.setReflectionData(lb.ReflectionData())
+        grp.enable_force()
+        if fused:
+            one.step(steps)
+            grp.step(steps)
+        else:
+            for _ in range(steps):
+                for ph in (lb.PHASE_STREAM, lb.PHASE_REFLECT, lb.PHASE_COLLIDE, lb.PHASE_SOURCE):
+                    one.step(1, ph)
+                    grp.step(1, ph)
+        a, b = one.retrieve_data(), grp.retrieve_data()
+        assert np.array_equal(a["f"], b["f"])
+        assert np.array_equal(a["is_internal"], b["is_internal"]) and np.array_equal(a["is_reflected"], b["is_reflected"])
+        assert np.array_equal(a["x"], b["x"])
+        assert np.allclose(grp.force(), one.force_f64(), rtol=1e-9, atol=1e-12)
+        cells = O.new_cells(n, n, n)
+        cells["f"] = flow[None, :]
+        mesh = O.Mesh(obj)
+        assert mesh.insert(cells, n, n, n, np.float32(spacing)) == 1
+        tables, tindex = mesh.preprocess(cells, n, n, n, np.float32(spacing))
+        force = np.zeros(3, np.float32)
+        want = O.step_cli(cells, n, n, n, 0.9, tables, tindex, force, O.SRC_PLANE_X0, flow, steps=steps)
+        err = float(np.abs(b["f"].astype(np.float64) - want["f"]).max() / np.abs(want["f"]).max())
+        assert err <= 1e-5
+        assert np.allclose(grp.force(), force, rtol=2e-4, atol=1e-7)
+    finally:
+        one.close()
+        grp.close()
+
+
 def check_refusals():
     import ctypes as C
     lib = capi.load()

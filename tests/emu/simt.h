@@ -47,6 +47,8 @@ inline void __syncthreads() { simt::block_barrier(); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __ldcs(const T* p) { return *p; }
 template <class T> inline void __stcs(T* p, T v) { *p = v; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
 inline void __threadfence_system() {}
 inline void __threadfence() {}
 inline int __popc(unsigned v) { return __builtin_popcount(v); }

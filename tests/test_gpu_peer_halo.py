@@ -37,6 +37,11 @@ def test_slab_group_equals_single_domain(name):
     cases.run_case(name, devices=_devices)
 
 
+@pytest.mark.parametrize("world,fused", [(2, True), (3, True), (4, False)])
+def test_reference_mode_on_slabs(world, fused):
+    cases.run_reference_mode_case(world, devices=_devices, steps=12 if fused else 5, fused=fused)
+
+
 def test_connect_refuses_mismatched_slabs():
     cases.check_refusals()
 

@@ -21,5 +21,10 @@ def test_slab_group_equals_single_domain(lib, name):
     cases.run_case(name, devices=lambda world: [0] * world)
 
 
+@pytest.mark.parametrize("world,fused", [(2, True), (3, True), (4, False)])
+def test_reference_mode_on_slabs(lib, world, fused):
+    cases.run_reference_mode_case(world, devices=lambda w: [0] * w, steps=8 if fused else 4, fused=fused)
+
+
 def test_connect_refuses_mismatched_slabs(lib):
     cases.check_refusals()
