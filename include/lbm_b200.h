@@ -167,6 +167,11 @@ LBM_API int lbm_set_slab_origin(lbm_handle h, int x0, int gx);
  * FlowCriterion::testCriteria is the box (1,1,1)-(1,1,1); testPlaneCriteria is x in [0,0]. */
 LBM_API int lbm_set_source(lbm_handle h, int kind, const int32_t lo[3], const int32_t hi[3], const float f[27]);
 
+/* the same for ANY criterion (FlowSurface.h:12 takes an arbitrary device predicate, SimCalcFuncs.cu:206 calls it per cell
+ * per step): the caller evaluates it once and hands over one byte per cell in host order, non-zero = the cell takes the
+ * source.  Kept on the device as one bit per cell; the kernels look at it only inside the box around the selected cells. */
+LBM_API int lbm_set_source_mask(lbm_handle h, const uint8_t *cells, const float f[27]);
+
 /* Lattice::setReflectionData / retrieve_reflection_data (Lattice.cpp:61-71,438-443) */
 LBM_API int lbm_set_force_accumulator(lbm_handle h, int enable, const float init[3]);
 LBM_API int lbm_set_force_accumulator_f64(lbm_handle h, int enable, const double init[3]);
@@ -266,6 +271,12 @@ LBM_API int lbm_halo_disconnect(lbm_handle h);
 LBM_API int lbm_halo_timeouts(lbm_handle h, unsigned long long *count);
 /* n steps of all slabs held by ONE process, in lockstep (every slab's "ready" signal is queued before any slab waits) */
 LBM_API int lbm_group_step(lbm_handle *slabs, int count, int n, unsigned phases);
+
+/* lbm_collide_tau / lbm_reflect_accumulate for all slabs of one process (the sum over the slabs is added to xyz) */
+LBM_API int lbm_group_collide_tau(lbm_handle *slabs, int count, float timescale);
+LBM_API int lbm_group_reflect_accumulate(lbm_handle *slabs, int count, float *xyz);
+/* number of CUDA devices this process sees */
+LBM_API int lbm_device_count(int *count);
 
 /* layout facts for tools: padded dims and strides in floats */
 typedef struct lbm_layout {

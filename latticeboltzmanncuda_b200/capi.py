@@ -86,6 +86,7 @@ SYMBOLS = [
     ("lbm_set_reflection_table_slab", _i, [_vp, _vp, _vp, _i]),
     ("lbm_set_slab_origin", _i, [_vp, _i, _i]),
     ("lbm_set_source", _i, [_vp, _i, _vp, _vp, _vp]),
+    ("lbm_set_source_mask", _i, [_vp, _vp, _vp]),
     ("lbm_set_force_accumulator", _i, [_vp, _i, _vp]),
     ("lbm_set_force_accumulator_f64", _i, [_vp, _i, _vp]),
     ("lbm_get_force", _i, [_vp, _vp]),
@@ -120,6 +121,9 @@ SYMBOLS = [
     ("lbm_halo_disconnect", _i, [_vp]),
     ("lbm_halo_timeouts", _i, [_vp, C.POINTER(C.c_ulonglong)]),
     ("lbm_group_step", _i, [C.POINTER(_vp), _i, _i, _u]),
+    ("lbm_group_collide_tau", _i, [C.POINTER(_vp), _i, C.c_float]),
+    ("lbm_group_reflect_accumulate", _i, [C.POINTER(_vp), _i, _vp]),
+    ("lbm_device_count", _i, [C.POINTER(_i)]),
     ("lbm_get_layout", _i, [_vp, C.POINTER(Layout)]),
     ("lbm_get_stats", _i, [_vp, C.POINTER(Stats)]),
     ("lbm_mesh_load", _i, [C.c_char_p, C.POINTER(_vp)]),

@@ -155,6 +155,39 @@ int rebuild_special(lbm_handle h)
         h->cellinfo_cap = n;
     }
     CK(launch_fill_cellinfo(solid, tmask, h->special_list, (long long)n, h->cellinfo, g, h->stream));
+    {
+        // single-buffer engine with obstacles: the list of blocks (4 z-words of a row) that hold a live word
+        cudaFree(h->live_blocks);
+        h->live_blocks = nullptr;
+        h->n_live = 0;
+        h->live_start.clear();
+        static const bool use_list = [] { const char* e = getenv("LBM_AA_LIVE_LIST"); return e ? atoi(e) != 0 : true; }();
+        const int nbw = (wcount + 3) / 4;
+        if (use_list && h->inplace && solid && g.nz >= 97 && g.nx <= 4096 && g.ny <= 4096 && nbw <= 256) {
+            std::vector<uint8_t> cls(h->cls_bytes);
+            CK(cudaMemcpyAsync(cls.data(), h->cls, h->cls_bytes, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            std::vector<uint32_t> live;
+            h->live_start.assign((size_t)g.nx + 1, 0u);
+            for (int x = 0; x < g.nx; ++x) {
+                h->live_start[x] = (uint32_t)live.size();
+                for (int y = 0; y < g.ny; ++y)
+                    for (int bw = 0; bw < nbw; ++bw) {
+                        bool any = false;
+                        for (int w = bw * 4; w < bw * 4 + 4 && w < wcount; ++w)
+                            if (cls[((size_t)x * wcount + w) * h->cls_pitch + y] != 1) any = true;      // 1 = all cells solid
+                        if (any) live.push_back(((uint32_t)x << 20) | ((uint32_t)y << 8) | (uint32_t)bw);
+                    }
+            }
+            h->live_start[g.nx] = (uint32_t)live.size();
+            h->n_live = live.size();
+            if (!live.empty()) {
+                CK(cudaMalloc(&h->live_blocks, live.size() * sizeof(uint32_t)));
+                CK(cudaMemcpyAsync(h->live_blocks, live.data(), live.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+            }
+        }
+    }
     pin_tables_in_l2(h);
     h->dead_dirty = 2;
     return LBM_OK;
@@ -218,6 +251,7 @@ void fill_params(lbm_handle h, StepParams& p, unsigned phases, int x0, int x1)
         for (int a = 0; a < 3; ++a)
             if (h->cfg.wall_u[k][a] != 0.0f) p.wall_moving = 1;
     std::memcpy(p.src_f, h->src_f, sizeof p.src_f);
+    p.src_mask = h->src_masked ? h->src_mask : nullptr;
     for (int i = 0; i < 27; ++i) {
         p.pop_off[i] = (long long)i * h->g.np;
         p.pull_off[i] = p.pop_off[i] - ((long long)dir_c(i, 0) * h->g.plane + (long long)(dir_c(i, 1) * h->g.zp + dir_c(i, 2)));
@@ -323,6 +357,7 @@ void fill_inplace(lbm_handle h, InplaceParams& ip)
     ip.src_on = h->src_on;
     for (int a = 0; a < 3; ++a) { ip.src_lo[a] = h->src_lo[a]; ip.src_hi[a] = h->src_hi[a]; }
     std::memcpy(ip.src_f, h->src_f, sizeof ip.src_f);
+    ip.src_mask = h->src_masked ? h->src_mask : nullptr;
 }
 
 int inplace_only(lbm_handle h, const char* what)
@@ -351,6 +386,11 @@ int inplace_range(lbm_handle h, unsigned phases, int xa, int xb, cudaStream_t s)
     if (ip.n_special && (int)h->special_start.size() == h->g.nx + 1) {
         ip.special_k0 = h->special_start[xa];
         ip.n_special = (long long)h->special_start[xb] - (long long)h->special_start[xa];
+    }
+    if (h->live_blocks && h->any_solid && (int)h->live_start.size() == h->g.nx + 1) {
+        ip.live_blocks = h->live_blocks;
+        ip.live_k0 = h->live_start[xa];
+        ip.n_live = (long long)h->live_start[xb] - (long long)h->live_start[xa];
     }
     // on the handle's main stream the face and special-word kernels of an odd step run next to the interior launch (on
     // the high-priority side stream): they touch disjoint slots, and the tail of one launch overlaps the other
@@ -592,6 +632,8 @@ LBM_API int lbm_destroy(lbm_handle h)
     cudaFree(h->solid); cudaFree(h->cls); cudaFree(h->cellinfo); cudaFree(h->special_list); cudaFree(h->solid_bytes); cudaFree(h->tmask); cudaFree(h->tprefix); cudaFree(h->toff);
     cudaFree(h->reflected); cudaFree(h->links); cudaFree(h->force); cudaFree(h->diag); cudaFree(h->flag);
     cudaFree(h->link_rank); cudaFree(h->force_moved); cudaFree(h->force_coef); cudaFree(h->force32);
+    cudaFree(h->live_blocks);
+    cudaFree(h->src_mask);
     cudaFree(h->staging);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -980,9 +1022,42 @@ LBM_API int lbm_set_slab_origin(lbm_handle h, int x0, int gx)
 LBM_API int lbm_set_source(lbm_handle h, int kind, const int32_t lo[3], const int32_t hi[3], const float f[27])
 {
     if (!h) return fail(LBM_ERR_INVALID, "null handle");
-    if (kind == LBM_SOURCE_NONE) { h->src_on = 0; return LBM_OK; }
+    if (kind == LBM_SOURCE_NONE) { h->src_on = 0; h->src_masked = false; return LBM_OK; }
     if (kind != LBM_SOURCE_BOX || !lo || !hi || !f) return fail(LBM_ERR_INVALID, "bad source arguments");
     h->src_on = 1;
+    h->src_masked = false;
+    for (int a = 0; a < 3; ++a) { h->src_lo[a] = lo[a]; h->src_hi[a] = hi[a]; }
+    for (int i = 0; i < 27; ++i) h->src_f[i] = (i < h->cfg.q) ? f[i] : 0.0f;
+    return LBM_OK;
+}
+
+LBM_API int lbm_set_source_mask(lbm_handle h, const uint8_t* cells, const float f[27])
+{
+    int rc = use(h);
+    if (rc) return rc;
+    if (!cells || !f) return fail(LBM_ERR_INVALID, "bad source arguments");
+    const Geom& g = h->g;
+    const size_t per = (size_t)g.ny * g.nz, n = per * (size_t)g.nx;
+    // the box around the selected cells keeps every launch that cannot contain one on the lean kernel variant
+    int lo[3] = {g.nx, g.ny, g.nz}, hi[3] = {-1, -1, -1};
+    for (int x = 0; x < g.nx; ++x)
+        for (int y = 0; y < g.ny; ++y) {
+            const uint8_t* row = cells + (size_t)x * per + (size_t)y * g.nz;
+            for (int z = 0; z < g.nz; ++z)
+                if (row[z]) {
+                    const int c[3] = {x, y, z};
+                    for (int a = 0; a < 3; ++a) { if (c[a] < lo[a]) lo[a] = c[a]; if (c[a] > hi[a]) hi[a] = c[a]; }
+                }
+        }
+    if (hi[0] < 0) { h->src_on = 0; h->src_masked = false; return LBM_OK; }      // the predicate selects nothing
+    if (!h->solid_bytes) CK(cudaMalloc(&h->solid_bytes, n + 2 * per));
+    if (!h->src_mask) CK(cudaMalloc(&h->src_mask, h->mask_words() * sizeof(uint32_t)));
+    CK(cudaMemcpyAsync(h->solid_bytes, cells, n, cudaMemcpyHostToDevice, h->stream));
+    const int open_edges[3] = {LBM_BC_ZERO_INFLOW, LBM_BC_ZERO_INFLOW, LBM_BC_ZERO_INFLOW};      // no images in the ghost cells
+    CK(launch_build_mask(h->solid_bytes, 0, h->src_mask, g, open_edges, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->src_on = 1;
+    h->src_masked = true;
     for (int a = 0; a < 3; ++a) { h->src_lo[a] = lo[a]; h->src_hi[a] = hi[a]; }
     for (int i = 0; i < 27; ++i) h->src_f[i] = (i < h->cfg.q) ? f[i] : 0.0f;
     return LBM_OK;
@@ -1069,70 +1144,82 @@ LBM_API int lbm_source(lbm_handle h) { return lbm_step_phases(h, 1, LBM_PHASE_SO
 
 LBM_API int lbm_collide_tau(lbm_handle h, float timescale)
 {
-    int rc = use(h);
-    if (rc) return rc;
-    if (!(timescale > 0.0f)) return fail(LBM_ERR_INVALID, "the timescale must be positive");
-    const float keep = h->cfg.tau;
-    h->cfg.tau = timescale;
-    rc = lbm_step_phases(h, 1, LBM_PHASE_COLLIDE);
-    h->cfg.tau = keep;
-    return rc;
+    return lbm_group_collide_tau(&h, 1, timescale);
 }
-
-namespace {
-// xyz[a] += (sum of the partial force sums now) - (the sum before the phase)
-__global__ void add_force_delta_kernel(const double* now, const double* before, float* xyz)
-{
-    const int a = threadIdx.x;
-    if (a >= 3) return;
-    double t = 0.0;
-    for (int k = 0; k < FORCE_SLOTS; ++k) t += now[3 * k + a] - before[3 * k + a];
-    xyz[a] += (float)t;
-}
-}  // namespace
 
 LBM_API int lbm_reflect_accumulate(lbm_handle h, float* xyz)
 {
-    int rc = use(h);
-    if (rc) return rc;
-    if (!xyz) return lbm_reflect(h);
-    if (h->force32) return fail(LBM_ERR_UNSUPPORTED, "lbm_reflect_accumulate: not with LBM_FORCE_ACCUM_REFERENCE_FP32 (use the handle's accumulator)");
-    const size_t bytes = 3 * FORCE_SLOTS * sizeof(double);
-    double* before = nullptr;
-    CK(cudaMalloc(&before, bytes));
-    CK(cudaMemcpyAsync(before, h->force, bytes, cudaMemcpyDeviceToDevice, h->stream));
-    const bool was_on = h->force_on;
-    h->force_on = true;
-    rc = lbm_step_phases(h, 1, LBM_PHASE_REFLECT);
-    h->force_on = was_on;
-    if (rc) { cudaFree(before); return rc; }
-    cudaPointerAttributes attr;
-    const bool on_device = cudaPointerGetAttributes(&attr, xyz) == cudaSuccess &&
-                           (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
-    cudaGetLastError();
-    if (on_device) {
-        add_force_delta_kernel<<<1, 32, 0, h->stream>>>(h->force, before, xyz);
-        rc = cudaGetLastError() == cudaSuccess ? LBM_OK : fail(LBM_ERR_CUDA, "lbm_reflect_accumulate: launch failed");
-    } else {
-        std::vector<double> a(3 * FORCE_SLOTS), b(3 * FORCE_SLOTS);
-        cudaError_t e = cudaMemcpyAsync(a.data(), h->force, bytes, cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(b.data(), before, bytes, cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-        if (e != cudaSuccess) rc = fail(LBM_ERR_CUDA, "lbm_reflect_accumulate: %s", cudaGetErrorString(e));
-        else
-            for (int c = 0; c < 3; ++c) {
-                double t = 0.0;
-                for (int k = 0; k < FORCE_SLOTS; ++k) t += a[3 * k + c] - b[3 * k + c];
-                xyz[c] += (float)t;
-            }
+    return lbm_group_reflect_accumulate(&h, 1, xyz);
+}
+
+// one reflect phase on every slab of a group (or on one handle) whose force is added to the caller's three floats
+LBM_API int lbm_group_reflect_accumulate(lbm_handle* slabs, int count, float* xyz)
+{
+    if (!slabs || count < 1) return fail(LBM_ERR_INVALID, "bad arguments");
+    for (int k = 0; k < count; ++k) {
+        if (!slabs[k]) return fail(LBM_ERR_INVALID, "null handle");
+        if (slabs[k]->force32) return fail(LBM_ERR_UNSUPPORTED, "lbm_reflect_accumulate: not with LBM_FORCE_ACCUM_REFERENCE_FP32 (use the handle's accumulator)");
     }
-    if (!was_on && rc == LBM_OK) {
-        // the handle's own accumulator is off: it keeps what it held
-        if (cudaMemcpyAsync(h->force, before, bytes, cudaMemcpyDeviceToDevice, h->stream) != cudaSuccess) rc = fail(LBM_ERR_CUDA, "lbm_reflect_accumulate: restore failed");
+    auto step = [&]() { return count == 1 ? lbm_step_phases(slabs[0], 1, LBM_PHASE_REFLECT) : lbm_group_step(slabs, count, 1, LBM_PHASE_REFLECT); };
+    if (!xyz) return step();
+    const size_t words = 2 * 3 * FORCE_SLOTS;
+    std::vector<std::vector<double>> before(count, std::vector<double>(words)), after(count, std::vector<double>(words));
+    std::vector<char> was_on(count);
+    int rc = LBM_OK;
+    for (int k = 0; k < count && rc == LBM_OK; ++k) {
+        lbm_handle h = slabs[k];
+        if ((rc = use(h))) break;
+        CK(cudaMemcpyAsync(before[k].data(), h->force, words * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        was_on[k] = h->force_on;
+        h->force_on = true;
     }
-    cudaStreamSynchronize(h->stream);
-    cudaFree(before);
+    if (rc == LBM_OK) rc = step();
+    double add[3] = {0.0, 0.0, 0.0};
+    for (int k = 0; k < count; ++k) {
+        lbm_handle h = slabs[k];
+        h->force_on = was_on[k] != 0;
+        if (rc != LBM_OK) continue;
+        if ((rc = use(h))) continue;
+        if (h->halo.edge) CK(cudaStreamSynchronize(h->halo.edge));
+        CK(cudaMemcpyAsync(after[k].data(), h->force, words * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int a = 0; a < 3; ++a)
+            for (int s = 0; s < FORCE_SLOTS; ++s) add[a] += after[k][3 * s + a] - before[k][3 * s + a];
+        if (!was_on[k])      // the handle's own accumulator is off: it keeps what it held
+            CK(cudaMemcpyAsync(h->force, before[k].data(), words * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (rc != LBM_OK) return rc;
+    // the caller's triple may live in device memory (the reference's d_reflectionData) or in host memory
+    float cur[3];
+    CK(cudaMemcpy(cur, xyz, sizeof cur, cudaMemcpyDefault));
+    for (int a = 0; a < 3; ++a) cur[a] += (float)add[a];
+    CK(cudaMemcpy(xyz, cur, sizeof cur, cudaMemcpyDefault));
+    return LBM_OK;
+}
+
+LBM_API int lbm_group_collide_tau(lbm_handle* slabs, int count, float timescale)
+{
+    if (!slabs || count < 1) return fail(LBM_ERR_INVALID, "bad arguments");
+    if (!(timescale > 0.0f)) return fail(LBM_ERR_INVALID, "the timescale must be positive");
+    std::vector<float> keep(count);
+    for (int k = 0; k < count; ++k) {
+        if (!slabs[k]) return fail(LBM_ERR_INVALID, "null handle");
+        keep[k] = slabs[k]->cfg.tau;
+        slabs[k]->cfg.tau = timescale;
+    }
+    const int rc = count == 1 ? lbm_step_phases(slabs[0], 1, LBM_PHASE_COLLIDE) : lbm_group_step(slabs, count, 1, LBM_PHASE_COLLIDE);
+    for (int k = 0; k < count; ++k) slabs[k]->cfg.tau = keep[k];
     return rc;
+}
+
+LBM_API int lbm_device_count(int* count)
+{
+    if (!count) return fail(LBM_ERR_INVALID, "null argument");
+    *count = 0;
+    CK(cudaGetDeviceCount(count));
+    return LBM_OK;
 }
 
 LBM_API int lbm_step_timed(lbm_handle h, int n, unsigned phases, float* ms, int* launches)

@@ -105,8 +105,7 @@ __device__ __forceinline__ bool solid_bit(const InplaceParams& p, int xpad, int 
 template <int Q>
 __device__ __forceinline__ void add_source(const InplaceParams& p, float (&f)[Q], int x, int y, int z)
 {
-    if (x >= p.src_lo[0] && x <= p.src_hi[0] && y >= p.src_lo[1] && y <= p.src_hi[1] &&
-        z >= p.src_lo[2] && z <= p.src_hi[2]) {
+    if (source_hit(p, x, y, z)) {
 #pragma unroll
         for (int i = 0; i < Q; ++i) f[i] += p.src_f[i];
     }
@@ -119,9 +118,16 @@ template <int Q, int MOMENT, bool EQ64, bool EXTRA>
 __global__ void __launch_bounds__(256, (Q == 19 && !EQ64) ? 6 : 4) aa_even_kernel(const __grid_constant__ InplaceParams p)
 {
     const Geom& g = p.g;
-    const int z = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int x = p.x0 + blockIdx.z;                 // the launch covers the planes [x0, x1)
+    int x, y, z;
+    if (EXTRA && p.live_blocks) {                    // one block per entry of the live-block list (128 threads = 4 z-words of a row)
+        const uint32_t id = __ldg(p.live_blocks + p.live_k0 + blockIdx.x);
+        x = (int)(id >> 20); y = (int)((id >> 8) & 0xfffu);
+        z = (int)(id & 0xffu) * 128 + (int)threadIdx.x;
+    } else {
+        z = blockIdx.x * blockDim.x + threadIdx.x;
+        y = blockIdx.y * blockDim.y + threadIdx.y;
+        x = p.x0 + blockIdx.z;                       // the launch covers the planes [x0, x1)
+    }
     if (z >= g.nz || y >= g.ny) return;
     if (EXTRA && p.solid) {
         // a warp is 32 consecutive z of one row = one 32-cell word (blockDim.x is a multiple of 32)
@@ -241,10 +247,17 @@ __global__ void __launch_bounds__(128, (MODE == 0 && Q == 19 && !EQ64) ? (EXTRA 
     // (MODE 0 and 3 are launched with [x0, x1) already clipped to the interior planes 1..nx-2, see launch_t)
     int x, y, w;
     if constexpr (MODE == 0) {
-        w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        if (w >= wcount) return;
-        y = 1 + blockIdx.y;
-        x = p.x0 + blockIdx.z;
+        if (EXTRA && p.live_blocks) {                // one block per entry of the live-block list; the faces have their own launches
+            const uint32_t id = __ldg(p.live_blocks + p.live_k0 + blockIdx.x);
+            x = (int)(id >> 20); y = (int)((id >> 8) & 0xfffu);
+            w = (int)(id & 0xffu) * 4 + (int)(threadIdx.x >> 5);
+            if (x == 0 || x == g.nx - 1 || y == 0 || y == g.ny - 1 || w >= wcount) return;
+        } else {
+            w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+            if (w >= wcount) return;
+            y = 1 + blockIdx.y;
+            x = p.x0 + blockIdx.z;
+        }
     } else if constexpr (MODE == 2) {
         // face planes of the range: plane 0 if x0 == 0, plane nx-1 if x1 == nx (one plane when nx == 1)
         const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -612,9 +625,13 @@ cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, cudaStream_t s
             InplaceParams pi = p;          // the interior planes of the range
             pi.x0 = xi0; pi.x1 = xi1;
             if (g.ny > 2) {
-                dim3 grid((wcount + 3) / 4, g.ny - 2, xi1 - xi0);
-                aa_odd_kernel<Q, MOMENT, EQ64, 0, EXTRA><<<grid, 128, 0, stream>>>(pi);
-                ++n;
+                if (EXTRA && p.live_blocks) {
+                    if (p.n_live > 0) { aa_odd_kernel<Q, MOMENT, EQ64, 0, EXTRA><<<(unsigned)p.n_live, 128, 0, stream>>>(p); ++n; }
+                } else {
+                    dim3 grid((wcount + 3) / 4, g.ny - 2, xi1 - xi0);
+                    aa_odd_kernel<Q, MOMENT, EQ64, 0, EXTRA><<<grid, 128, 0, stream>>>(pi);
+                    ++n;
+                }
             }
             const long long warps = (long long)(xi1 - xi0) * (g.ny < 2 ? g.ny : 2) * wcount;
             aa_odd_kernel<Q, MOMENT, EQ64, 3, EXTRA><<<(unsigned)((warps + 3) / 4), 128, 0, side>>>(pi);
@@ -637,8 +654,12 @@ cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, cudaStream_t s
         int by = 128 / bz;
         if (by > g.ny) by = g.ny;
         dim3 block(bz, by, 1), grid((g.nz + bz - 1) / bz, (g.ny + by - 1) / by, p.x1 - p.x0);
-        aa_even_kernel<Q, MOMENT, EQ64, EXTRA><<<grid, block, 0, stream>>>(p);
-        ++n;
+        if (EXTRA && p.live_blocks) {
+            if (p.n_live > 0) { aa_even_kernel<Q, MOMENT, EQ64, EXTRA><<<(unsigned)p.n_live, 128, 0, stream>>>(p); ++n; }
+        } else {
+            aa_even_kernel<Q, MOMENT, EQ64, EXTRA><<<grid, block, 0, stream>>>(p);
+            ++n;
+        }
         if (EXTRA && p.cls && p.force && !p.force_pending && p.n_special > 0) {
             aa_even_special_kernel<Q, MOMENT, EQ64><<<special_blocks, 128, 0, side>>>(p);
             ++n;

@@ -51,6 +51,9 @@ struct lbm_lattice_s {
     uint32_t* special_list = nullptr;   // mask-word indices of the special words
     size_t n_special = 0;
     std::vector<uint32_t> special_start;   // [nx + 1]: first list entry of every interior plane (host side)
+    uint32_t* live_blocks = nullptr;       // single-buffer engine: packed ids of the blocks with a live word (InplaceParams)
+    size_t n_live = 0;
+    std::vector<uint32_t> live_start;      // [nx + 1]: first entry of every plane
     bool any_solid = false;          // some bit set (geometry or wall ghosts)
     uint8_t* solid_bytes = nullptr;  // nx*ny*nz (+2 planes) scratch
     uint32_t *tmask = nullptr, *tprefix = nullptr, *toff = nullptr, *reflected = nullptr;
@@ -68,6 +71,8 @@ struct lbm_lattice_s {
     int src_on = 0;
     int src_lo[3] = {0, 0, 0}, src_hi[3] = {0, 0, 0};
     float src_f[27] = {0};
+    uint32_t* src_mask = nullptr;    // lbm_set_source_mask: the cells of the source box that take the source (padded bit mask)
+    bool src_masked = false;
     double* diag = nullptr;          // 4 doubles
     unsigned* flag = nullptr;
     void* staging = nullptr;

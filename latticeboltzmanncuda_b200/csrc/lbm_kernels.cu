@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(32 * LBM_GEN_WARPS, LBM_GEN_MINB) step_general
         // ---- additive source on the selected cells (SimCalcFuncs.cu:200-215); bounce-back solids take none
         // (SRC is set for the launches that cover the planes the source box intersects, see launch_step_general_r)
         if (SRC && (p.phases & PH_SOURCE) && p.src_on && !(dead && p.boundary_mode == 1)) {
-            if (x >= p.src_lo[0] && x <= p.src_hi[0] && y >= p.src_lo[1] && y <= p.src_hi[1] && z >= p.src_lo[2] && z <= p.src_hi[2]) {
+            if (source_hit(p, x, y, z)) {
 #pragma unroll
                 for (int i = 0; i < Q; ++i) f[i] += p.src_f[i];
             }
@@ -589,8 +589,7 @@ __global__ void __launch_bounds__(128, LBM_SPC_MINB) step_special_kernel(const _
         else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
     }
     if ((p.phases & PH_SOURCE) && p.src_on && !(dead && p.boundary_mode == 1)) {
-        if (x >= p.src_lo[0] && x <= p.src_hi[0] && y >= p.src_lo[1] && y <= p.src_hi[1] &&
-            z >= p.src_lo[2] && z <= p.src_hi[2]) {
+        if (source_hit(p, x, y, z)) {
 #pragma unroll
             for (int i = 0; i < Q; ++i) f[i] += p.src_f[i];
         }

@@ -275,6 +275,123 @@ int main(int argc, char** argv)
         delete[] out[0]; delete[] out[1];
     }
 
+    printf("RunCudaFunctions honour their arguments: timescale of the call, ReflectionData of the call, a criterion that is no box\n");
+    {
+        // SimCalcFuncs.cu:225-228: the kernel divides by the timescale it is GIVEN (the FluidData's is 1.0 here)
+        dim3 threads(1, 1, 1), blocks(1, 1, 1);
+        Lattice lat(1, 1, 1, blocks, threads, fluid, 0.1);
+        LatticeData data(lat.getCudaDataPointer(), lat.getDimensions());
+        LatticePoint* a = zeroed(1);
+        a[0].particle_distribution[0] = 2.0;
+        lat.load_data(a);
+        RunCudaFunctions::run_calculate_collision(blocks, threads, data, 2.0f);
+        LatticePoint* r = lat.retrieve_data();
+        EXPECT_NEAR(r[0].particle_distribution[0], 2.0 + (0.592592593 - 2.0) / 2.0, 1e-6);       // half way to TestCollision's answer
+        EXPECT_NEAR(r[0].particle_distribution[1], 0.148148148 / 2.0, 1e-6);
+        delete[] a; delete[] r;
+    }
+    {
+        // TestReflectionsData's lattice, but the accumulator is the CALLER's (Lattice::setReflectionData never called),
+        // and a phase queued by the Lattice before the direct call must run first
+        dim3 threads(3, 3, 3), blocks(1, 1, 1);
+        Lattice lat(3, 3, 3, blocks, threads, fluid, 0.5);
+        LatticeData data(lat.getCudaDataPointer(), lat.getDimensions());
+        LatticePoint* a = zeroed(27);
+        lat.load_data(a);
+        lat.insertModel(dir + "/cube_angled.obj");
+        lat.preProcessModel();
+        LatticePoint* b = lat.retrieve_data();
+        b[13].particle_distribution[1] = 1.0;
+        lat.load_data(b);
+        lat.insertModel(dir + "/cube_angled.obj");
+        lat.preProcessModel();
+        ReflectionData mine;
+        mine.x = 10.0f;
+        RunCudaFunctions::run_calculate_reflections_data(blocks, threads, data, data, &mine);
+        EXPECT_NEAR(mine.x, 10.0 + 0.28086, 1e-5);
+        EXPECT_NEAR(mine.y, -0.194318, 1e-5);
+        EXPECT_NEAR(mine.z, 0.648261, 1e-5);
+        LatticePoint* r = lat.retrieve_data();
+        EXPECT_NEAR(r[2 * 9 + 1 * 3 + 2].particle_distribution[17], 0.367402, 1e-5);
+        delete[] a; delete[] b; delete[] r;
+    }
+    {
+        struct Pattern { static bool hit(int x, int y, int z) { return (x + 2 * y + 3 * z) % 5 == 0 && x >= 1; } };
+        dim3 threads(4, 4, 4), blocks(1, 1, 1);
+        Lattice lat(4, 4, 4, blocks, threads, fluid, 0.1);
+        LatticePoint* a = zeroed(64);
+        lat.load_data(a);
+        LatticePoint flowRef;
+        std::memset((void*)&flowRef, 0, sizeof flowRef);
+        flowRef.particle_distribution[0] = 1.0;
+        static bool (*ppattern)(int, int, int) = &Pattern::hit;      // (FlowData takes the address of a function-pointer symbol)
+        FlowData* flow = new FlowData(&ppattern, flowRef);
+        lat.setFlowData(flow);
+        lat.simulateFlow();
+        LatticePoint* r = lat.retrieve_data();
+        int wrong = 0;
+        for (int x = 0; x < 4; ++x) for (int y = 0; y < 4; ++y) for (int z = 0; z < 4; ++z)
+            if (r[z + 4 * y + 16 * x].particle_distribution[0] != (Pattern::hit(x, y, z) ? 1.0f : 0.0f)) ++wrong;
+        EXPECT_EQ(wrong, 0);
+        EXPECT_TRUE(lat.lastError().empty());
+        delete[] a; delete[] r; delete flow;
+    }
+
+    printf("A Lattice cut into x slabs (one per device, peer-memory halos) equals the Lattice on one GPU\n");
+    {
+        dim3 threads(8, 8, 8), blocks(2, 2, 2);
+        LatticePoint flowRef;
+        std::memset((void*)&flowRef, 0, sizeof flowRef);
+        for (int i = 0; i < 27; ++i) flowRef.particle_distribution[i] = 0.001;
+        flowRef.particle_distribution[6] = 0.002;
+        float force[3][3];
+        LatticePoint* out[3];
+        const int gpus[3] = {1, 2, 3};
+        for (int mode = 0; mode < 3; ++mode) {
+            Lattice::Options o;                       // the reference's behaviour ...
+            o.gpus = gpus[mode];                      // ... on that many slabs (devices are reused when the box has fewer)
+            Lattice lat(16, 16, 16, blocks, threads, FluidData(1.0, 0.8), 1.0f / 16, o);
+            EXPECT_EQ(lat.deviceCount(), gpus[mode]);
+            LatticeData data(lat.getCudaDataPointer(), lat.getDimensions());
+            LatticePoint* a = zeroed(4096);
+            for (int k = 0; k < 4096; ++k)
+                for (int i = 0; i < 27; ++i) a[k].particle_distribution[i] = flowRef.particle_distribution[i];
+            lat.load_data(a);
+            lat.insertModel(dir + "/cube_angled.obj");
+            lat.preProcessModel();
+            FlowData* flow = new FlowData(&FlowCriterion::ptestPlaneCriteria, flowRef);
+            lat.setFlowData(flow);
+            ReflectionData* refl = new ReflectionData;
+            lat.setReflectionData(refl);
+            for (int s = 0; s < 6; ++s) { lat.simulateStreaming(); lat.simulateReflections(); lat.simulateCollision(); lat.simulateFlow(); }
+            // and the kernel wrappers, which see only the LatticeData
+            RunCudaFunctions::run_calculate_streaming(blocks, threads, data, data);
+            RunCudaFunctions::run_calculate_reflections(blocks, threads, data, data);
+            RunCudaFunctions::run_calculate_collision(blocks, threads, data, 0.8f);
+            lat.simulateSteps(5);
+            refl = lat.retrieve_reflection_data();
+            force[mode][0] = refl->x; force[mode][1] = refl->y; force[mode][2] = refl->z;
+            out[mode] = lat.retrieve_data();
+            EXPECT_TRUE(lat.lastError().empty());
+            delete[] a; delete flow; delete refl;
+        }
+        for (int mode = 1; mode < 3; ++mode) {
+            int diff = 0, coords = 0, flags = 0;
+            for (int k = 0; k < 4096; ++k) {
+                for (int i = 0; i < 27; ++i)
+                    if (out[0][k].particle_distribution[i] != out[mode][k].particle_distribution[i]) ++diff;
+                if (out[0][k].x != out[mode][k].x || out[0][k].y != out[mode][k].y || out[0][k].z != out[mode][k].z) ++coords;
+                if (out[0][k].isInternal != out[mode][k].isInternal || out[0][k].isReflected != out[mode][k].isReflected) ++flags;
+            }
+            EXPECT_EQ(diff, 0);                        // bit for bit
+            EXPECT_EQ(coords, 0);
+            EXPECT_EQ(flags, 0);
+            for (int a = 0; a < 3; ++a) EXPECT_NEAR(force[mode][a], force[0][a], 1e-5 * (1 + std::fabs(force[0][a])));
+        }
+        EXPECT_TRUE(std::fabs(force[0][0]) > 0.0);
+        for (int mode = 0; mode < 3; ++mode) delete[] out[mode];
+    }
+
     printf("%d checks, %d failed\n", g_checks, g_failed);
     return g_failed;
 }

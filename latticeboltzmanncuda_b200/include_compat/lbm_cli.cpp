@@ -1,6 +1,14 @@
 // lbm_cli.cpp -- the reference's command line contract (LatticeBoltzmannCuda.cpp:11-96) on the compatibility layer:
 //
 //   lbm_cli <model.obj> <threads x y z> <blocks x y z> <fluid density> <tau> <lattice spacing> <steps> [print_every]
+//           [--gpus N] [--q 19|27] [--boundary reflect|bounce] [--bc zpw] [--moments reference|standard]
+//           [--eq fp64|fp32] [--engine pull2|inplace]
+//
+// The eleven positional arguments are the reference's; the named options select what the reference has no switch for
+// (SURVEY.md section 5): x slabs across N GPUs of this process (peer-memory halos), the velocity set, the boundary model,
+// the edge rule per axis (one letter each: z zero inflow, p periodic, w wall), the velocity moment, the arithmetic of the
+// equilibrium and the streaming engine.  Defaults = the reference's behaviour on one GPU (or the LBM_* environment
+// variables, Lattice::Options::fromEnvironment).
 //
 // The lattice is threads * blocks cells per axis; every population starts at 0.001 and the +x population at 0.002;
 // the same values are injected on the plane x == 0 after every step; the force accumulated on the body is written
@@ -8,8 +16,11 @@
 // reference blocks on a device-to-host copy every step; 0 = never).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <iostream>
 #include <memory>
+#include <string>
+#include <vector>
 
 #include "lbm_reference_api.hpp"
 
@@ -20,13 +31,37 @@ struct Options {
     dim3 threads, blocks;
     float density = 1.0f, tau = 1.0f, spacing = 1.0f;
     int steps = 0, print_every = 1;
+    Lattice::Options lattice = Lattice::Options::fromEnvironment();
     int nx() const { return (int)(threads.x * blocks.x); }
     int ny() const { return (int)(threads.y * blocks.y); }
     int nz() const { return (int)(threads.z * blocks.z); }
 };
 
-bool parse(int argc, char* argv[], Options& o)
+bool parse(int argc_all, char* argv_all[], Options& o)
 {
+    // named options may stand anywhere; what is left are the positional arguments
+    std::vector<char*> pos;
+    for (int k = 0; k < argc_all; ++k) {
+        const std::string a = argv_all[k];
+        if (a.rfind("--", 0) != 0) { pos.push_back(argv_all[k]); continue; }
+        if (k + 1 >= argc_all) return false;
+        const std::string v = argv_all[++k];
+        if (a == "--gpus") o.lattice.gpus = std::atoi(v.c_str()) > 0 ? std::atoi(v.c_str()) : 1;
+        else if (a == "--q") { if (v != "19" && v != "27") return false; o.lattice.q = std::atoi(v.c_str()); }
+        else if (a == "--boundary") { if (v != "reflect" && v != "bounce") return false; o.lattice.boundary_mode = v == "bounce"; }
+        else if (a == "--moments") { if (v != "reference" && v != "standard") return false; o.lattice.moment_mode = v == "standard"; }
+        else if (a == "--eq") { if (v != "fp64" && v != "fp32") return false; o.lattice.eq_precision = v == "fp64"; }
+        else if (a == "--engine") { if (v != "pull2" && v != "inplace") return false; o.lattice.engine = v == "inplace" ? 2 : 1; }
+        else if (a == "--bc") {
+            if (v.size() != 3) return false;
+            for (int ax = 0; ax < 3; ++ax) {
+                if (v[ax] != 'z' && v[ax] != 'p' && v[ax] != 'w') return false;
+                o.lattice.bc[ax] = v[ax] == 'p' ? 1 : (v[ax] == 'w' ? 2 : 0);
+            }
+        } else return false;
+    }
+    const int argc = (int)pos.size();
+    char** argv = pos.data();
     if (argc < 12) return false;
     auto u = [&](int k) { return (unsigned)std::atoi(argv[k]); };
     o.model = argv[1];
@@ -64,10 +99,11 @@ int main(int argc, char* argv[])
 {
     Options o;
     if (!parse(argc, argv, o)) {
-        std::fprintf(stderr, "usage: %s model.obj tx ty tz bx by bz density tau spacing steps [print_every]\n", argv[0]);
+        std::fprintf(stderr, "usage: %s model.obj tx ty tz bx by bz density tau spacing steps [print_every] [--gpus N] [--q 19|27] "
+                             "[--boundary reflect|bounce] [--bc zpw] [--moments reference|standard] [--eq fp64|fp32] [--engine pull2|inplace]\n", argv[0]);
         return -1;
     }
-    Lattice lattice(o.nx(), o.ny(), o.nz(), o.blocks, o.threads, FluidData(o.density, o.tau), o.spacing);
+    Lattice lattice(o.nx(), o.ny(), o.nz(), o.blocks, o.threads, FluidData(o.density, o.tau), o.spacing, o.lattice);
     const LatticePoint inflow = inflow_record();
     fill_uniform(lattice, o, inflow);
 

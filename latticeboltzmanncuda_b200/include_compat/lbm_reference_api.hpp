@@ -148,7 +148,24 @@ private:
 
 class Lattice {
 public:
+    // What the reference has no switch for (it has one velocity set, one boundary model, one edge rule, one GPU).  The
+    // defaults are the reference's behaviour on one GPU; `fromEnvironment()` reads LBM_GPUS (x slabs across that many
+    // devices of this process, joined by peer-memory halos), LBM_Q (19 | 27), LBM_BOUNDARY (reflect | bounce),
+    // LBM_BC ("zpw": one letter per axis -- z zero inflow, p periodic, w wall), LBM_MOMENTS (reference | standard),
+    // LBM_EQ (fp64 | fp32), LBM_ENGINE (pull2 | inplace).  The constructor with the reference's signature uses it.
+    struct Options {
+        int gpus = 1;
+        int q = 27;
+        int boundary_mode = 0;           // lbm_boundary_mode
+        int bc[3] = {0, 0, 0};           // lbm_bc per axis
+        int moment_mode = 0;             // lbm_moment_mode
+        int eq_precision = 1;            // lbm_eq_precision (1 = fp64, the reference's)
+        int engine = 0;                  // lbm_engine
+        static Options fromEnvironment();
+    };
+
     Lattice(int x, int y, int z, dim3 blocks, dim3 threads, FluidData fluid, float spacing);
+    Lattice(int x, int y, int z, dim3 blocks, dim3 threads, FluidData fluid, float spacing, const Options& options);
     ~Lattice();
     Lattice(const Lattice&) = delete;
     Lattice& operator=(const Lattice&) = delete;
@@ -181,16 +198,27 @@ public:
     // additions
     void simulateSteps(int n);                       // n fused steps: stream, reflect, collide, source
     void synchronize();
-    lbm_lattice_s* handle() { flush(); return handle_; }
-    static void flush_owner_of(lbm_lattice_s* h);   // runs the phases the Lattice that owns `h` has queued (RunCudaFunctions)
+    int  deviceCount() const { return (int)slabs_.size(); }
+    lbm_lattice_s* handle() { flush(); return handle_; }      // the first slab
     const std::string& lastError() const { return last_error_; }
 
+    // what RunCudaFunctions::* do once they have found the Lattice a LatticeData names
+    static Lattice* owner_of(lbm_lattice_s* h);
+    void runPhase(unsigned phase, const char* what);
+    void runCollision(float timescale);
+    void runReflections(ReflectionData* into);
+
 private:
+    void create(const Options& options);
     void queue(unsigned phase);
     void flush();
     bool check(int rc, const char* what);
+    bool stepPhases(int n, unsigned phases, const char* what);
 
-    lbm_lattice_s* handle_  = nullptr;
+    lbm_lattice_s* handle_  = nullptr;               // == slabs_[0]
+    std::vector<lbm_lattice_s*> slabs_;              // one per device, cut along x
+    std::vector<int> slab_x0_;                       // first plane of every slab, and nx_ at the end
+    bool           periodic_x_ = false;
     unsigned       pending_ = 0;                     // phases queued in CLI order, not yet executed
     unsigned short nx_, ny_, nz_;
     float          spacing_;

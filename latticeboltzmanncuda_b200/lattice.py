@@ -223,11 +223,23 @@ class Lattice:
         if flowData is None:
             capi.check(self._lib.lbm_set_source(self._h, capi.SOURCE_NONE, None, None, None))
             return
-        lo_c, hi_c = flowData.pointCriterion
+        crit = flowData.pointCriterion
+        f = np.ascontiguousarray(flowData.inducedFlow, np.float32)
+        if callable(crit) or isinstance(crit, np.ndarray):
+            # any predicate (the reference takes a device function pointer, FlowSurface.h:12): evaluated once, here,
+            # on index grids -- crit(x, y, z) -> bool arrays -- or given as a [nx, ny, nz] array; kept as a bit per cell
+            if callable(crit):
+                x, y, z = np.meshgrid(np.arange(self.nx), np.arange(self.ny), np.arange(self.nz), indexing="ij", sparse=True)
+                sel = np.broadcast_to(np.asarray(crit(x, y, z)), (self.nx, self.ny, self.nz))
+            else:
+                sel = crit
+            sel = np.ascontiguousarray(sel, np.uint8).reshape(self.nx, self.ny, self.nz)
+            capi.check(self._lib.lbm_set_source_mask(self._h, capi.ptr(sel), capi.ptr(f)))
+            return
+        lo_c, hi_c = crit
         dims = (self.nx, self.ny, self.nz)
         lo = np.array([0 if v is None else v for v in lo_c], np.int32)
         hi = np.array([dims[a] - 1 if v is None else v for a, v in enumerate(hi_c)], np.int32)
-        f = np.ascontiguousarray(flowData.inducedFlow, np.float32)
         capi.check(self._lib.lbm_set_source(self._h, capi.SOURCE_BOX, capi.ptr(lo), capi.ptr(hi), capi.ptr(f)))
 
     def setReflectionData(self, reflection, exact=None):

@@ -217,6 +217,7 @@ void lbo_source(lbo_lattice_point *cells, int X, int Y, int Z, int kind, const f
         for (int y = 0; y < Y; ++y)
             for (int z = 0; z < Z; ++z) {
                 int hit = (kind == LBO_SRC_CELL_111) ? (x == 1 && y == 1 && z == 1)   /* FlowCriterion.cu:5-8 */
+                        : (kind == LBO_SRC_LATTICE_PATTERN) ? ((x + 2 * y + 3 * z) % 5 == 0 && x >= 1)   /* ours: not a box */
                                                      : (x == 0);                       /* FlowCriterion.cu:10-13 */
                 if (!hit) continue;
                 float *f = cells[lbo_index(x, y, z, Y, Z)].f;

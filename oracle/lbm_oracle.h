@@ -51,7 +51,8 @@ extern const int   LBO_DIRECTIONS[27][3];
 extern const int   LBO_INVERSE[27];
 extern const float LBO_SPLIT[27];
 
-enum { LBO_SRC_NONE = 0, LBO_SRC_CELL_111 = 1, LBO_SRC_PLANE_X0 = 2 };
+enum { LBO_SRC_NONE = 0, LBO_SRC_CELL_111 = 1, LBO_SRC_PLANE_X0 = 2,
+       LBO_SRC_LATTICE_PATTERN = 3 /* (x + 2y + 3z) % 5 == 0 && x >= 1: a criterion that is not an index box (test only) */ };
 enum { LBO_BC_ZERO_INFLOW = 0, LBO_BC_PERIODIC = 1 };
 enum { LBO_MOMENT_REFERENCE = 0, LBO_MOMENT_STANDARD = 1 };
 

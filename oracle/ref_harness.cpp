@@ -16,6 +16,9 @@
 #include "FlowCriterion.cuh"
 #include "SimCalcFuncs.cuh"
 
+// a flow criterion of our own that is not an index box (oracle/ref_extra_criterion.cu), C++ linkage
+namespace LbmExtraCriterion { extern __device__ bool (*platticePattern)(int, int, int); }
+
 struct RefHandle {
     Lattice* lattice;
     void* storage;
@@ -88,14 +91,16 @@ void ref_sync() { cudaDeviceSynchronize(); }
 void ref_insert_model(void* hv, const char* path) { ((RefHandle*)hv)->lattice->insertModel(std::string(path)); }
 void ref_preprocess(void* hv) { ((RefHandle*)hv)->lattice->preProcessModel(); }
 
-// kind 1: FlowCriterion::ptestCriteria (cell 1,1,1); kind 2: ptestPlaneCriteria (x == 0)
+// kind 1: FlowCriterion::ptestCriteria (cell 1,1,1); kind 2: ptestPlaneCriteria (x == 0); kind 3: a criterion of our own
+// that is not a box (oracle/ref_extra_criterion.cu), to exercise the reference's per-cell predicate call
 void ref_set_flow(void* hv, int kind, const float* f27)
 {
     RefHandle* h = (RefHandle*)hv;
     LatticePoint flowRef;
     std::memset((void*)&flowRef, 0, sizeof(flowRef));
     for (int i = 0; i < 27; ++i) flowRef.particle_distribution[i] = f27[i];
-    h->flow = new FlowData(kind == 1 ? &FlowCriterion::ptestCriteria : &FlowCriterion::ptestPlaneCriteria, flowRef);
+    h->flow = new FlowData(kind == 1 ? &FlowCriterion::ptestCriteria
+                           : kind == 3 ? &LbmExtraCriterion::platticePattern : &FlowCriterion::ptestPlaneCriteria, flowRef);
     h->lattice->setFlowData(h->flow);
 }
 

@@ -184,7 +184,8 @@ def reference_library():
         fcntl.flock(lock, fcntl.LOCK_EX)
         mine = [os.path.join(oracle, f) for f in ("ref_harness.cpp", "ref_model_stub.cpp")]
         host = [os.path.join(src_dir, f) for f in ("Lattice.cpp", "Geometry.cpp", "Constants.cpp", "Utils.cpp")]
-        dev = [os.path.join(src_dir, f) for f in ("SimCalcFuncs.cu", "FlowCriterion.cu")]
+        # (+ a flow criterion of our own that is not an index box, next to the reference's two: oracle/ref_extra_criterion.cu)
+        dev = [os.path.join(src_dir, f) for f in ("SimCalcFuncs.cu", "FlowCriterion.cu")] + [os.path.join(oracle, "ref_extra_criterion.cu")]
         if _newer(so, mine + host + dev + [os.path.join(EMU, "simt.h"), os.path.join(EMU, "simt_runtime.cpp"), os.path.abspath(__file__)]):
             import _oracle
             _oracle.lib()                                              # liblbm_oracle.so answers the mesh queries of the model stub

@@ -19,7 +19,7 @@ LATTICE_POINT = np.dtype({
 REFLECTION_VALUES = np.dtype([("dirs", "<i4", 14), ("w", "<f4", 81)])
 assert REFLECTION_VALUES.itemsize == 380
 
-SRC_NONE, SRC_CELL_111, SRC_PLANE_X0 = 0, 1, 2
+SRC_NONE, SRC_CELL_111, SRC_PLANE_X0, SRC_LATTICE_PATTERN = 0, 1, 2, 3
 BC_ZERO, BC_PERIODIC, BC_WALL = 0, 1, 2
 MOMENT_REFERENCE, MOMENT_STANDARD = 0, 1
 

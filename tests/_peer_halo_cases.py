@@ -33,6 +33,11 @@ def _body(X, Y, Z, kind):
         s[0, Y - 3:Y - 1, 10:14] = 1
         s[X - 1, 1:4, 20:23] = 1
         s[(2 * X) // 3 - 1:(2 * X) // 3 + 1, 4, 33:70] = 1
+    if kind == "slab_of_solid":
+        # whole 32-cell words and whole 4-word blocks of solid (dead words, dead blocks) next to partly solid ones
+        s[1:X - 1, 1:Y - 1, 30:165] = 1
+        s[X // 2, 2, 60:70] = 0
+        s[0, 0, 128:160] = 1
     return s
 
 
@@ -44,6 +49,9 @@ CASES = {
     "inplace_q27_walls_w2": dict(engine=lb.ENGINE_INPLACE, q=27, shape=(6, 4, 33), world=2, bc=(P, W, W), steps=4, wall_u=WALL_U),
     "inplace_q19_thin_slabs_w2": dict(engine=lb.ENGINE_INPLACE, q=19, shape=(4, 6, 64), world=2, bc=(P, P, W), body="edges",
                                       force=True, steps=3),
+    # nz >= 97: the single-buffer kernels are launched over the list of blocks that hold a live word
+    "inplace_q19_live_block_list_w2": dict(engine=lb.ENGINE_INPLACE, q=19, shape=(6, 5, 170), world=2, bc=(P, W, W), body="slab_of_solid",
+                                           force=True, steps=5, wall_u=WALL_U),
     "inplace_q19_self_ring_w1": dict(engine=lb.ENGINE_INPLACE, q=19, shape=(5, 4, 36), world=1, bc=(P, W, P), steps=3),
     "pull2_q19_body_w3": dict(engine=lb.ENGINE_PULL2, q=19, shape=(10, 7, 70), world=3, bc=(P, W, P), body="edges", source=True,
                               force=True, steps=4, wall_u=WALL_U),

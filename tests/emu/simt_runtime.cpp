@@ -203,6 +203,7 @@ extern "C" {
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "simt emulation error"; }
 cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaDeviceGetAttribute(int* v, enum cudaDeviceAttr, int) { *v = 0; return cudaSuccess; }
 cudaError_t cudaDeviceSetLimit(enum cudaLimit, size_t) { return cudaSuccess; }

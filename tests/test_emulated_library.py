@@ -25,7 +25,8 @@ SELECTION = [
     (TP, "test_collision_known_answer", 1), (TP, "test_full_known_answer", 1), (TP, "test_reflections_known_answer", 1),
     (TP, "test_flow_generation_known_answer", 1), (TP, "test_plane_flow_generation_known_answer", 1),
     (TP, "test_stream_bit_exact", 1), (TP, "test_collide_parity", 1), (TP, "test_reflect_parity_16", 1),
-    (TP, "test_cli_steps_parity_with_geometry", 2), (TP, "test_force_accumulator_in_the_reference_arithmetic", 1), (TP, "test_unfused_phases_equal_fused_step", 1),
+    (TP, "test_cli_steps_parity_with_geometry", 2), (TP, "test_force_accumulator_in_the_reference_arithmetic", 1),
+    (TP, "test_source_with_an_arbitrary_criterion", 1), (TP, "test_unfused_phases_equal_fused_step", 1),
     (TP, "test_soa_engine_parity", 1), (TP, "test_bounce_back_obstacle_parity", 1), (TP, "test_lid_driven_cavity_parity", 1),
     (TP, "test_bad_arguments_are_reported", 1), (TP, "test_inplace_engine_equals_two_buffer_engine", 9),
     (TP, "test_inplace_engine_with_obstacles", 5), (TP, "test_inplace_engine_refuses_what_it_cannot_do", 1),
@@ -79,10 +80,14 @@ def test_checkpoint_round_trip_on_the_host_build(host_build, tmp_path):
     TI.test_checkpoint_round_trip_continues_bit_for_bit(tmp_path)
 
 
-@pytest.mark.parametrize("body", [TC.test_reference_gtest_cases_through_the_cpp_headers, TC.test_cli_force_trace_matches_oracle],
-                         ids=["reference_gtest_cases", "cli_force_trace"])
+@pytest.mark.parametrize("body", [TC.test_reference_gtest_cases_through_the_cpp_headers,
+                                  lambda: TC.test_cli_force_trace_matches_oracle([]),
+                                  lambda: TC.test_cli_force_trace_matches_oracle(["--gpus", "2"]),
+                                  TC.test_cli_rejects_unknown_options],
+                         ids=["reference_gtest_cases", "cli_force_trace", "cli_force_trace_two_slabs", "cli_usage"])
 def test_cpp_layer_on_the_host_build(monkeypatch, body):
-    """the C++ drop-in layer (the reference's gtest cases, the CLI's force trace) linked against the host build"""
+    """the C++ drop-in layer (the reference's gtest cases, the CLI's force trace -- also cut into two slabs) linked
+    against the host build"""
     monkeypatch.setattr(TC, "_built", _emu.compat_executable)
     body()
 

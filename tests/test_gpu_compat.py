@@ -32,13 +32,16 @@ def test_reference_gtest_cases_through_the_cpp_headers():
     assert " 0 failed" in res.stdout
 
 
-def test_cli_force_trace_matches_oracle():
-    """LatticeBoltzmannCuda.cpp:11-96: 11 positional arguments, one "Fx Fy Fz" line per step"""
+@pytest.mark.parametrize("extra", [[], ["--gpus", "2"], ["--gpus", "3", "--q", "27", "--bc", "zzz"]])
+def test_cli_force_trace_matches_oracle(extra):
+    """LatticeBoltzmannCuda.cpp:11-96: 11 positional arguments, one "Fx Fy Fz" line per step.  The named options are
+    additions (the reference has no switches): --gpus N cuts the lattice into x slabs, one per device (devices are
+    reused on a smaller box), joined by peer-memory halos -- the trace must not change."""
     exe = _built("lbm_cli")
     n, tau, steps = 16, 0.9, 25
     spacing = np.float32(1.0 / n)
     res = subprocess.run([exe, os.path.join(OBJ, "cube_angled.obj"), "8", "8", "8", "2", "2", "2", "1.0", str(tau),
-                          repr(float(spacing)), str(steps)], capture_output=True, text=True, timeout=600)
+                          repr(float(spacing)), str(steps)] + extra, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr
     got = np.array([[float(v) for v in line.split()] for line in res.stdout.strip().splitlines()])
     assert got.shape == (steps, 3)
@@ -57,3 +60,10 @@ def test_cli_force_trace_matches_oracle():
     want = np.array(want)
     assert np.allclose(got, want, rtol=5e-4, atol=1e-6)
     assert np.abs(got[-1]).max() > 0
+
+
+def test_cli_rejects_unknown_options():
+    exe = _built("lbm_cli")
+    res = subprocess.run([exe, "x.obj", "8", "8", "8", "2", "2", "2", "1.0", "1.0", "0.1", "1", "--colour", "blue"],
+                         capture_output=True, text=True, timeout=60)
+    assert res.returncode != 0 and "usage" in res.stderr

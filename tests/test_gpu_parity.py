@@ -227,6 +227,69 @@ def test_reflect_parity_16():
     assert np.allclose([r.x, r.y, r.z], force, rtol=1e-4, atol=1e-6)
 
 
+def soa_equilibrium(q, n, solid):
+    w = O.weights(q).astype(np.float32)
+    f = np.ascontiguousarray(np.broadcast_to(w[:, None, None, None], (q, n, n, n))).copy()
+    f[6] *= 1.05
+    f[:, solid.astype(bool)] = 0
+    return f
+
+
+def lattice_pattern(x, y, z):
+    """a flow criterion that is not an index box (restated in oracle/lbm_oracle.c, LBO_SRC_LATTICE_PATTERN, and compiled
+    as a device predicate for the reference's own generate_flow in oracle/ref_extra_criterion.cu)"""
+    return ((x + 2 * y + 3 * z) % 5 == 0) & (x >= 1)
+
+
+def test_source_with_an_arbitrary_criterion():
+    """FlowData takes ANY device predicate in the reference (FlowSurface.h:12, called per cell at SimCalcFuncs.cu:206);
+    here it is evaluated once and kept as a bit per cell (lbm_set_source_mask): the source phase alone, the CLI loop with
+    geometry, and the same mask on both throughput engines"""
+    n = 16
+    cells, tables, tindex = geometry_case(n)
+    flow = (np.arange(27, dtype=np.float32) + 1.0) * 1e-4
+    cells["f"] = np.float32(0.002)
+    want1 = O.source(cells, n, n, n, O.SRC_LATTICE_PATTERN, flow)
+    lat = make(n, n, n, tau=0.8)
+    lat.load_data(cells)
+    lat.setFlowData(lb.FlowData(lattice_pattern, flow))
+    lat.simulateFlow()
+    got1 = lat.retrieve_data()
+    assert np.array_equal(got1["f"], want1["f"])                       # additions of the same floats: bit for bit
+    hit = lattice_pattern(*np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")).ravel()
+    assert 0 < hit.sum() < n ** 3 // 4 and np.all(got1["f"][~hit] == np.float32(0.002))
+    # the CLI loop with this criterion
+    force = np.zeros(3, np.float32)
+    want = O.step_cli(cells, n, n, n, 0.8, tables, tindex, force, O.SRC_LATTICE_PATTERN, flow, steps=12)
+    lat.load_data(cells)
+    lat.set_reflection_tables(tables, np.nonzero(tindex >= 0)[0])
+    lat.step(12)
+    assert rel_err(lat.retrieve_data()["f"], want["f"]) <= REL
+    # the same selection as an array, on the two throughput engines: identical states
+    solid = cells["is_internal"].reshape(n, n, n).astype(np.uint8)
+    sel = hit.reshape(n, n, n)
+    f0 = soa_equilibrium(19, n, solid)
+    got = []
+    for engine in (lb.ENGINE_PULL2, lb.ENGINE_INPLACE):
+        l2 = lb.Lattice(n, n, n, None, None, lb.FluidData(1.0, 0.7), 1.0, q=19, bc=(lb.BC_PERIODIC, lb.BC_WALL, lb.BC_PERIODIC),
+                        moment_mode=lb.MOMENT_STANDARD, eq_precision=lb.EQ_FP32, boundary_mode=lb.BOUNDARY_BOUNCE_BACK, engine=engine)
+        l2.set_solid_mask(solid)
+        l2.load_populations(f0)
+        l2.setFlowData(lb.FlowData(sel, flow * 0.1))
+        l2.step(7)
+        got.append(l2.retrieve_populations())
+        l2.close()
+    assert rel_err(got[1], got[0]) <= 2e-6
+    mass0 = float(f0.astype(np.float64).sum())
+    fluid_hits = int((sel & (solid == 0)).sum())
+    assert abs(float(got[0].astype(np.float64).sum()) - mass0 - 7 * fluid_hits * float(flow[:19].sum()) * 0.1) <= 1e-4 * mass0
+    # a criterion that selects nothing switches the source off
+    lat.setFlowData(lb.FlowData(lambda x, y, z: x < 0, flow))
+    before = lat.retrieve_data()["f"]
+    lat.simulateFlow()
+    assert np.array_equal(lat.retrieve_data()["f"], before)
+
+
 @pytest.mark.parametrize("tau,steps,fused", [(1.0, 40, True), (0.6, 25, True), (1.0, 12, False)])
 def test_force_accumulator_in_the_reference_arithmetic(tau, steps, fused):
     """SURVEY.md 8c holds the force to 1e-5.  The reference adds every reflected slot into ONE float triple

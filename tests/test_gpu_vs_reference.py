@@ -214,3 +214,26 @@ def test_reference_flow_generation_and_ours(kind):
     assert np.array_equal(got["f"], want["f"])
     changed = np.nonzero((want["f"] != cells["f"]).any(1))[0]
     assert len(changed) == (1 if kind == 1 else n * n)
+
+
+def test_source_with_a_criterion_that_is_not_a_box_equals_the_reference_kernel():
+    """the reference calls a device predicate for every cell (SimCalcFuncs.cu:206); ours is a bit per cell evaluated on
+    the host (lbm_set_source_mask).  The predicate is one of our own, compiled as a __device__ function-pointer symbol
+    next to the reference's sources (oracle/ref_extra_criterion.cu) and handed to the reference's unmodified
+    generate_flow through its own FlowData mechanism."""
+    from test_gpu_parity import lattice_pattern
+    X = Y = Z = 16
+    cells = random_cells(X, Y, Z, 9)
+    flow = (np.arange(27, dtype=np.float32) + 1.0) * 1e-3
+    ref = R.RefLattice(X, Y, Z)
+    ref.load(cells); ref.prime(); ref.set_flow(3, flow); ref.flow()
+    want = ref.retrieve()
+    lat = ours(X, Y, Z)
+    lat.load_data(cells)
+    lat.setFlowData(lb.FlowData(lattice_pattern, flow))
+    lat.simulateFlow()
+    got = lat.retrieve_data()
+    assert np.array_equal(got["f"], want["f"])
+    assert np.array_equal(O.source(cells, X, Y, Z, O.SRC_LATTICE_PATTERN, flow)["f"], want["f"])      # and the oracle's restatement
+    changed = np.any(want["f"] != cells["f"], axis=1)
+    assert 0 < changed.sum() < X * Y * Z // 4
