@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=512, help="N = 1: cells per axis")
     ap.add_argument("--slab", default="128,1024,1024", help="N > 1: cells of one GPU's x-slab (nx,ny,nz)")
+    ap.add_argument("--workload", default="auto", choices=["auto", "slab"],
+                    help="slab: run one slab of the N > 1 workload on ONE GPU (the per-GPU rate the scaling run is compared with)")
     ap.add_argument("--q", type=int, default=19, choices=[19, 27])
     ap.add_argument("--engine", default="inplace", choices=["inplace", "pull2"],
                     help="inplace = single-buffer AA streaming (headline), pull2 = two-buffer fused pull")
@@ -210,7 +212,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     q, tau = args.q, 0.6
-    if world == 1:
+    slab_shape = world > 1 or args.workload == "slab"
+    if not slab_shape:
         nx = gy = gz = args.size
     else:
         nx, gy, gz = (int(v) for v in args.slab.split(","))
@@ -236,7 +239,7 @@ def run_ours(args):
         lat = slab.lattice
 
     # synthetic inputs: obstacle mask + uniform initial state (host, pinned) + inflow plane source at global x == 0
-    interior = obstacle_mask(world, nx, gy, gz)
+    interior = obstacle_mask(2 if slab_shape else 1, nx, gy, gz)
     solid = interior
     if world > 1:
         ghost = np.zeros((1, gy, gz), np.uint8)          # the bodies keep clear of the slab faces
@@ -428,7 +431,7 @@ def run_ours(args):
                     else "two-buffer fused pull, classified 32-cell words")
         kern = ("aa_odd_kernel<%d> + aa_odd_special_kernel<%d> / aa_even_kernel<%d> + aa_even_special_kernel<%d> (odd / even step)" % (q, q, q, q)
                 if engine == lb.ENGINE_INPLACE else "step_general_kernel<%d> + step_special_kernel<%d> (one step)" % (q, q))
-        if world == 1:
+        if not slab_shape:
             wl = ("flow past obstacle (reference test geometry, tapered hexahedron) %dx%dx%d D3Q%d BGK, half-way bounce-back, periodic in x, "
                   "walls in y/z, initial u=(0.04,0,0), plane source at x=0, force accumulator on" % (gx, gy, gz, q))
         else:

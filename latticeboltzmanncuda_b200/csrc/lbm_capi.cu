@@ -161,7 +161,10 @@ int rebuild_special(lbm_handle h)
         h->live_blocks = nullptr;
         h->n_live = 0;
         h->live_start.clear();
-        static const bool use_list = [] { const char* e = getenv("LBM_AA_LIVE_LIST"); return e ? atoi(e) != 0 : true; }();
+        // Measured on B200 (profiles/r02_notes.md, 512^3 obstacle, same box): 2.566 ms/step with the list against 2.534
+        // without -- the dependent list load in front of every block and the lost launch order cost more than the
+        // skipped blocks save -- so the list is OFF unless LBM_AA_LIVE_LIST=1 asks for it.
+        static const bool use_list = [] { const char* e = getenv("LBM_AA_LIVE_LIST"); return e ? atoi(e) != 0 : false; }();
         const int nbw = (wcount + 3) / 4;
         if (use_list && h->inplace && solid && g.nz >= 97 && g.nx <= 4096 && g.ny <= 4096 && nbw <= 256) {
             std::vector<uint8_t> cls(h->cls_bytes);

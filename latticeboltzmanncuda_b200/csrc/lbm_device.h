@@ -165,9 +165,9 @@ struct InplaceParams {
     long long xshift[2][27];
     // Lattices with obstacles: the blocks (4 consecutive z-words of one row) that hold at least one live word, as a
     // sorted list of packed ids (x << 20 | y << 8 | block-in-row); the main kernels are launched over this list instead
-    // of the whole box, so that all-solid regions cost no block launches at all (a block that only finds out that its
-    // words are dead still holds a scheduler slot for a memory round trip: 12 % of the slot time on the 512^3 obstacle).
-    // nullptr: launch over the box.  The entries of the planes of this launch: [live_k0, live_k0 + n_live).
+    // of the whole box, so that all-solid regions cost no block launches at all.  An experiment that lost (1.2 % slower
+    // on the 512^3 obstacle: profiles/r02_notes.md), kept behind LBM_AA_LIVE_LIST=1.  nullptr (the default): launch over
+    // the box.  The entries of the planes of this launch: [live_k0, live_k0 + n_live).
     const uint32_t* live_blocks;
     long long live_k0, n_live;
 };
