@@ -157,6 +157,50 @@ LBM_HD bool point_inside(const MeshView& m, float px, float py, float pz)
     return false;
 }
 
+// The same answer from far fewer triangles.  A triangle can only matter to the point (px, py, pz) if
+//   * its xy bounding box (slightly inflated) holds (px, py): only then can the point lie on it or the +z ray hit it, or
+//   * it is parallel to the +z ray ("vertical"): ray_triangle then reports a degenerate hit for EVERY point in its plane,
+//     however far from the triangle, and the ray is re-shot.
+// `cand` = the triangles binned to this lattice column, `vert` = all vertical triangles.  Every triangle left out would
+// have answered "no" to both tests, so the crossings counted are the ones point_inside() counts; a degenerate hit falls
+// back to point_inside() itself (re-shot rays go anywhere and need every triangle).
+LBM_HD bool point_inside_binned(const MeshView& m, float px, float py, float pz, const int* cand, int ncand, const int* vert, int nvert)
+{
+    if (!m.valid || m.nf == 0) return false;
+    if (px < m.lo[0] || px > m.hi[0] || py < m.lo[1] || py > m.hi[1] || pz < m.lo[2] || pz > m.hi[2]) return false;
+    const double p[3] = {px, py, pz};
+    for (int k = 0; k < ncand; ++k)
+        if (on_triangle(m, cand[k], p)) return true;
+    const double dir[3] = {0.0, 0.0, 1.0};
+    int crossings = 0;
+    bool bad = false;
+    for (int k = 0; k < ncand && !bad; ++k) {
+        double t;
+        const int r = ray_triangle(m, cand[k], p, dir, &t);
+        if (r == 2) bad = true;
+        else if (r == 1) ++crossings;
+    }
+    for (int k = 0; k < nvert && !bad; ++k) {
+        double t;
+        if (ray_triangle(m, vert[k], p, dir, &t) == 2) bad = true;
+    }
+    if (!bad) return crossings & 1;
+    return point_inside(m, px, py, pz);
+}
+
+// is triangle f parallel to the +z ray in ray_triangle's own terms (its first branch)?
+LBM_HD bool parallel_to_z(const MeshView& m, int f)
+{
+    double a[3], b[3], c[3], e1[3], e2[3], pv[3];
+    load_tri(m, f, a, b, c);
+    for (int k = 0; k < 3; ++k) { e1[k] = b[k] - a[k]; e2[k] = c[k] - a[k]; }
+    const double dir[3] = {0.0, 0.0, 1.0};
+    cross(dir, e2, pv);
+    const double det = dot(e1, pv);
+    const double scale = sqrt(dot(e1, e1) * dot(e2, e2) * dot(dir, dir)) + 1e-300;
+    return fabs(det) <= 1e-12 * scale;
+}
+
 // rotateVectorAroundAxis with the half-angle cosine / sine supplied (they come from the host's libm so
 // that host and device agree to the last bit)
 LBM_HD void rotate_cs(const float axis_in[3], const float vec[3], float c, float s, float cn, float sn, float out[3])
@@ -263,6 +307,23 @@ __global__ void voxelise_kernel(MeshView m, uint8_t* __restrict__ solid, int nx,
     const int y = (int)((k / nz) % ny);
     const int x = (int)(k / ((long long)nz * ny)) + x_origin;
     solid[k] = (x >= 0 && x < gx && point_inside(m, x * spacing, y * spacing, z * spacing)) ? 1 : 0;
+}
+
+// The same loop with the triangles binned per lattice column (x, y): col_start / col_tris is a CSR list over the nx * ny
+// columns of the planes being voxelised; cost per cell = the triangles over its column instead of the whole mesh.
+__global__ void voxelise_binned_kernel(MeshView m, const int* __restrict__ col_start, const int* __restrict__ col_tris,
+                                       const int* __restrict__ vert, int nvert, uint8_t* __restrict__ solid,
+                                       int nx, int ny, int nz, float spacing, int x_origin, int gx)
+{
+    const long long n = (long long)nx * ny * nz;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int z = (int)(k % nz);
+    const int y = (int)((k / nz) % ny);
+    const int xl = (int)(k / ((long long)nz * ny));
+    const int x = xl + x_origin;
+    const int c0 = col_start[xl * ny + y], c1 = col_start[xl * ny + y + 1];
+    solid[k] = (x >= 0 && x < gx && point_inside_binned(m, x * spacing, y * spacing, z * spacing, col_tris + c0, c1 - c0, vert, nvert)) ? 1 : 0;
 }
 
 // solid cells with at least one in-domain fluid neighbour: the only cells that can own a table
@@ -541,6 +602,76 @@ LBM_API unsigned lbm_compress_ints(const int* array, int num, int bit_length)
     return out;
 }
 
+// Voxelises the planes x_origin .. x_origin + nxv - 1 (global indices) into `bytes` ([nxv][ny][nz], device).  The triangles
+// are binned per lattice column on the host (each triangle goes to the columns its inflated xy bounding box covers, plus
+// one column all round for the rounding of index * spacing), so the device loop over a cell sees only the triangles above
+// and below it.  Meshes whose bins would not fit (huge triangles on a huge lattice) take the all-pairs kernel.
+static int voxelise_planes(lbm_handle h, lbm_mesh m, const MeshView& v, uint8_t* bytes, int nxv, int x_origin, int gx, float spacing)
+{
+    const Geom& g = h->g;
+    const int ny = g.ny, nz = g.nz;
+    const size_t n = (size_t)nxv * ny * nz;
+    static const bool binned = [] { const char* e = getenv("LBM_VOXELISE_BINNED"); return e ? atoi(e) != 0 : true; }();
+    const int nf = (int)(m->tri.size() / 3);
+    const size_t ncol = (size_t)nxv * ny;
+    std::vector<int> count(ncol + 1, 0), vertical;
+    std::vector<int> lo_x(nf), hi_x(nf), lo_y(nf), hi_y(nf);
+    size_t entries = 0;
+    bool use_bins = binned && nf > 0 && m->valid;
+    if (use_bins) {
+        const MeshView hv = host_view(m);
+        for (int f = 0; f < nf; ++f) {
+            if (parallel_to_z(hv, f)) vertical.push_back(f);
+            double bl[3] = {1e300, 1e300, 1e300}, bh[3] = {-1e300, -1e300, -1e300};
+            for (int c = 0; c < 3; ++c)
+                for (int a = 0; a < 3; ++a) {
+                    const double w = m->v[(size_t)m->tri[3 * f + c] * 3 + a];
+                    bl[a] = std::min(bl[a], w); bh[a] = std::max(bh[a], w);
+                }
+            const double diag = sqrt((bh[0] - bl[0]) * (bh[0] - bl[0]) + (bh[1] - bl[1]) * (bh[1] - bl[1]) + (bh[2] - bl[2]) * (bh[2] - bl[2]));
+            const double margin = 1e-6 * (diag + fabs(bl[0]) + fabs(bh[0]) + fabs(bl[1]) + fabs(bh[1])) + 1e-30;
+            // columns whose lattice point can lie within the inflated box, one more on each side for rounding
+            const long long ax = (long long)floor((bl[0] - margin) / spacing) - 1 - x_origin, bx = (long long)ceil((bh[0] + margin) / spacing) + 1 - x_origin;
+            const long long ay = (long long)floor((bl[1] - margin) / spacing) - 1, by = (long long)ceil((bh[1] + margin) / spacing) + 1;
+            lo_x[f] = (int)std::max<long long>(ax, 0); hi_x[f] = (int)std::min<long long>(bx, nxv - 1);
+            lo_y[f] = (int)std::max<long long>(ay, 0); hi_y[f] = (int)std::min<long long>(by, ny - 1);
+            if (hi_x[f] < lo_x[f] || hi_y[f] < lo_y[f]) continue;
+            entries += (size_t)(hi_x[f] - lo_x[f] + 1) * (size_t)(hi_y[f] - lo_y[f] + 1);
+        }
+        if (entries > (size_t(64) << 20)) use_bins = false;
+    }
+    if (!use_bins) {
+        voxelise_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(v, bytes, nxv, ny, nz, spacing, x_origin, gx);
+        GCK(cudaGetLastError());
+        return LBM_OK;
+    }
+    for (int f = 0; f < nf; ++f)
+        for (int x = lo_x[f]; x <= hi_x[f]; ++x)
+            for (int y = lo_y[f]; y <= hi_y[f]; ++y) ++count[(size_t)x * ny + y + 1];
+    for (size_t c = 0; c < ncol; ++c) count[c + 1] += count[c];
+    std::vector<int> tris(entries ? entries : 1), fill(count.begin(), count.end() - 1);
+    for (int f = 0; f < nf; ++f)             // ascending triangle order within a column, like the all-pairs loop
+        for (int x = lo_x[f]; x <= hi_x[f]; ++x)
+            for (int y = lo_y[f]; y <= hi_y[f]; ++y) tris[(size_t)fill[(size_t)x * ny + y]++] = f;
+    int *d_start = nullptr, *d_tris = nullptr, *d_vert = nullptr;
+    cudaError_t e = cudaMalloc(&d_start, count.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&d_tris, tris.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&d_vert, (vertical.size() + 1) * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_start, count.data(), count.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tris, tris.data(), tris.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && !vertical.empty())
+        e = cudaMemcpyAsync(d_vert, vertical.data(), vertical.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        voxelise_binned_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(v, d_start, d_tris, d_vert, (int)vertical.size(), bytes,
+                                                                              nxv, ny, nz, spacing, x_origin, gx);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);      // the host vectors and the bins go away here
+    cudaFree(d_start); cudaFree(d_tris); cudaFree(d_vert);
+    if (e != cudaSuccess) return lbm_internal_fail(e == cudaErrorMemoryAllocation ? LBM_ERR_NOMEM : LBM_ERR_CUDA, cudaGetErrorString(e));
+    return LBM_OK;
+}
+
 // Lattice::insertModel (Lattice.cpp:228-260): voxelise the mesh on the lattice points index*spacing.
 // On a slab (lbm_set_slab_origin) the index is the global one and the neighbours' edge planes are voxelised too.
 LBM_API int lbm_insert_model(lbm_handle h, lbm_mesh m, float spacing, int* accepted)
@@ -563,13 +694,9 @@ LBM_API int lbm_insert_model(lbm_handle h, lbm_mesh m, float spacing, int* accep
     const size_t per = (size_t)g.ny * g.nz;
     const size_t n = (size_t)g.nx * per;
     if (!h->solid_bytes) GCK(cudaMalloc(&h->solid_bytes, n + 2 * per));
-    if (slab) {
-        voxelise_kernel<<<(unsigned)((n + 2 * per + 127) / 128), 128, 0, h->stream>>>(v, h->solid_bytes, g.nx + 2, g.ny, g.nz, spacing,
-                                                                                  h->slab_x0 - 1, gx);
-    } else {
-        voxelise_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(v, h->solid_bytes, g.nx, g.ny, g.nz, spacing, 0, g.nx);
-    }
-    GCK(cudaGetLastError());
+    if ((rc = slab ? voxelise_planes(h, m, v, h->solid_bytes, g.nx + 2, h->slab_x0 - 1, gx, spacing)
+                   : voxelise_planes(h, m, v, h->solid_bytes, g.nx, 0, g.nx, spacing)))
+        return rc;
     if (accepted) *accepted = 1;
     return lbm_internal_rebuild_mask(h, h->solid_bytes, slab ? 1 : 0);
 }
@@ -604,7 +731,7 @@ LBM_API int lbm_preprocess_model(lbm_handle h, lbm_mesh m, float spacing)
         GCK(cudaMalloc(&box, n));
         MeshView vv = v;
         if (!m->loaded) vv.nf = 0;
-        voxelise_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(vv, box, bx, g.ny, g.nz, spacing, xa, h->slab_gx);
+        if ((rc = voxelise_planes(h, m, vv, box, bx, xa, h->slab_gx, spacing))) { cudaFree(box); return rc; }
     } else {
         if (!h->solid_bytes) GCK(cudaMalloc(&h->solid_bytes, n + 2 * per));
         GCK(launch_mask_to_bytes(h->solid, h->solid_bytes, g, h->stream));

@@ -355,6 +355,8 @@ int lbo_insert_model(const lbo_mesh *m, lbo_lattice_point *cells, int X, int Y, 
     if (lo[0] < 0.0 || lo[1] < 0.0 || lo[2] < 0.0 ||
         hi[0] > X * spacing || hi[1] > Y * spacing || hi[2] > Z * spacing)
         return 0;
+    /* (every cell is an independent query: the loop is spread over the cores, the answers do not depend on that) */
+#pragma omp parallel for collapse(2) schedule(dynamic, 4)
     for (int x = 0; x < X; ++x)
         for (int y = 0; y < Y; ++y)
             for (int z = 0; z < Z; ++z)

@@ -111,6 +111,53 @@ def test_mask_and_tables_bit_exact(shape, name):
     assert np.array_equal(out["is_reflected"], cells["is_reflected"])
 
 
+def _icosphere(tmp_path, level):
+    import sys
+    sys.path.insert(0, O.GOLDEN_DIR)
+    from make_icosphere import write_icosphere
+    path = str(tmp_path / ("icosphere_%d.obj" % level))
+    nv, nf = write_icosphere(path, level)
+    return path, nf
+
+
+ICO_CASE = (int(os.environ.get("LBM_ICO_LEVEL", "5")), int(os.environ.get("LBM_ICO_N", "128")))
+
+
+def test_voxeliser_scales_with_the_mesh(tmp_path):
+    """A mesh of 20 480 triangles (an icosphere written by tests/golden/make_icosphere.py) voxelised at 128^3: the GPU
+    voxeliser bins the triangles per lattice column, so a cell looks at the few triangles above and below it instead of
+    the whole mesh, and must still give the all-pairs answer of the oracle (oracle/geom_oracle.c) bit for bit."""
+    import time
+    level, n = ICO_CASE
+    path, nf = _icosphere(tmp_path, level)
+    assert nf == 20 * 4 ** level
+    spacing = np.float32(1.0 / n)
+    cells = O.new_cells(n, n, n)
+    mesh = O.Mesh(path)
+    assert mesh.is_closed and not mesh.check_error
+    assert mesh.insert(cells, n, n, n, spacing) == 1
+    want = cells["is_internal"].reshape(n, n, n)
+    lat = make(n, n, n, float(spacing))
+    t0 = time.perf_counter()
+    assert lat.insertModel(path)
+    lat.sync()
+    seconds = time.perf_counter() - t0
+    got = lat.get_solid_mask()
+    assert np.array_equal(got, want)
+    inside = int(want.sum())
+    assert abs(inside / n ** 3 - 4.0 / 3.0 * np.pi * 0.3719 ** 3) < 0.01          # it is the sphere
+    print("voxelised %d^3 against %d triangles in %.2f s (%d cells inside)" % (n, nf, seconds, inside))
+    # slabs voxelise in global coordinates: the same mask, cut in three
+    from latticeboltzmanncuda_b200.slab import SlabGroup
+    grp = SlabGroup(n, n, n, lb.FluidData(1.0, 1.0), [0, 0, 0], bc_x=lb.BC_ZERO_INFLOW, bc_yz=(lb.BC_ZERO_INFLOW,) * 2)
+    try:
+        assert grp.insertModel(path, float(spacing))
+        assert np.array_equal(np.concatenate([s.get_solid_mask() for s in grp.slabs], axis=0), want)
+    finally:
+        grp.close()
+    lat.close()
+
+
 _CONFIG1 = {}
 
 

@@ -81,12 +81,10 @@ def test_two_slabs_equal_one_gpu(tmp_path, q, bc_x, bc_yz, overlap):
         assert np.allclose(got_diag, want_diag, rtol=1e-10, atol=1e-9 * abs(want_diag[0]))   # fp64 sums, different order
 
 
-@pytest.mark.skipif(not os.environ.get("LBM_TEST_INPLACE_SLABS"),
-                    reason="single-buffer slabs are verified over gloo on the host build (tests/test_slab_gloo.py) but had not been "
-                           "run over NCCL when round 1 ended: opt in with LBM_TEST_INPLACE_SLABS=1 (under a timeout) for the first run")
 @pytest.mark.parametrize("q,bc_yz,steps", [(19, (2, 2), 9), (27, (1, 2), 6)])
 def test_two_single_buffer_slabs_equal_one_gpu(tmp_path, q, bc_yz, steps):
-    """one copy of the populations per slab: the edge planes travel before and after every odd step"""
+    """one copy of the populations per slab: the edge planes travel before and after every odd step (NCCL transport;
+    first run on two B200s in round 2, profiles/r02e_pytest_2gpu.log)"""
     import latticeboltzmanncuda_b200 as lb
     gx, Y, Z = 24, 10, 40
     rng = np.random.default_rng(5)

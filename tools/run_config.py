@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--size", type=int, default=0, help="override the edge length (taylor-green, cavity) for small trials")
     ap.add_argument("--engine", default="pull2", choices=["pull2", "inplace"])
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="slabs: peer-memory halos below the C ABI, or NCCL send/recv")
     args = ap.parse_args()
 
     import torch
@@ -117,9 +118,9 @@ def main():
         stepper = lat
     else:
         from latticeboltzmanncuda_b200.slab import SlabLattice
-        # (single-buffer slabs: verified over gloo on the host build, not yet measured over NCCL -- DESIGN.md section 4)
         stepper = SlabLattice(gx, gy, gz, lb.FluidData(1.0, tau), rank=rank, world=world, device=local, bc_x=P,
-                              bc_yz=(bc[1], bc[2]), **common, **({"engine": engine} if args.engine == "inplace" else {}))
+                              bc_yz=(bc[1], bc[2]), transport=args.transport, **common,
+                              **({"engine": engine} if args.engine == "inplace" else {}))
         lat = stepper.lattice
     live = gx * gy * gz
     if args.config == "obstacle":
@@ -176,17 +177,21 @@ def main():
     t_setup = time.perf_counter() - t_setup
     stepper.step(args.warmup)
     barrier()
+    if world > 1:
+        stepper.sync()
     # the energy baseline is taken after the warm-up steps: the state starts as a pure equilibrium and spends its
     # first steps growing the non-equilibrium part, which is not the decay being checked
     _, e0, _ = diagnostics()
     ms, launches = stepper.step_timed(args.steps)
     barrier()
     ms = allmax(ms)
+    if world > 1:
+        stepper.sync()
     mass1, e1, lid = diagnostics()
     cells = gx * gy * gz
     mlups = cells * args.steps / (ms * 1e-3) / 1e6
     out = {"config": name, "n_gpus": world, "engine": "in-place single buffer" if args.engine == "inplace" else "two-buffer fused pull",
-           "slab": "%dx%dx%d per GPU" % (nx, gy, gz), "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+           "transport": (args.transport if world > 1 else None), "slab": "%dx%dx%d per GPU" % (nx, gy, gz), "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
            "mlups": mlups, "mlups_per_gpu": mlups / world, "hbm_gbs_per_gpu": mlups / world * 1e6 * 152 / 1e9 * live / cells,
            "gpu_launches": int(launches), "state_gb_per_gpu": lat.layout().state_bytes * lat.layout().n_buffers / 1e9,
            "mass_drift_rel": (mass1 - mass0) / mass0, "setup_seconds": t_setup}
