@@ -40,6 +40,16 @@ def build_native(force=False, verbose=False, variant=None, defines=()):
     global_lib = LIB if not variant else os.path.join(HERE, "liblbm_b200.%s.so" % variant)
     if not variant and not force and not is_stale():
         return LIB
+    # several ranks of one job may find the library stale at the same moment: one builds, the others wait and re-check
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not variant and not force and not is_stale():
+            return LIB
+        return _build_locked(global_lib, variant, defines, verbose)
+
+
+def _build_locked(global_lib, variant, defines, verbose):
     nvcc = nvcc_path()
     common = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-fvisibility=hidden"] + ["-D" + d for d in defines]
@@ -55,7 +65,8 @@ def build_native(force=False, verbose=False, variant=None, defines=()):
     for pr in procs:
         if pr.wait() != 0:
             raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", global_lib] + objs, cwd=CSRC)
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", global_lib + ".tmp"] + objs, cwd=CSRC)
+    os.replace(global_lib + ".tmp", global_lib)          # never a half-written library under the final name
     return global_lib
 
 

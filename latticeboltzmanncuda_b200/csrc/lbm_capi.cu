@@ -1134,6 +1134,56 @@ LBM_API int lbm_step_phases(lbm_handle h, int n, unsigned phases)
     int rc = use(h);
     if (rc) return rc;
     if (n < 0 || (phases & ~15u) || phases == 0) return fail(LBM_ERR_INVALID, "bad step arguments");
+#if defined(__CUDACC__)
+    // Small lattices (BASELINE configs[0]: 64^3, a few launches of ~10 us per step) spend a visible part of a step between
+    // launches: for long runs two consecutive steps (the buffers / the storage form swap with the step parity) are
+    // captured once into a CUDA graph and replayed.  Only in the steady state: no slab neighbours (their handshake spans
+    // processes), solid words already settled, nothing pending.  LBM_STEP_GRAPH=0 switches it off, =1 forces it.
+    static const int graph_mode = [] { const char* e = getenv("LBM_STEP_GRAPH"); return e ? atoi(e) : -1; }();
+    const bool small = (long long)h->g.nx * h->g.ny * h->g.nz <= (1ll << 21);
+    if (graph_mode != 0 && (small || graph_mode == 1) && n >= 16 && !h->halo.connected && !h->pending_commit && !h->force32) {
+        int done = 0;
+        while (done < 4 && done < n) {            // settle dead words / first-step work outside the graph
+            if ((rc = one_step(h, phases))) return rc;
+            ++done;
+        }
+        const int pairs = (n - done) / 2;
+        if (pairs >= 4 && h->dead_dirty == 0 && !h->aa_dirty) {
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            const long long launches0 = h->launches;
+            if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                rc = one_step(h, phases);
+                if (!rc) rc = one_step(h, phases);
+                const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+                if (!rc && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                    const long long per_pair = h->launches - launches0;
+                    h->launches = launches0;          // (captured, not run)
+                    cudaError_t le = cudaSuccess;
+                    for (int k = 0; k < pairs && le == cudaSuccess; ++k) le = cudaGraphLaunch(exec, h->stream);
+                    cudaGraphExecDestroy(exec);
+                    cudaGraphDestroy(graph);
+                    if (le != cudaSuccess) return fail(LBM_ERR_CUDA, "graph launch: %s", cudaGetErrorString(le));
+                    h->launches += per_pair * pairs;
+                    done += 2 * pairs;
+                } else {
+                    if (graph) cudaGraphDestroy(graph);
+                    cudaGetLastError();
+                    if (rc) return rc;
+                    // nothing ran: the capture only recorded the two steps, and the host-side state (buffer roles, storage
+                    // form) flipped twice, i.e. is unchanged -- take the two steps for real
+                    h->launches = launches0;
+                    if ((rc = one_step(h, phases))) return rc;
+                    if ((rc = one_step(h, phases))) return rc;
+                    done += 2;
+                }
+            }
+        }
+        for (; done < n; ++done)
+            if ((rc = one_step(h, phases))) return rc;
+        return LBM_OK;
+    }
+#endif
     for (int s = 0; s < n; ++s)
         if ((rc = one_step(h, phases))) return rc;
     return LBM_OK;
