@@ -400,7 +400,8 @@ def run_ours(args):
             refmode = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
         # ---- BASELINE.json configs[0] on the GPU: 64^3, 1000 steps of the CLI loop in the reference's own mode.
-        # 2.6e5 cells fit the L2: this line is bound by launch latency, not by bandwidth.
+        # 2.6e5 cells are 512 blocks of work: too little to fill 148 SMs (a CUDA graph of the step changes nothing,
+        # profiles/r02_notes.md), so this line says nothing about bandwidth.
         n1, spacing1, flow1, obj1 = config1_inputs()
         l5 = lb.Lattice(n1, n1, n1, None, None, lb.FluidData(1.0, 1.0), spacing1, device=local)
         start = np.zeros(n1 ** 3, dtype=lb.LATTICE_POINT)
@@ -415,7 +416,7 @@ def run_ours(args):
         ms5, n5 = l5.step_timed(1000)
         config1 = {"workload": "BASELINE configs[0]: reference test geometry %d^3 D3Q27, reference mode, 1000 steps" % n1,
                    "mlups": n1 ** 3 * 1000 / (ms5 * 1e-3) / 1e6, "ms_per_step": ms5 / 1000, "launches_per_step": n5 / 1000,
-                   "note": "launch-latency bound (the lattice fits the L2)"}
+                   "note": "too small to fill the GPU (512 blocks per launch); not a bandwidth figure"}
         l5.close()
 
     out = None

@@ -1135,12 +1135,13 @@ LBM_API int lbm_step_phases(lbm_handle h, int n, unsigned phases)
     if (rc) return rc;
     if (n < 0 || (phases & ~15u) || phases == 0) return fail(LBM_ERR_INVALID, "bad step arguments");
 #if defined(__CUDACC__)
-    // Small lattices (BASELINE configs[0]: 64^3, a few launches of ~10 us per step) spend a visible part of a step between
-    // launches: for long runs two consecutive steps (the buffers / the storage form swap with the step parity) are
-    // captured once into a CUDA graph and replayed.  Only in the steady state: no slab neighbours (their handshake spans
-    // processes), solid words already settled, nothing pending.  LBM_STEP_GRAPH=0 switches it off, =1 forces it.
-    static const int graph_mode = [] { const char* e = getenv("LBM_STEP_GRAPH"); return e ? atoi(e) : -1; }();
-    const bool small = (long long)h->g.nx * h->g.ny * h->g.nz <= (1ll << 21);
+    // LBM_STEP_GRAPH=1: for long runs two consecutive steps (the buffers / the storage form swap with the step parity) are
+    // captured once into a CUDA graph and replayed -- tried for BASELINE configs[0] (64^3, three launches per step) and
+    // measured on B200 to change nothing (0.100-0.102 ms/step with the graph, 0.090-0.106 without,
+    // profiles/r02_notes.md): that lattice is too small to fill the GPU, it is not waiting for launches.  Off by default.
+    // Only in the steady state: no slab neighbours (their handshake spans processes), solid words settled, nothing pending.
+    static const int graph_mode = [] { const char* e = getenv("LBM_STEP_GRAPH"); return e ? atoi(e) : 0; }();
+    const bool small = false;
     if (graph_mode != 0 && (small || graph_mode == 1) && n >= 16 && !h->halo.connected && !h->pending_commit && !h->force32) {
         int done = 0;
         while (done < 4 && done < n) {            // settle dead words / first-step work outside the graph

@@ -35,6 +35,12 @@
 #ifndef LBM_AA_ODD_MINB
 #define LBM_AA_ODD_MINB 12      // blocks/SM of the D3Q19 fp32 odd interior kernel with obstacles (40 registers, no spills)
 #endif
+#ifndef LBM_AA_ODD_WARPS
+#define LBM_AA_ODD_WARPS 4      // z-words (warps) per block of the odd interior kernel
+#endif
+#ifndef LBM_AA_EVEN_THREADS
+#define LBM_AA_EVEN_THREADS 128 // threads per block of the even kernel along z
+#endif
 
 namespace lbm {
 
@@ -115,7 +121,7 @@ enum : unsigned { AA_ORDINARY = 0, AA_DEAD = 1, AA_SPECIAL = 2 };      // word c
 
 // EXTRA: the lattice has a solid mask and / or a source (kept out of the all-fluid instantiation)
 template <int Q, int MOMENT, bool EQ64, bool EXTRA>
-__global__ void __launch_bounds__(256, (Q == 19 && !EQ64) ? 6 : 4) aa_even_kernel(const __grid_constant__ InplaceParams p)
+__global__ void __launch_bounds__(LBM_AA_EVEN_THREADS > 256 ? LBM_AA_EVEN_THREADS : 256, ((Q == 19 && !EQ64) ? 6 : 4) * 256 / (LBM_AA_EVEN_THREADS > 256 ? LBM_AA_EVEN_THREADS : 256)) aa_even_kernel(const __grid_constant__ InplaceParams p)
 {
     const Geom& g = p.g;
     int x, y, z;
@@ -240,7 +246,8 @@ __device__ __forceinline__ void aa_odd_zedge_cell(const InplaceParams& p, float*
 // With geometry (EXTRA and a class array) all launches take the ordinary words only: all-solid words are
 // skipped and the special words are left to aa_odd_special_kernel.
 template <int Q, int MOMENT, bool EQ64, int MODE, bool EXTRA>
-__global__ void __launch_bounds__(128, (MODE == 0 && Q == 19 && !EQ64) ? (EXTRA ? LBM_AA_ODD_MINB : 12) : 8) aa_odd_kernel(const __grid_constant__ InplaceParams p)
+__global__ void __launch_bounds__(MODE == 0 ? 32 * LBM_AA_ODD_WARPS : 128,
+                                  (MODE == 0 && Q == 19 && !EQ64) ? (EXTRA ? LBM_AA_ODD_MINB : 12) * 4 / LBM_AA_ODD_WARPS : (MODE == 0 ? 8 * 4 / LBM_AA_ODD_WARPS : 8)) aa_odd_kernel(const __grid_constant__ InplaceParams p)
 {
     const Geom& g = p.g;
     const int wcount = (g.nz + 31) >> 5;
@@ -628,8 +635,8 @@ cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, cudaStream_t s
                 if (EXTRA && p.live_blocks) {
                     if (p.n_live > 0) { aa_odd_kernel<Q, MOMENT, EQ64, 0, EXTRA><<<(unsigned)p.n_live, 128, 0, stream>>>(p); ++n; }
                 } else {
-                    dim3 grid((wcount + 3) / 4, g.ny - 2, xi1 - xi0);
-                    aa_odd_kernel<Q, MOMENT, EQ64, 0, EXTRA><<<grid, 128, 0, stream>>>(pi);
+                    dim3 grid((wcount + LBM_AA_ODD_WARPS - 1) / LBM_AA_ODD_WARPS, g.ny - 2, xi1 - xi0);
+                    aa_odd_kernel<Q, MOMENT, EQ64, 0, EXTRA><<<grid, 32 * LBM_AA_ODD_WARPS, 0, stream>>>(pi);
                     ++n;
                 }
             }
@@ -650,8 +657,8 @@ cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, cudaStream_t s
         }
     } else {                    // arrived form -> local
         int bz = ((g.nz + 31) / 32) * 32;
-        if (bz > 128) bz = 128;
-        int by = 128 / bz;
+        if (bz > LBM_AA_EVEN_THREADS) bz = LBM_AA_EVEN_THREADS;
+        int by = bz >= 128 ? 1 : 128 / bz;
         if (by > g.ny) by = g.ny;
         dim3 block(bz, by, 1), grid((g.nz + bz - 1) / bz, (g.ny + by - 1) / by, p.x1 - p.x0);
         if (EXTRA && p.live_blocks) {
