@@ -208,6 +208,8 @@ int main(int argc, char** argv)
         Model m;
         m.importModel(dir + "/triangle.obj");
         EXPECT_EQ(m.number_of_vertices(), 3);
+        EXPECT_EQ(m.getMesh().number_of_vertices(), 3u);      // as the reference's test spells it (ModelTest.cpp:11)
+        EXPECT_EQ(m.getMesh().number_of_faces(), 1u);
         m.importModel(dir + "/cube.obj");
         EXPECT_TRUE(m.isModelClosed());
         EXPECT_TRUE(m.isPointInsideModel(Point_3(0.0, 0.0, 0.0)));

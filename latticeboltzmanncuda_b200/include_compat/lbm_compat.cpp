@@ -57,6 +57,12 @@ void Model::importModel(std::string filename)
     lbm_mesh_destroy(mesh_);
     mesh_ = nullptr;
     lbm_mesh_load(filename.c_str(), &mesh_);
+    int nv = 0, nf = 0;
+    modelMesh = Meshdata();
+    if (mesh_ && lbm_mesh_info(mesh_, &nv, &nf, nullptr, nullptr) == LBM_OK) {
+        modelMesh.vertices_ = (std::size_t)nv;
+        modelMesh.faces_ = (std::size_t)nf;
+    }
 }
 
 bool Model::isModelClosed()

@@ -118,6 +118,16 @@ struct BoundingBox {
     float zmax() const { return hi[2]; }
 };
 
+// What `Model::getMesh()` returns.  The reference hands out its CGAL::Surface_mesh (`inc/Model.h:14,32`); callers use it
+// for counts (`getMesh().number_of_vertices()`, test/ModelTest.cpp:11).  CGAL is not a dependency here, so this is a small
+// stand-in with the Surface_mesh member names for exactly that.
+struct Meshdata {
+    std::size_t number_of_vertices() const { return vertices_; }
+    std::size_t number_of_faces() const { return faces_; }
+    bool is_empty() const { return vertices_ == 0; }
+    std::size_t vertices_ = 0, faces_ = 0;
+};
+
 class Model {
 public:
     Model() = default;
@@ -128,7 +138,8 @@ public:
     void    importModel(std::string filename);
     bool    checkError();
     bool    isModelClosed();
-    int     number_of_vertices();                    // getMesh().number_of_vertices() in the reference's tests
+    const Meshdata& getMesh() const { return modelMesh; }     // counts of the imported mesh (Model.h:32)
+    int     number_of_vertices();                    // == getMesh().number_of_vertices()
     BoundingBox bounding_box();
     bool    isPointInsideModel(Point_3 point);
     Point_3 reflectionVector(Point_3 point_1, Point_3 point_2);
@@ -137,6 +148,7 @@ public:
 
 private:
     lbm_mesh_s* mesh_ = nullptr;
+    Meshdata modelMesh;
 };
 
 // ===================================================================================================
