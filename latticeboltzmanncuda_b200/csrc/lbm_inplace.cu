@@ -38,6 +38,9 @@
 #ifndef LBM_AA_ODD_WARPS
 #define LBM_AA_ODD_WARPS 4      // z-words (warps) per block of the odd interior kernel
 #endif
+#ifndef LBM_AA_SPC_MINB
+#define LBM_AA_SPC_MINB 8       // blocks/SM of the D3Q19 odd special-word kernel (64 registers)
+#endif
 #ifndef LBM_AA_EVEN_THREADS
 #define LBM_AA_EVEN_THREADS 128 // threads per block of the even kernel along z
 #endif
@@ -407,7 +410,7 @@ __device__ __forceinline__ void aa_odd_geo_cell(const InplaceParams& p, float* a
 // (solid and out-of-range lanes then stay for the warp sum; without it they leave at once -- keeping them cost the
 // kernel 0.09 ms of 0.41 in a measurement, hence the two instantiations).
 template <int Q, int MOMENT, bool EQ64, bool FORCE>
-__global__ void __launch_bounds__(128, Q == 19 ? 8 : 6) aa_odd_special_kernel(const __grid_constant__ InplaceParams p)
+__global__ void __launch_bounds__(128, Q == 19 ? LBM_AA_SPC_MINB : 6) aa_odd_special_kernel(const __grid_constant__ InplaceParams p)
 {
     const Geom& g = p.g;
     const unsigned lane = threadIdx.x & 31u;

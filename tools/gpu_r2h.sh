@@ -6,7 +6,7 @@ mkdir -p $O
 P=$PWD/latticeboltzmanncuda_b200
 {
 for rep in 1 2; do
-for v in default w2 w8 w16 mb10 mb16; do
+for v in default w2 w8 w16 mb10 mb16 spc10 spc12; do
   echo "== $v (rep $rep)"
   if [ $v = default ]; then LBM_PROBE_FORCE=1 timeout 60 python tools/perf_one.py inplace_obst 512 40
   else LBM_B200_LIB=$P/liblbm_b200.$v.so LBM_PROBE_FORCE=1 timeout 60 python tools/perf_one.py inplace_obst 512 40; fi
