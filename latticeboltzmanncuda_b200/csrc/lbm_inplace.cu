@@ -41,6 +41,12 @@
 #ifndef LBM_AA_SPC_MINB
 #define LBM_AA_SPC_MINB 8       // blocks/SM of the D3Q19 odd special-word kernel (64 registers)
 #endif
+#ifndef LBM_AA_EVEN_ROWS
+#define LBM_AA_EVEN_ROWS 1      // rows a thread of the even kernel takes at once (2: both rows' loads in flight before the first collision)
+#endif
+#ifndef LBM_AA_EVEN_ROWS_MINB
+#define LBM_AA_EVEN_ROWS_MINB 8
+#endif
 #ifndef LBM_AA_EVEN_THREADS
 #define LBM_AA_EVEN_THREADS 128 // threads per block of the even kernel along z
 #endif
@@ -159,6 +165,42 @@ __global__ void __launch_bounds__(LBM_AA_EVEN_THREADS > 256 ? LBM_AA_EVEN_THREAD
     asm volatile("" : "+l"(a));          // rebuild the Q addresses next to the stores instead of keeping them alive
 #pragma unroll
     for (int i = 0; i < Q; ++i) a[p.pop_off[dir_inv(i)]] = f[i];
+}
+
+// Experiment (LBM_AA_EVEN_ROWS = 2): a thread takes the same z of ROWS consecutive rows and issues the loads of all of
+// them before the first collision -- ROWS x Q requests in flight per thread at fewer resident warps.
+template <int Q, int MOMENT, bool EQ64, bool EXTRA, int ROWS>
+__global__ void __launch_bounds__(128, LBM_AA_EVEN_ROWS_MINB) aa_even_rows_kernel(const __grid_constant__ InplaceParams p)
+{
+    const Geom& g = p.g;
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = blockIdx.y * ROWS;
+    const int x = p.x0 + blockIdx.z;
+    if (z >= g.nz) return;
+    float* a = p.f + g.cell(x, y0, z);
+    float f[ROWS][Q];
+    bool live[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        live[r] = y0 + r < g.ny;
+        if (EXTRA && p.solid && live[r]) live[r] = !solid_bit(p, x + 1, y0 + r + 1, z + PAD_Z);
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+        if (live[r]) {
+#pragma unroll
+            for (int i = 0; i < Q; ++i) f[r][i] = a[p.pop_off[i] + r * g.zp];
+        }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+        if (live[r]) {
+            if (EQ64) collide_fp64<Q, MOMENT>(f[r], p.tau);
+            else      collide_fp32<Q, MOMENT>(f[r], p.inv_tau);
+            if (EXTRA && p.src_on) add_source<Q>(p, f[r], x, y0 + r, z);
+            asm volatile("" : "+l"(a));
+#pragma unroll
+            for (int i = 0; i < Q; ++i) a[p.park_off[i] + r * g.zp] = f[r][i];
+        }
 }
 
 // pull + collide + push of one cell that may sit on a domain edge of the axes in AXES
@@ -664,7 +706,11 @@ cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, cudaStream_t s
         int by = bz >= 128 ? 1 : 128 / bz;
         if (by > g.ny) by = g.ny;
         dim3 block(bz, by, 1), grid((g.nz + bz - 1) / bz, (g.ny + by - 1) / by, p.x1 - p.x0);
-        if (EXTRA && p.live_blocks) {
+        if (LBM_AA_EVEN_ROWS > 1 && bz == 128 && !(p.force && !p.force_pending)) {
+            dim3 grid2((g.nz + 127) / 128, (g.ny + LBM_AA_EVEN_ROWS - 1) / LBM_AA_EVEN_ROWS, p.x1 - p.x0);
+            aa_even_rows_kernel<Q, MOMENT, EQ64, EXTRA, LBM_AA_EVEN_ROWS><<<grid2, 128, 0, stream>>>(p);
+            ++n;
+        } else if (EXTRA && p.live_blocks) {
             if (p.n_live > 0) { aa_even_kernel<Q, MOMENT, EQ64, EXTRA><<<(unsigned)p.n_live, 128, 0, stream>>>(p); ++n; }
         } else {
             aa_even_kernel<Q, MOMENT, EQ64, EXTRA><<<grid, block, 0, stream>>>(p);

@@ -202,6 +202,9 @@ __device__ __noinline__ float moving_wall_term(const StepParams& p, int i, int x
 #ifndef LBM_GEN_PREFETCH
 #define LBM_GEN_PREFETCH 0     // experiment: per-lane prefetch.global.L2 of the next row's lines. Measured on B200: 2.08 -> 3.08 ms
 #endif                         // (19 divergent requests per instruction load the L1 request path; profiles/r01_notes.md)
+#ifndef LBM_GEN_PAIR
+#define LBM_GEN_PAIR 0         // experiment: two ordinary rows at once, both rows' pulls issued before the first collision
+#endif
 #ifndef LBM_SPC_PREFETCH
 #define LBM_SPC_PREFETCH 0     // the same for the next list entry of the special kernel: 0.35 -> 0.46 ms
 #endif
@@ -397,6 +400,28 @@ __global__ void __launch_bounds__(32 * LBM_GEN_WARPS, LBM_GEN_MINB) step_general
 #endif
         if (cls == CLS_SPECIAL) continue;              // step_special_kernel owns these words
         const long long idx = ((long long)(x + 1) * g.yp + (y + 1)) * g.zp + (z + PAD_Z);
+#if LBM_GEN_PAIR
+        // software pipelining by hand: when this row and the next are both ordinary, the 2 x Q pulls of both rows are in
+        // flight before the first collision starts (the kernel waits for memory: 9.8 warps per issue on the long scoreboard)
+        if (!SRC && (r & 1) == 0 && r + 1 < ROWS_PER_WARP && y + 1 < g.ny && do_stream && (p.phases & PH_COLLIDE) && cls == CLS_ORDINARY &&
+            ((unsigned)(((ROWS_PER_WARP > 8 && r + 1 >= 8) ? cw1 : cw0) >> (8 * ((r + 1) & 7))) & 0xffu) == CLS_ORDINARY) {
+            const bool edge = wi == 0 || wi == wcount - 1;
+            float f0[Q], f1[Q];
+            pull_populations<Q>(p, p.fin + idx, x, y, z, edge, f0);
+            pull_populations<Q>(p, p.fin + idx + g.zp, x, y + 1, z, edge, f1);
+            if (EQ64) { collide_fp64<Q, MOMENT>(f0, p.tau); collide_fp64<Q, MOMENT>(f1, p.tau); }
+            else      { collide_fp32<Q, MOMENT>(f0, p.inv_tau); collide_fp32<Q, MOMENT>(f1, p.inv_tau); }
+            if (active) {
+                float* __restrict__ fo = p.fout + idx;
+#pragma unroll
+                for (int i = 0; i < Q; ++i) st_pop(fo + p.pop_off[i], f0[i]);
+#pragma unroll
+                for (int i = 0; i < Q; ++i) st_pop(fo + p.pop_off[i] + g.zp, f1[i]);
+            }
+            ++r;
+            continue;
+        }
+#endif
         float f[Q];
         bool dead = false;
         if (cls == CLS_DEAD && p.dead_mode) {
