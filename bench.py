@@ -418,6 +418,22 @@ def run_ours(args):
                    "mlups": n1 ** 3 * 1000 / (ms5 * 1e-3) / 1e6, "ms_per_step": ms5 / 1000, "launches_per_step": n5 / 1000,
                    "note": "too small to fill the GPU (512 blocks per launch); not a bandwidth figure"}
         l5.close()
+        # the same configuration through the C++ drop-in: the reference's `main` rebuilt against the compatibility headers
+        # (include_compat/lbm_cli.cpp), its step loop timed by the program itself, force trace printed every 100 steps
+        cli = os.path.join(ROOT, "latticeboltzmanncuda_b200", "include_compat", "lbm_cli")
+        if os.path.exists(cli):
+            import re
+            import subprocess
+            try:
+                res = subprocess.run([cli, obj1, "8", "8", "8", str(n1 // 8), str(n1 // 8), str(n1 // 8), "1.0", "1.0", repr(spacing1), "1000",
+                                      "100", "--time", "1"], capture_output=True, text=True, timeout=300)
+                m = re.search(r"in ([0-9.]+) s = ([0-9.]+) MLUPS", res.stderr)
+                if m:
+                    config1["cpp_cli"] = {"seconds": float(m.group(1)), "mlups": float(m.group(2)),
+                                          "what": "lbm_cli (the reference's main on the C++ compatibility layer), 1000 steps, four "
+                                                  "simulate* calls per step fused into one, force read back every 100 steps"}
+            except Exception as exc:      # noqa: BLE001
+                config1["cpp_cli"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     out = None
     if rank == 0:

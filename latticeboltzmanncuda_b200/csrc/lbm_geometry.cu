@@ -225,28 +225,26 @@ LBM_HD void rotate_cs(const float axis_in[3], const float vec[3], float c, float
 
 struct HalfTurn { float c, s, cn, sn; };   // cos / sin of +pi/2 and -pi/2 as the host's libm rounds them
 
-// Model::reflectionVector: mirror of the incoming direction about the first facet the ray p1 -> p2 hits
-LBM_HD void reflection_vector(const MeshView& m, const float p1[3], const float p2[3], HalfTurn ht, float out[3])
+// one triangle of the first-hit search of Model::reflectionVector (AABB_tree::first_intersection in the reference)
+LBM_HD void first_hit_consider(const MeshView& m, int f, const double o[3], const double dir[3], int& best, double& best_t)
+{
+    double t;
+    const int r = ray_triangle(m, f, o, dir, &t);
+    if (r == 0) return;
+    if (r == 2) {
+        double a[3], b[3], c[3], e1[3], e2[3], n[3];
+        load_tri(m, f, a, b, c);
+        for (int k = 0; k < 3; ++k) { e1[k] = b[k] - a[k]; e2[k] = c[k] - a[k]; }
+        cross(e1, e2, n);
+        if (fabs(dot(n, dir)) <= 1e-12 * sqrt(dot(n, n) * dot(dir, dir))) return;   // in-plane ray: no usable hit
+    }
+    if (best < 0 || t < best_t - 1e-12) { best = f; best_t = t; }
+}
+
+// the mirror of the incoming direction p1 -> p2 about facet `best` (none: the zero vector)
+LBM_HD void mirror_about_facet(const MeshView& m, int best, const float p1[3], const float p2[3], HalfTurn ht, float out[3])
 {
     out[0] = out[1] = out[2] = 0.0f;
-    if (m.nf == 0) return;
-    const double o[3] = {p1[0], p1[1], p1[2]};
-    const double dir[3] = {(double)p2[0] - p1[0], (double)p2[1] - p1[1], (double)p2[2] - p1[2]};
-    int best = -1;
-    double best_t = 0.0;
-    for (int f = 0; f < m.nf; ++f) {
-        double t;
-        const int r = ray_triangle(m, f, o, dir, &t);
-        if (r == 0) continue;
-        if (r == 2) {
-            double a[3], b[3], c[3], e1[3], e2[3], n[3];
-            load_tri(m, f, a, b, c);
-            for (int k = 0; k < 3; ++k) { e1[k] = b[k] - a[k]; e2[k] = c[k] - a[k]; }
-            cross(e1, e2, n);
-            if (fabs(dot(n, dir)) <= 1e-12 * sqrt(dot(n, n) * dot(dir, dir))) continue;   // in-plane ray: no usable hit
-        }
-        if (best < 0 || t < best_t - 1e-12) { best = f; best_t = t; }
-    }
     float vx = p1[0] - p2[0], vy = p1[1] - p2[1], vz = p1[2] - p2[2];
     const float norm = sqrtf((vx * vx) + (vy * vy) + (vz * vz));
     vx /= norm; vy /= norm; vz /= norm;
@@ -262,6 +260,49 @@ LBM_HD void reflection_vector(const MeshView& m, const float p1[3], const float 
     if (nl != 0.0f) { n[0] /= nl; n[1] /= nl; n[2] /= nl; }
     const float v[3] = {vx, vy, vz};
     rotate_cs(n, v, ht.c, ht.s, ht.cn, ht.sn, out);
+}
+
+// Model::reflectionVector: mirror of the incoming direction about the first facet the ray p1 -> p2 hits
+LBM_HD void reflection_vector(const MeshView& m, const float p1[3], const float p2[3], HalfTurn ht, float out[3])
+{
+    out[0] = out[1] = out[2] = 0.0f;
+    if (m.nf == 0) return;
+    const double o[3] = {p1[0], p1[1], p1[2]};
+    const double dir[3] = {(double)p2[0] - p1[0], (double)p2[1] - p1[1], (double)p2[2] - p1[2]};
+    int best = -1;
+    double best_t = 0.0;
+    for (int f = 0; f < m.nf; ++f) first_hit_consider(m, f, o, dir, best, best_t);
+    mirror_about_facet(m, best, p1, p2, ht, out);
+}
+
+// The same for a ray between two NEIGHBOURING lattice points with the triangles binned per lattice column.  A triangle
+// that the ray meets between the two points (t <= 1) covers, in xy, a point of the segment between two adjacent columns,
+// and every column's bin reaches one column further than the triangle's box: it is in the bin of p1's column or of p2's.
+// So the two bins are searched first, in ascending triangle order like the full loop (ties go to the lower index); a
+// hit at t <= 1 found there is the first hit of the whole mesh.  Only a ray that meets nothing between the two points
+// (it then runs on through other columns) takes the full loop.
+LBM_HD void reflection_vector_binned(const MeshView& m, const float p1[3], const float p2[3], HalfTurn ht, float out[3],
+                                     const int* bin1, int n1, const int* bin2, int n2)
+{
+    out[0] = out[1] = out[2] = 0.0f;
+    if (m.nf == 0) return;
+    const double o[3] = {p1[0], p1[1], p1[2]};
+    const double dir[3] = {(double)p2[0] - p1[0], (double)p2[1] - p1[1], (double)p2[2] - p1[2]};
+    int best = -1;
+    double best_t = 0.0;
+    int i = 0, j = 0;
+    while (i < n1 || j < n2) {                 // merge of two ascending lists, every triangle once
+        int f;
+        if (j >= n2 || (i < n1 && bin1[i] <= bin2[j])) { f = bin1[i]; if (j < n2 && bin2[j] == f) ++j; ++i; }
+        else { f = bin2[j]; ++j; }
+        first_hit_consider(m, f, o, dir, best, best_t);
+    }
+    if (best < 0 || best_t > 1.0 - 1e-9) {     // nothing (safely) between the two points: ask the whole mesh
+        best = -1;
+        best_t = 0.0;
+        for (int f = 0; f < m.nf; ++f) first_hit_consider(m, f, o, dir, best, best_t);
+    }
+    mirror_about_facet(m, best, p1, p2, ht, out);
 }
 
 // Lattice::distributeVector: the 27 unit directions ranked by 2 - distance, ties broken towards the
@@ -354,7 +395,7 @@ struct TableRecord {       // ReflectionValues, simulation/include/LatticePoint.
 // (slabs: the array holds the planes x_origin .. x_origin + nx - 1 of the lattice; positions use the global index)
 __global__ void table_kernel(MeshView m, const uint8_t* __restrict__ solid, const long long* __restrict__ cells, int ncells,
                              TableRecord* __restrict__ tables, uint8_t* __restrict__ reflected, int nx, int ny, int nz,
-                             float spacing, HalfTurn ht, int x_origin)
+                             float spacing, HalfTurn ht, int x_origin, const int* __restrict__ col_start, const int* __restrict__ col_tris)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
@@ -372,7 +413,13 @@ __global__ void table_kernel(MeshView m, const uint8_t* __restrict__ solid, cons
         const float p2[3] = {spacing * (x + x_origin), spacing * y, spacing * z};
         float r[3], scores[27];
         int dirs[27];
-        reflection_vector(m, p1, p2, ht, r);
+        if (col_start) {
+            const int c1 = nxp * ny + nyp, c2 = x * ny + y;          // columns of the fluid neighbour and of this cell
+            reflection_vector_binned(m, p1, p2, ht, r, col_tris + col_start[c1], col_start[c1 + 1] - col_start[c1],
+                                     col_tris + col_start[c2], col_start[c2 + 1] - col_start[c2]);
+        } else {
+            reflection_vector(m, p1, p2, ht, r);
+        }
         distribute_vector(r, scores, dirs);
         int counter = 0;
         float norm = 0.0f;
@@ -602,73 +649,94 @@ LBM_API unsigned lbm_compress_ints(const int* array, int num, int bit_length)
     return out;
 }
 
-// Voxelises the planes x_origin .. x_origin + nxv - 1 (global indices) into `bytes` ([nxv][ny][nz], device).  The triangles
-// are binned per lattice column on the host (each triangle goes to the columns its inflated xy bounding box covers, plus
-// one column all round for the rounding of index * spacing), so the device loop over a cell sees only the triangles above
-// and below it.  Meshes whose bins would not fit (huge triangles on a huge lattice) take the all-pairs kernel.
-static int voxelise_planes(lbm_handle h, lbm_mesh m, const MeshView& v, uint8_t* bytes, int nxv, int x_origin, int gx, float spacing)
+// The triangles of a mesh binned per lattice column (x, y) of the planes x_origin .. x_origin + nxv - 1 (global indices):
+// each triangle goes to the columns its inflated xy bounding box covers plus one column all round (rounding of
+// index * spacing; the table builder relies on that extra column too).  CSR on the device + the list of triangles
+// parallel to the z axis.  `ok` false: no bins (empty or invalid mesh, switched off, or they would not fit).
+struct DeviceBins {
+    int *start = nullptr, *tris = nullptr, *vert = nullptr;
+    int nvert = 0;
+    bool ok = false;
+    void release() { cudaFree(start); cudaFree(tris); cudaFree(vert); start = tris = vert = nullptr; ok = false; }
+};
+
+static int build_bins(lbm_handle h, lbm_mesh m, int nxv, int x_origin, float spacing, DeviceBins* out)
 {
-    const Geom& g = h->g;
-    const int ny = g.ny, nz = g.nz;
-    const size_t n = (size_t)nxv * ny * nz;
+    const int ny = h->g.ny;
     static const bool binned = [] { const char* e = getenv("LBM_VOXELISE_BINNED"); return e ? atoi(e) != 0 : true; }();
     const int nf = (int)(m->tri.size() / 3);
     const size_t ncol = (size_t)nxv * ny;
+    if (!binned || nf == 0 || !m->valid || !m->loaded) return LBM_OK;
     std::vector<int> count(ncol + 1, 0), vertical;
     std::vector<int> lo_x(nf), hi_x(nf), lo_y(nf), hi_y(nf);
     size_t entries = 0;
-    bool use_bins = binned && nf > 0 && m->valid;
-    if (use_bins) {
-        const MeshView hv = host_view(m);
-        for (int f = 0; f < nf; ++f) {
-            if (parallel_to_z(hv, f)) vertical.push_back(f);
-            double bl[3] = {1e300, 1e300, 1e300}, bh[3] = {-1e300, -1e300, -1e300};
-            for (int c = 0; c < 3; ++c)
-                for (int a = 0; a < 3; ++a) {
-                    const double w = m->v[(size_t)m->tri[3 * f + c] * 3 + a];
-                    bl[a] = std::min(bl[a], w); bh[a] = std::max(bh[a], w);
-                }
-            const double diag = sqrt((bh[0] - bl[0]) * (bh[0] - bl[0]) + (bh[1] - bl[1]) * (bh[1] - bl[1]) + (bh[2] - bl[2]) * (bh[2] - bl[2]));
-            const double margin = 1e-6 * (diag + fabs(bl[0]) + fabs(bh[0]) + fabs(bl[1]) + fabs(bh[1])) + 1e-30;
-            // columns whose lattice point can lie within the inflated box, one more on each side for rounding
-            const long long ax = (long long)floor((bl[0] - margin) / spacing) - 1 - x_origin, bx = (long long)ceil((bh[0] + margin) / spacing) + 1 - x_origin;
-            const long long ay = (long long)floor((bl[1] - margin) / spacing) - 1, by = (long long)ceil((bh[1] + margin) / spacing) + 1;
-            lo_x[f] = (int)std::max<long long>(ax, 0); hi_x[f] = (int)std::min<long long>(bx, nxv - 1);
-            lo_y[f] = (int)std::max<long long>(ay, 0); hi_y[f] = (int)std::min<long long>(by, ny - 1);
-            if (hi_x[f] < lo_x[f] || hi_y[f] < lo_y[f]) continue;
-            entries += (size_t)(hi_x[f] - lo_x[f] + 1) * (size_t)(hi_y[f] - lo_y[f] + 1);
-        }
-        if (entries > (size_t(64) << 20)) use_bins = false;
+    const MeshView hv = host_view(m);
+    for (int f = 0; f < nf; ++f) {
+        if (parallel_to_z(hv, f)) vertical.push_back(f);
+        double bl[3] = {1e300, 1e300, 1e300}, bh[3] = {-1e300, -1e300, -1e300};
+        for (int c = 0; c < 3; ++c)
+            for (int a = 0; a < 3; ++a) {
+                const double w = m->v[(size_t)m->tri[3 * f + c] * 3 + a];
+                bl[a] = std::min(bl[a], w); bh[a] = std::max(bh[a], w);
+            }
+        const double diag = sqrt((bh[0] - bl[0]) * (bh[0] - bl[0]) + (bh[1] - bl[1]) * (bh[1] - bl[1]) + (bh[2] - bl[2]) * (bh[2] - bl[2]));
+        const double margin = 1e-6 * (diag + fabs(bl[0]) + fabs(bh[0]) + fabs(bl[1]) + fabs(bh[1])) + 1e-30;
+        // columns whose lattice point can lie within the inflated box, one more on each side
+        const long long ax = (long long)floor((bl[0] - margin) / spacing) - 1 - x_origin, bx = (long long)ceil((bh[0] + margin) / spacing) + 1 - x_origin;
+        const long long ay = (long long)floor((bl[1] - margin) / spacing) - 1, by = (long long)ceil((bh[1] + margin) / spacing) + 1;
+        lo_x[f] = (int)std::max<long long>(ax, 0); hi_x[f] = (int)std::min<long long>(bx, nxv - 1);
+        lo_y[f] = (int)std::max<long long>(ay, 0); hi_y[f] = (int)std::min<long long>(by, ny - 1);
+        if (hi_x[f] < lo_x[f] || hi_y[f] < lo_y[f]) continue;
+        entries += (size_t)(hi_x[f] - lo_x[f] + 1) * (size_t)(hi_y[f] - lo_y[f] + 1);
     }
-    if (!use_bins) {
-        voxelise_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(v, bytes, nxv, ny, nz, spacing, x_origin, gx);
-        GCK(cudaGetLastError());
-        return LBM_OK;
-    }
+    if (entries > (size_t(64) << 20)) return LBM_OK;          // huge triangles on a huge lattice: all-pairs kernels
     for (int f = 0; f < nf; ++f)
         for (int x = lo_x[f]; x <= hi_x[f]; ++x)
             for (int y = lo_y[f]; y <= hi_y[f]; ++y) ++count[(size_t)x * ny + y + 1];
     for (size_t c = 0; c < ncol; ++c) count[c + 1] += count[c];
     std::vector<int> tris(entries ? entries : 1), fill(count.begin(), count.end() - 1);
-    for (int f = 0; f < nf; ++f)             // ascending triangle order within a column, like the all-pairs loop
+    for (int f = 0; f < nf; ++f)             // ascending triangle order within a column, like the all-pairs loops
         for (int x = lo_x[f]; x <= hi_x[f]; ++x)
             for (int y = lo_y[f]; y <= hi_y[f]; ++y) tris[(size_t)fill[(size_t)x * ny + y]++] = f;
-    int *d_start = nullptr, *d_tris = nullptr, *d_vert = nullptr;
-    cudaError_t e = cudaMalloc(&d_start, count.size() * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc(&d_tris, tris.size() * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc(&d_vert, (vertical.size() + 1) * sizeof(int));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_start, count.data(), count.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tris, tris.data(), tris.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    cudaError_t e = cudaMalloc(&out->start, count.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&out->tris, tris.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&out->vert, (vertical.size() + 1) * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out->start, count.data(), count.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out->tris, tris.data(), tris.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess && !vertical.empty())
-        e = cudaMemcpyAsync(d_vert, vertical.data(), vertical.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) {
-        voxelise_binned_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(v, d_start, d_tris, d_vert, (int)vertical.size(), bytes,
-                                                                              nxv, ny, nz, spacing, x_origin, gx);
-        e = cudaGetLastError();
+        e = cudaMemcpyAsync(out->vert, vertical.data(), vertical.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);      // the host vectors go away here
+    if (e != cudaSuccess) {
+        out->release();
+        return lbm_internal_fail(e == cudaErrorMemoryAllocation ? LBM_ERR_NOMEM : LBM_ERR_CUDA, cudaGetErrorString(e));
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);      // the host vectors and the bins go away here
-    cudaFree(d_start); cudaFree(d_tris); cudaFree(d_vert);
-    if (e != cudaSuccess) return lbm_internal_fail(e == cudaErrorMemoryAllocation ? LBM_ERR_NOMEM : LBM_ERR_CUDA, cudaGetErrorString(e));
+    out->nvert = (int)vertical.size();
+    out->ok = true;
+    return LBM_OK;
+}
+
+// Voxelises the planes x_origin .. x_origin + nxv - 1 (global indices) into `bytes` ([nxv][ny][nz], device): with the bins a
+// cell looks at the triangles over its column only, without them at the whole mesh.  `keep` (optional) receives the bins.
+static int voxelise_planes(lbm_handle h, lbm_mesh m, const MeshView& v, uint8_t* bytes, int nxv, int x_origin, int gx, float spacing,
+                           DeviceBins* keep = nullptr)
+{
+    const Geom& g = h->g;
+    const size_t n = (size_t)nxv * g.ny * g.nz;
+    DeviceBins bins;
+    int rc = build_bins(h, m, nxv, x_origin, spacing, &bins);
+    if (rc) return rc;
+    if (bins.ok)
+        voxelise_binned_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(v, bins.start, bins.tris, bins.vert, bins.nvert, bytes,
+                                                                              nxv, g.ny, g.nz, spacing, x_origin, gx);
+    else
+        voxelise_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(v, bytes, nxv, g.ny, g.nz, spacing, x_origin, gx);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (keep) *keep = bins; else bins.release();
+    if (e != cudaSuccess) {
+        if (keep) { keep->release(); }
+        return lbm_internal_fail(LBM_ERR_CUDA, cudaGetErrorString(e));
+    }
     return LBM_OK;
 }
 
@@ -727,17 +795,19 @@ LBM_API int lbm_preprocess_model(lbm_handle h, lbm_mesh m, float spacing)
     const size_t per = (size_t)g.ny * g.nz;
     const size_t n = (size_t)bx * per;
     uint8_t* box = nullptr;          // solid flags of the box
+    DeviceBins bins;                 // the triangles per lattice column of the box (first-hit searches look at two columns)
     if (slab) {
         GCK(cudaMalloc(&box, n));
         MeshView vv = v;
         if (!m->loaded) vv.nf = 0;
-        if ((rc = voxelise_planes(h, m, vv, box, bx, xa, h->slab_gx, spacing))) { cudaFree(box); return rc; }
+        if ((rc = voxelise_planes(h, m, vv, box, bx, xa, h->slab_gx, spacing, &bins))) { cudaFree(box); return rc; }
     } else {
         if (!h->solid_bytes) GCK(cudaMalloc(&h->solid_bytes, n + 2 * per));
         GCK(launch_mask_to_bytes(h->solid, h->solid_bytes, g, h->stream));
         box = h->solid_bytes;
+        if ((rc = build_bins(h, m, bx, xa, spacing, &bins))) return rc;
     }
-    auto drop_box = [&] { if (slab) cudaFree(box); };
+    auto drop_box = [&] { if (slab) cudaFree(box); bins.release(); };
     uint8_t* d_cand = nullptr;
     cudaError_t e = cudaMalloc(&d_cand, n);
     if (e != cudaSuccess) { drop_box(); return lbm_internal_fail(LBM_ERR_NOMEM, cudaGetErrorString(e)); }
@@ -768,7 +838,8 @@ LBM_API int lbm_preprocess_model(lbm_handle h, lbm_mesh m, float spacing)
     std::vector<TableRecord> tables(nc);
     std::vector<uint8_t> refl(nc);
     if (e == cudaSuccess) {
-        table_kernel<<<(nc + 63) / 64, 64, 0, h->stream>>>(v, box, d_cells, nc, d_tables, d_refl, bx, g.ny, g.nz, spacing, half_turn(), xa);
+        table_kernel<<<(nc + 63) / 64, 64, 0, h->stream>>>(v, box, d_cells, nc, d_tables, d_refl, bx, g.ny, g.nz, spacing, half_turn(), xa,
+                                                           bins.ok ? bins.start : nullptr, bins.ok ? bins.tris : nullptr);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(tables.data(), d_tables, nc * sizeof(TableRecord), cudaMemcpyDeviceToHost, h->stream);

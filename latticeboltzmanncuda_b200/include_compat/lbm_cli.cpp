@@ -2,18 +2,20 @@
 //
 //   lbm_cli <model.obj> <threads x y z> <blocks x y z> <fluid density> <tau> <lattice spacing> <steps> [print_every]
 //           [--gpus N] [--q 19|27] [--boundary reflect|bounce] [--bc zpw] [--moments reference|standard]
-//           [--eq fp64|fp32] [--engine pull2|inplace]
+//           [--eq fp64|fp32] [--engine pull2|inplace] [--time 1]
 //
 // The eleven positional arguments are the reference's; the named options select what the reference has no switch for
 // (SURVEY.md section 5): x slabs across N GPUs of this process (peer-memory halos), the velocity set, the boundary model,
 // the edge rule per axis (one letter each: z zero inflow, p periodic, w wall), the velocity moment, the arithmetic of the
 // equilibrium and the streaming engine.  Defaults = the reference's behaviour on one GPU (or the LBM_* environment
-// variables, Lattice::Options::fromEnvironment).
+// variables, Lattice::Options::fromEnvironment).  --time 1 writes the seconds the step loop took (device work finished) and
+// the lattice-cell updates per second to stderr; stdout stays the reference's force trace.
 //
 // The lattice is threads * blocks cells per axis; every population starts at 0.001 and the +x population at 0.002;
 // the same values are injected on the plane x == 0 after every step; the force accumulated on the body is written
 // as one "Fx Fy Fz" line before each step.  The optional 12th argument prints that line every K steps only (the
 // reference blocks on a device-to-host copy every step; 0 = never).
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -31,6 +33,7 @@ struct Options {
     dim3 threads, blocks;
     float density = 1.0f, tau = 1.0f, spacing = 1.0f;
     int steps = 0, print_every = 1;
+    bool time_loop = false;
     Lattice::Options lattice = Lattice::Options::fromEnvironment();
     int nx() const { return (int)(threads.x * blocks.x); }
     int ny() const { return (int)(threads.y * blocks.y); }
@@ -46,7 +49,8 @@ bool parse(int argc_all, char* argv_all[], Options& o)
         if (a.rfind("--", 0) != 0) { pos.push_back(argv_all[k]); continue; }
         if (k + 1 >= argc_all) return false;
         const std::string v = argv_all[++k];
-        if (a == "--gpus") o.lattice.gpus = std::atoi(v.c_str()) > 0 ? std::atoi(v.c_str()) : 1;
+        if (a == "--time") o.time_loop = std::atoi(v.c_str()) != 0;
+        else if (a == "--gpus") o.lattice.gpus = std::atoi(v.c_str()) > 0 ? std::atoi(v.c_str()) : 1;
         else if (a == "--q") { if (v != "19" && v != "27") return false; o.lattice.q = std::atoi(v.c_str()); }
         else if (a == "--boundary") { if (v != "reflect" && v != "bounce") return false; o.lattice.boundary_mode = v == "bounce"; }
         else if (a == "--moments") { if (v != "reference" && v != "standard") return false; o.lattice.moment_mode = v == "standard"; }
@@ -119,6 +123,8 @@ int main(int argc, char* argv[])
 
     RunCudaFunctions::run_prime_points(o.blocks, o.threads, LatticeData(lattice.getCudaDataPointer(), lattice.getDimensions()));
 
+    lattice.synchronize();
+    const auto t0 = std::chrono::steady_clock::now();
     for (int step = 0; step < o.steps; ++step) {
         if (o.print_every > 0 && step % o.print_every == 0) {
             const ReflectionData* f = lattice.retrieve_reflection_data();
@@ -130,5 +136,10 @@ int main(int argc, char* argv[])
         lattice.simulateFlow();
     }
     lattice.synchronize();
+    if (o.time_loop) {
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::fprintf(stderr, "lbm_cli: %d steps of %dx%dx%d in %.6f s = %.1f MLUPS on %d GPU(s)\n", o.steps, o.nx(), o.ny(), o.nz(), sec,
+                     (double)o.nx() * o.ny() * o.nz() * o.steps / sec / 1e6, lattice.deviceCount());
+    }
     return 0;
 }

@@ -158,6 +158,31 @@ def test_voxeliser_scales_with_the_mesh(tmp_path):
     lat.close()
 
 
+ICO_TABLE_CASE = (int(os.environ.get("LBM_ICO_TABLE_LEVEL", "5")), int(os.environ.get("LBM_ICO_TABLE_N", "64")))
+
+
+def test_table_builder_with_a_large_mesh(tmp_path):
+    """the reflection tables of a 20 480-triangle icosphere at 64^3: the GPU builder searches the first facet a link's ray hits in
+    the bins of the two lattice columns the link spans (the whole mesh only when nothing lies between the two points);
+    the oracle tests every triangle for every link.  Same cells, same packed directions, same weights, bit for bit."""
+    level, n = ICO_TABLE_CASE
+    path, nf = _icosphere(tmp_path, level)
+    spacing = np.float32(1.0 / n)
+    cells = O.new_cells(n, n, n)
+    mesh = O.Mesh(path)
+    assert mesh.insert(cells, n, n, n, spacing) == 1
+    tables, tindex = mesh.preprocess(cells, n, n, n, spacing)
+    lat = make(n, n, n, float(spacing))
+    assert lat.insertModel(path)
+    lat.preProcessModel()
+    got_t, got_k = lat.reflection_tables()
+    assert len(got_k) > 100
+    assert np.array_equal(got_k, np.nonzero(tindex >= 0)[0])
+    assert np.array_equal(got_t["dirs"], tables["dirs"])
+    assert np.array_equal(got_t["w"], tables["w"])
+    lat.close()
+
+
 _CONFIG1 = {}
 
 
