@@ -465,6 +465,9 @@ def run_ours(args):
             "config": {"workload": wl, "cells_per_gpu": nx * gy * gz, "live_cells_per_gpu": live_total // world, "tau": tau,
                        "engine": eng_name, "transport": (args.transport if world > 1 else None),
                        "counting": "value counts live (non-solid) cell updates only; mlups_all_cells counts every lattice cell",
+                       "parity": "extension of the reference (D3Q19, half-way bounce-back, periodic / wall edges: the reference has "
+                                 "D3Q27, table reflection and zero-inflow edges only), checked against the CPU oracle; the reference's "
+                                 "own mode on this library is `reference_mode`, checked against the reference's kernels",
                        "l2": "state per GPU %.1f GB >> 126 MB L2, no flush needed" % state_gb},
             "gpu_launches": int(launches),
             "live_cells": live_total, "mlups_all_cells": cells_total * args.steps / (ms * 1e-3) / 1e6,
