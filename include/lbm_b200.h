@@ -95,15 +95,15 @@ enum lbm_source_kind { LBM_SOURCE_NONE = 0, LBM_SOURCE_BOX = 1 };
 
 /* streaming engine.  PULL2 keeps two copies of the populations (A -> B) and runs everything.
  * INPLACE is the single-buffer AA pattern (half the footprint, same traffic): fused
- * stream + collide steps (lbm_step / lbm_step_phases with STREAM and COLLIDE set) on one GPU,
- * periodic or wall edges (LBM_BC_HALO on x for slabs: the caller moves the edge planes around
- * every odd step through lbm_plane_ptr, see latticeboltzmanncuda_b200/slab.py), all-fluid
- * lattices or a solid mask in LBM_BOUNDARY_BOUNCE_BACK mode, box source, force accumulator, SoA
- * transfers; everything else (table reflection, unfused phases, zero-inflow edges, AoS
- * transfers, lbm_step_range) returns LBM_ERR_UNSUPPORTED.  On this engine
- * lbm_set_solid_mask is accepted before stepping or after an even number of steps
- * (LBM_ERR_STATE otherwise).  AUTO = PULL2.  TMA is reserved (LBM_ERR_UNSUPPORTED). */
-enum lbm_engine { LBM_ENGINE_AUTO = 0, LBM_ENGINE_PULL2 = 1, LBM_ENGINE_INPLACE = 2, LBM_ENGINE_TMA = 3 };
+ * stream + collide steps (lbm_step / lbm_step_phases with STREAM and COLLIDE set),
+ * periodic or wall edges, LBM_BC_HALO on x for slabs (lbm_halo_connect: the edge cells work on the
+ * neighbouring slab's memory; or, without a connection, the caller moves the edge planes around
+ * every odd step through lbm_plane_ptr / lbm_inplace_merge_edges), all-fluid lattices or a solid
+ * mask in LBM_BOUNDARY_BOUNCE_BACK mode, source (box or mask), force accumulator, SoA transfers;
+ * everything else (table reflection, unfused phases, zero-inflow edges, AoS transfers,
+ * lbm_step_range) returns LBM_ERR_UNSUPPORTED.  On this engine lbm_set_solid_mask is accepted
+ * before stepping or after an even number of steps (LBM_ERR_STATE otherwise).  AUTO = PULL2. */
+enum lbm_engine { LBM_ENGINE_AUTO = 0, LBM_ENGINE_PULL2 = 1, LBM_ENGINE_INPLACE = 2 };
 
 typedef struct lbm_config {
     int32_t nx, ny, nz;           /* Lattice::Lattice(x, y, z, ...), Lattice.cpp:22-39 */

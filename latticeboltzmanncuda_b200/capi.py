@@ -19,7 +19,7 @@ FORCE_REFERENCE_SLOT_INDEX, FORCE_PHYSICAL = 0, 1
 FORCE_ACCUM_F64_PARTIALS, FORCE_ACCUM_REFERENCE_FP32 = 0, 1
 PHASE_STREAM, PHASE_REFLECT, PHASE_COLLIDE, PHASE_SOURCE, PHASE_ALL = 1, 2, 4, 8, 15
 SOURCE_NONE, SOURCE_BOX = 0, 1
-ENGINE_AUTO, ENGINE_PULL2, ENGINE_INPLACE, ENGINE_TMA = range(4)
+ENGINE_AUTO, ENGINE_PULL2, ENGINE_INPLACE = range(3)
 HALO_BLOB_BYTES = 320
 
 # simulation/include/LatticePoint.h:9-17 (144 B) and :3-7 (380 B) as numpy record types
