@@ -105,6 +105,83 @@ void pin_tables_in_l2(lbm_handle h)
     cudaGetLastError();   // best effort: an unsupported attribute must not poison later calls
 }
 
+// Up to LBM_DEAD_BOXES disjoint boxes (in x, y and 32-cell z-words) that hold all-solid words only, as large as a greedy search finds:
+// the warps of the single-buffer kernels that land inside leave on a compare of kernel parameters instead of waiting for
+// their class byte or mask word (a third of the warps of the 512^3 obstacle).  Each box is grown from a seed word, one
+// layer at a time over its six faces in turn, while the new layer is all solid (3-D prefix sums answer that in O(1));
+// the best of a few hundred seeds wins.  Conservative by construction: a word outside every box is treated as before.
+void find_dead_boxes(const std::vector<uint8_t>& cls, int nx, int ny, int wc, int pitch, int n_boxes, int (*box)[6], double* covered)
+{
+    const size_t sy = (size_t)wc + 1, sx = ((size_t)ny + 1) * sy;
+    std::vector<uint8_t> dead((size_t)nx * ny * wc);
+    std::vector<int32_t> S(((size_t)nx + 1) * sx);
+    size_t n_dead = 0, taken = 0;
+    for (int x = 0; x < nx; ++x)
+        for (int y = 0; y < ny; ++y)
+            for (int w = 0; w < wc; ++w) {
+                const bool d = cls[((size_t)x * wc + w) * pitch + y] == 1;      // 1 = every cell of the word is solid
+                dead[((size_t)x * ny + y) * wc + w] = d;
+                n_dead += d;
+            }
+    for (int b = 0; b < LBM_DEAD_BOXES; ++b)
+        for (int k = 0; k < 6; ++k) box[b][k] = 0;
+    *covered = 0.0;
+    if (n_dead == 0) return;
+    auto count = [&](int x0, int x1, int y0, int y1, int w0, int w1) {
+        auto at = [&](int x, int y, int w) { return S[(size_t)x * sx + (size_t)y * sy + w]; };
+        return at(x1, y1, w1) - at(x0, y1, w1) - at(x1, y0, w1) - at(x1, y1, w0) + at(x0, y0, w1) + at(x0, y1, w0) + at(x1, y0, w0) - at(x0, y0, w0);
+    };
+    for (int b = 0; b < n_boxes && b < LBM_DEAD_BOXES; ++b) {
+        std::fill(S.begin(), S.end(), 0);
+        for (int x = 0; x < nx; ++x)
+            for (int y = 0; y < ny; ++y) {
+                int32_t row = 0;
+                for (int w = 0; w < wc; ++w) {
+                    row += dead[((size_t)x * ny + y) * wc + w];
+                    S[(size_t)(x + 1) * sx + (size_t)(y + 1) * sy + (w + 1)] =
+                        row + S[(size_t)x * sx + (size_t)(y + 1) * sy + (w + 1)] + S[(size_t)(x + 1) * sx + (size_t)y * sy + (w + 1)] -
+                        S[(size_t)x * sx + (size_t)y * sy + (w + 1)];
+                }
+            }
+        const int32_t left = S[(size_t)nx * sx + (size_t)ny * sy + wc];
+        if (left == 0) break;
+        // seeds: every (left / 384)-th remaining all-solid word in storage order
+        const int32_t stride = left / 384 + 1;
+        long long best = 0;
+        int bb[6] = {0, 0, 0, 0, 0, 0};
+        int32_t seen = 0;
+        for (size_t k = 0; k < dead.size(); ++k) {
+            if (!dead[k]) continue;
+            if (seen++ % stride != stride / 2) continue;
+            int lo[3] = {(int)(k / ((size_t)ny * wc)), (int)(k / wc % ny), (int)(k % wc)};
+            int hi[3] = {lo[0] + 1, lo[1] + 1, lo[2] + 1};
+            const int lim[3] = {nx, ny, wc};
+            for (bool grew = true; grew;) {
+                grew = false;
+                for (int a = 0; a < 3; ++a)
+                    for (int side = 0; side < 2; ++side) {
+                        int l2[3] = {lo[0], lo[1], lo[2]}, h2[3] = {hi[0], hi[1], hi[2]};
+                        if (side == 0) { if (lo[a] == 0) continue; l2[a] = lo[a] - 1; h2[a] = lo[a]; }
+                        else           { if (hi[a] == lim[a]) continue; l2[a] = hi[a]; h2[a] = hi[a] + 1; }
+                        const long long layer = (long long)(h2[0] - l2[0]) * (h2[1] - l2[1]) * (h2[2] - l2[2]);
+                        if (count(l2[0], h2[0], l2[1], h2[1], l2[2], h2[2]) != layer) continue;
+                        if (side == 0) lo[a] -= 1; else hi[a] += 1;
+                        grew = true;
+                    }
+            }
+            const long long vol = (long long)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+            if (vol > best) { best = vol; for (int a = 0; a < 3; ++a) { bb[a] = lo[a]; bb[3 + a] = hi[a] - lo[a]; } }
+        }
+        if (best == 0) break;
+        for (int k = 0; k < 6; ++k) box[b][k] = bb[k];
+        taken += (size_t)best;
+        for (int x = bb[0]; x < bb[0] + bb[3]; ++x)          // the next box is searched in what is left
+            for (int y = bb[1]; y < bb[1] + bb[4]; ++y)
+                for (int w = bb[2]; w < bb[2] + bb[5]; ++w) dead[((size_t)x * ny + y) * wc + w] = 0;
+    }
+    *covered = (double)taken / (double)n_dead;
+}
+
 // rebuild the classification of every interior 32-cell word and the neighbourhood words of the special
 // ones; call after the solid mask or the link lists change
 int rebuild_special(lbm_handle h)
@@ -189,6 +266,39 @@ int rebuild_special(lbm_handle h)
                 CK(cudaMemcpyAsync(h->live_blocks, live.data(), live.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
                 CK(cudaStreamSynchronize(h->stream));
             }
+        }
+    }
+    std::memset(h->dead_box, 0, sizeof h->dead_box);
+    const int whole[6] = {0, 0, 0, g.nx, g.ny, wcount};
+    std::memcpy(h->busy_box, whole, sizeof whole);
+    static const int n_boxes = [] { const char* e = getenv("LBM_AA_DEAD_BOXES"); return e ? atoi(e) : LBM_DEAD_BOXES; }();
+    if (n_boxes > 0 && h->inplace && solid) {
+        std::vector<uint8_t> cls(h->cls_bytes);
+        CK(cudaMemcpyAsync(cls.data(), h->cls, h->cls_bytes, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        double covered = 0.0;
+        find_dead_boxes(cls, g.nx, g.ny, wcount, h->cls_pitch, n_boxes, h->dead_box, &covered);
+        static const bool use_busy = [] { const char* e = getenv("LBM_AA_BUSY_BOX"); return e ? atoi(e) != 0 : true; }();
+        if (use_busy) {
+            int lo[3] = {g.nx, g.ny, wcount}, hi[3] = {0, 0, 0};
+            for (int x = 0; x < g.nx; ++x)
+                for (int w = 0; w < wcount; ++w) {
+                    const uint8_t* row = cls.data() + ((size_t)x * wcount + w) * h->cls_pitch;
+                    for (int y = 0; y < g.ny; ++y)
+                        if (row[y] != 0) {           // 0 = ordinary
+                            lo[0] = std::min(lo[0], x); hi[0] = std::max(hi[0], x + 1);
+                            lo[1] = std::min(lo[1], y); hi[1] = std::max(hi[1], y + 1);
+                            lo[2] = std::min(lo[2], w); hi[2] = std::max(hi[2], w + 1);
+                        }
+                }
+            for (int a = 0; a < 3; ++a) { h->busy_box[a] = hi[a] > lo[a] ? lo[a] : 0; h->busy_box[3 + a] = hi[a] > lo[a] ? hi[a] - lo[a] : 0; }
+        }
+        if (getenv("LBM_VERBOSE")) {
+            for (int b = 0; b < LBM_DEAD_BOXES; ++b)
+                fprintf(stderr, "lbm: all-solid box %d: origin %d %d %d extent %d %d %d (x, y, z-words)\n", b, h->dead_box[b][0], h->dead_box[b][1],
+                        h->dead_box[b][2], h->dead_box[b][3], h->dead_box[b][4], h->dead_box[b][5]);
+            fprintf(stderr, "lbm: the boxes hold %.1f %% of the all-solid words; words that are not ordinary lie in origin %d %d %d extent %d %d %d of %d %d %d\n",
+                    100.0 * covered, h->busy_box[0], h->busy_box[1], h->busy_box[2], h->busy_box[3], h->busy_box[4], h->busy_box[5], g.nx, g.ny, wcount);
         }
     }
     pin_tables_in_l2(h);
@@ -356,6 +466,9 @@ void fill_inplace(lbm_handle h, InplaceParams& ip)
         ip.force = h->force_on ? h->force : nullptr;
         static const bool split_even = [] { const char* e = getenv("LBM_AA_FORCE_SPLIT"); return e ? atoi(e) != 0 : false; }();
         ip.force_pending = (ip.force && !split_even) ? h->force + 3 * FORCE_SLOTS : nullptr;
+        static_assert(sizeof ip.dead_box == sizeof h->dead_box, "box tables differ");
+        std::memcpy(ip.dead_box, h->dead_box, sizeof ip.dead_box);
+        std::memcpy(ip.busy_box, h->busy_box, sizeof ip.busy_box);
     }
     ip.src_on = h->src_on;
     for (int a = 0; a < 3; ++a) { ip.src_lo[a] = h->src_lo[a]; ip.src_hi[a] = h->src_hi[a]; }

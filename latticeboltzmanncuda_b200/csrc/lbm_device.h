@@ -120,6 +120,9 @@ struct StepParams {
 };
 
 // single-buffer (AA pattern) engine, lbm_inplace.cu
+#ifndef LBM_DEAD_BOXES
+#define LBM_DEAD_BOXES 4      // boxes of all-solid words the single-buffer kernels skip without a load (find_dead_boxes)
+#endif
 struct InplaceParams {
     float* f;
     Geom  g;
@@ -170,6 +173,8 @@ struct InplaceParams {
     // the box.  The entries of the planes of this launch: [live_k0, live_k0 + n_live).
     const uint32_t* live_blocks;
     long long live_k0, n_live;
+    int   dead_box[LBM_DEAD_BOXES][6];   // boxes of all-solid words, origin (x, y, word) and extent; extent 0 = unused
+    int   busy_box[6];        // bounding box of the words that are not ordinary, origin and extent; outside it no class byte is read
 };
 
 // does cell (x, y, z) take the additive source?  The reference asks a device predicate for every cell

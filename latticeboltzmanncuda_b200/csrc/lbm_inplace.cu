@@ -109,6 +109,27 @@ __device__ __forceinline__ Edge edge_lookup(const InplaceParams& p, int i, int x
     return e;
 }
 
+// Word (x, y, w) lies in one of the boxes of all-solid words the host found (csrc/lbm_capi.cu find_dead_boxes): the warp
+// leaves on a compare of kernel parameters, before any load.  An unused box has extent 0 and matches nothing.
+__device__ __forceinline__ bool in_dead_box(const InplaceParams& p, int x, int y, int w)
+{
+#pragma unroll
+    for (int b = 0; b < LBM_DEAD_BOXES; ++b)
+        if ((unsigned)(x - p.dead_box[b][0]) < (unsigned)p.dead_box[b][3] && (unsigned)(y - p.dead_box[b][1]) < (unsigned)p.dead_box[b][4] &&
+            (unsigned)(w - p.dead_box[b][2]) < (unsigned)p.dead_box[b][5]) return true;
+    return false;
+}
+
+// Word (x, y, w) lies in the bounding box of the words that are not ordinary (all-solid, next to a solid cell or holding a
+// reflection target).  Outside it every cell is plain fluid: the warp asks for its populations at once instead of waiting
+// for its class byte or mask word first -- one dependent load less in front of every block upstream, downstream and
+// beside an obstacle (measured: profiles/r02_notes.md section 4).
+__device__ __forceinline__ bool in_busy_box(const InplaceParams& p, int x, int y, int w)
+{
+    return (unsigned)(x - p.busy_box[0]) < (unsigned)p.busy_box[3] && (unsigned)(y - p.busy_box[1]) < (unsigned)p.busy_box[4] &&
+           (unsigned)(w - p.busy_box[2]) < (unsigned)p.busy_box[5];
+}
+
 // solid flag of the padded cell (xpad, ypad, zpad); ghost cells hold the periodic images, wall ghosts are clear
 __device__ __forceinline__ bool solid_bit(const InplaceParams& p, int xpad, int ypad, int zpad)
 {
@@ -144,7 +165,8 @@ __global__ void __launch_bounds__(LBM_AA_EVEN_THREADS > 256 ? LBM_AA_EVEN_THREAD
         x = p.x0 + blockIdx.z;                       // the launch covers the planes [x0, x1)
     }
     if (z >= g.nz || y >= g.ny) return;
-    if (EXTRA && p.solid) {
+    if (EXTRA && p.solid && in_busy_box(p, x, y, z >> 5)) {
+        if (in_dead_box(p, x, y, z >> 5)) return;
         // a warp is 32 consecutive z of one row = one 32-cell word (blockDim.x is a multiple of 32)
         if (p.force && !p.force_pending) {
             // the momentum exchange is summed by aa_even_special_kernel, which takes the special words: ordinary words only
@@ -333,7 +355,8 @@ __global__ void __launch_bounds__(MODE == 0 ? 32 * LBM_AA_ODD_WARPS : 128,
     }
     const int z = w * 32 + (int)(threadIdx.x & 31u);
     if (z >= g.nz) return;
-    if (EXTRA && p.cls) {                          // warp-uniform: one class byte per 32-cell word, resident in L2
+    if (EXTRA && p.cls && (MODE != 0 || in_busy_box(p, x, y, w))) {      // warp-uniform: one class byte per 32-cell word, resident in L2
+        if (MODE == 0 && in_dead_box(p, x, y, w)) return;
         if (__ldg(p.cls + ((long long)x * wcount + w) * p.cls_pitch + y) != AA_ORDINARY) return;
     }
     float* a = p.f + g.cell(x, y, z);

@@ -29,7 +29,8 @@ SELECTION = [
     (TP, "test_source_with_an_arbitrary_criterion", 1), (TP, "test_unfused_phases_equal_fused_step", 1),
     (TP, "test_soa_engine_parity", 1), (TP, "test_bounce_back_obstacle_parity", 1), (TP, "test_lid_driven_cavity_parity", 1),
     (TP, "test_bad_arguments_are_reported", 1), (TP, "test_inplace_engine_equals_two_buffer_engine", 9),
-    (TP, "test_inplace_engine_with_obstacles", 5), (TP, "test_inplace_engine_refuses_what_it_cannot_do", 1),
+    (TP, "test_inplace_engine_with_obstacles", 5), (TP, "test_inplace_engine_with_a_compact_body", 1),
+    (TP, "test_inplace_engine_refuses_what_it_cannot_do", 1),
     (TG, "test_coordinates_with_model", 1), (TG, "test_mask_and_tables_bit_exact", 1),
     (TG, "test_missing_file_and_bounding_box_guard", 1), (TG, "test_reflection_table_known_answer", 1),
     (TG, "test_reflections_known_answer_end_to_end", 1),

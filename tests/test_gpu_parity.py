@@ -554,6 +554,35 @@ def test_inplace_engine_equals_two_buffer_engine(q, eq, bc, steps):
         assert np.allclose(a, b, rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("bc", [(1, 1, 1), (1, 2, 2)])
+def test_inplace_engine_with_a_compact_body(bc):
+    """one compact body in a box: the single-buffer kernels skip the all-solid words inside it by a box test on the kernel
+    parameters and read no class byte outside the bounding box of the body (csrc/lbm_capi.cu find_dead_boxes, busy_box);
+    state and force stay the oracle's after every step"""
+    X, Y, Z, q = 16, 14, 200, 19
+    solid = np.zeros((X, Y, Z), np.uint8)
+    solid[6:10, 5:9, 60:140] = 1                # words 2 and 3 of these rows are all solid; words 0, 5, 6 of every row are ordinary
+    solid[7, 6, 59] = 1; solid[10, 8, 100] = 1  # (not a box)
+    f = soa_state(q, X, Y, Z, 31, solid)
+    lat = make(X, Y, Z, engine=lb.ENGINE_INPLACE, tau=0.7, q=q, bc=bc, moment_mode=lb.MOMENT_STANDARD, eq_precision=lb.EQ_FP32,
+               boundary_mode=lb.BOUNDARY_BOUNCE_BACK)
+    lat.set_solid_mask(solid)
+    lat.load_populations(f)
+    lat.setReflectionData(lb.ReflectionData())
+    st = lat.stats()
+    assert st["words_dead"] == 4 * 4 * 2 and st["words_special"] > 0 and st["words_total"] > 4 * (st["words_dead"] + st["words_special"])
+    force = np.zeros(3, np.float64)
+    state = f
+    for step in range(1, 7):
+        lat.step(1)
+        state = O.step_soa(state, X, Y, Z, q, 0.7, bc=bc, solid=solid, moment=O.MOMENT_STANDARD, eq64=False, steps=1, force=force)
+        got = lat.retrieve_populations()
+        assert rel_err(got, state) <= REL, "step %d" % step
+        assert np.all(got[:, solid.astype(bool)] == 0)
+        assert np.allclose(lat.force_f64(), force, rtol=1e-4, atol=1e-4), "step %d" % step
+    lat.close()
+
+
 @pytest.mark.parametrize("q", [19, 27])
 @pytest.mark.parametrize("bc", [(1, 1, 1), (2, 2, 2), (1, 2, 2), (2, 1, 2)])
 @pytest.mark.parametrize("shape", [(14, 12, 40), (9, 8, 130)])

@@ -48,6 +48,8 @@ def run(name, q, eq, bc, boundary, obstacle, source, moment=lb.MOMENT_STANDARD, 
     name = "%s [dead %.0f%% special %.1f%%]" % (name, 100.0 * st["words_dead"] / st["words_total"], 100.0 * st["words_special"] / st["words_total"])
     print("%-44s %8.0f MLUPS %7.0f GB/s %5.1f%% of %.0f  (%.3f ms/step, %d launches)" %
           (name, mlups, gbs, 100 * gbs / PEAK, PEAK, ms / K, launches), flush=True)
+    if os.environ.get("LBM_PROBE_FORCE"):      # a checksum to compare builds / launch modes with: must be identical
+        print("    force %r mass %r" % (tuple(float(v) for v in lat.force_f64()), float(lat.mass())), flush=True)
     lat.close()
 
 
