@@ -232,42 +232,6 @@ int rebuild_special(lbm_handle h)
         h->cellinfo_cap = n;
     }
     CK(launch_fill_cellinfo(solid, tmask, h->special_list, (long long)n, h->cellinfo, g, h->stream));
-    {
-        // single-buffer engine with obstacles: the list of blocks (4 z-words of a row) that hold a live word
-        cudaFree(h->live_blocks);
-        h->live_blocks = nullptr;
-        h->n_live = 0;
-        h->live_start.clear();
-        // Measured on B200 (profiles/r02_notes.md, 512^3 obstacle, same box): 2.566 ms/step with the list against 2.534
-        // without -- the dependent list load in front of every block and the lost launch order cost more than the
-        // skipped blocks save -- so the list is OFF unless LBM_AA_LIVE_LIST=1 asks for it.
-        static const bool use_list = [] { const char* e = getenv("LBM_AA_LIVE_LIST"); return e ? atoi(e) != 0 : false; }();
-        const int nbw = (wcount + 3) / 4;
-        if (use_list && h->inplace && solid && g.nz >= 97 && g.nx <= 4096 && g.ny <= 4096 && nbw <= 256) {
-            std::vector<uint8_t> cls(h->cls_bytes);
-            CK(cudaMemcpyAsync(cls.data(), h->cls, h->cls_bytes, cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
-            std::vector<uint32_t> live;
-            h->live_start.assign((size_t)g.nx + 1, 0u);
-            for (int x = 0; x < g.nx; ++x) {
-                h->live_start[x] = (uint32_t)live.size();
-                for (int y = 0; y < g.ny; ++y)
-                    for (int bw = 0; bw < nbw; ++bw) {
-                        bool any = false;
-                        for (int w = bw * 4; w < bw * 4 + 4 && w < wcount; ++w)
-                            if (cls[((size_t)x * wcount + w) * h->cls_pitch + y] != 1) any = true;      // 1 = all cells solid
-                        if (any) live.push_back(((uint32_t)x << 20) | ((uint32_t)y << 8) | (uint32_t)bw);
-                    }
-            }
-            h->live_start[g.nx] = (uint32_t)live.size();
-            h->n_live = live.size();
-            if (!live.empty()) {
-                CK(cudaMalloc(&h->live_blocks, live.size() * sizeof(uint32_t)));
-                CK(cudaMemcpyAsync(h->live_blocks, live.data(), live.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
-                CK(cudaStreamSynchronize(h->stream));
-            }
-        }
-    }
     std::memset(h->dead_box, 0, sizeof h->dead_box);
     const int whole[6] = {0, 0, 0, g.nx, g.ny, wcount};
     std::memcpy(h->busy_box, whole, sizeof whole);
@@ -502,11 +466,6 @@ int inplace_range(lbm_handle h, unsigned phases, int xa, int xb, cudaStream_t s)
     if (ip.n_special && (int)h->special_start.size() == h->g.nx + 1) {
         ip.special_k0 = h->special_start[xa];
         ip.n_special = (long long)h->special_start[xb] - (long long)h->special_start[xa];
-    }
-    if (h->live_blocks && h->any_solid && (int)h->live_start.size() == h->g.nx + 1) {
-        ip.live_blocks = h->live_blocks;
-        ip.live_k0 = h->live_start[xa];
-        ip.n_live = (long long)h->live_start[xb] - (long long)h->live_start[xa];
     }
     // on the handle's main stream the face and special-word kernels of an odd step run next to the interior launch (on
     // the high-priority side stream): they touch disjoint slots, and the tail of one launch overlaps the other
@@ -748,7 +707,6 @@ LBM_API int lbm_destroy(lbm_handle h)
     cudaFree(h->solid); cudaFree(h->cls); cudaFree(h->cellinfo); cudaFree(h->special_list); cudaFree(h->solid_bytes); cudaFree(h->tmask); cudaFree(h->tprefix); cudaFree(h->toff);
     cudaFree(h->reflected); cudaFree(h->links); cudaFree(h->force); cudaFree(h->diag); cudaFree(h->flag);
     cudaFree(h->link_rank); cudaFree(h->force_moved); cudaFree(h->force_coef); cudaFree(h->force32);
-    cudaFree(h->live_blocks);
     cudaFree(h->src_mask);
     cudaFree(h->staging);
     if (h->ev0) cudaEventDestroy(h->ev0);

@@ -166,13 +166,8 @@ struct InplaceParams {
     // in thickness and therefore in population stride.
     long long shift[3][2];
     long long xshift[2][27];
-    // Lattices with obstacles: the blocks (4 consecutive z-words of one row) that hold at least one live word, as a
-    // sorted list of packed ids (x << 20 | y << 8 | block-in-row); the main kernels are launched over this list instead
-    // of the whole box, so that all-solid regions cost no block launches at all.  An experiment that lost (1.2 % slower
-    // on the 512^3 obstacle: profiles/r02_notes.md), kept behind LBM_AA_LIVE_LIST=1.  nullptr (the default): launch over
-    // the box.  The entries of the planes of this launch: [live_k0, live_k0 + n_live).
-    const uint32_t* live_blocks;
-    long long live_k0, n_live;
+    // Lattices with obstacles: two box tests on these parameters keep loads off the critical path of the big kernels
+    // (csrc/lbm_capi.cu find_dead_boxes; measured in profiles/r02_notes.md section 4).
     int   dead_box[LBM_DEAD_BOXES][6];   // boxes of all-solid words, origin (x, y, word) and extent; extent 0 = unused
     int   busy_box[6];        // bounding box of the words that are not ordinary, origin and extent; outside it no class byte is read
 };

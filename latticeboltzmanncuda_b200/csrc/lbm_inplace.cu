@@ -154,16 +154,9 @@ template <int Q, int MOMENT, bool EQ64, bool EXTRA>
 __global__ void __launch_bounds__(LBM_AA_EVEN_THREADS > 256 ? LBM_AA_EVEN_THREADS : 256, ((Q == 19 && !EQ64) ? 6 : 4) * 256 / (LBM_AA_EVEN_THREADS > 256 ? LBM_AA_EVEN_THREADS : 256)) aa_even_kernel(const __grid_constant__ InplaceParams p)
 {
     const Geom& g = p.g;
-    int x, y, z;
-    if (EXTRA && p.live_blocks) {                    // one block per entry of the live-block list (128 threads = 4 z-words of a row)
-        const uint32_t id = __ldg(p.live_blocks + p.live_k0 + blockIdx.x);
-        x = (int)(id >> 20); y = (int)((id >> 8) & 0xfffu);
-        z = (int)(id & 0xffu) * 128 + (int)threadIdx.x;
-    } else {
-        z = blockIdx.x * blockDim.x + threadIdx.x;
-        y = blockIdx.y * blockDim.y + threadIdx.y;
-        x = p.x0 + blockIdx.z;                       // the launch covers the planes [x0, x1)
-    }
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = p.x0 + blockIdx.z;                 // the launch covers the planes [x0, x1)
     if (z >= g.nz || y >= g.ny) return;
     if (EXTRA && p.solid && in_busy_box(p, x, y, z >> 5)) {
         if (in_dead_box(p, x, y, z >> 5)) return;
@@ -183,7 +176,19 @@ __global__ void __launch_bounds__(LBM_AA_EVEN_THREADS > 256 ? LBM_AA_EVEN_THREAD
     for (int i = 0; i < Q; ++i) f[i] = a[p.pop_off[i]];
     if (EQ64) collide_fp64<Q, MOMENT>(f, p.tau);
     else      collide_fp32<Q, MOMENT>(f, p.inv_tau);
-    if (EXTRA && p.src_on) add_source<Q>(p, f, x, y, z);
+    if (EXTRA && p.src_on) {
+        // the coordinates are read again from the special registers (volatile: no common subexpression with the ones above),
+        // so that x, y, z do not have to stay in registers across the collision: the kernel sits at its 40-register cap
+        unsigned bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z, tx = threadIdx.x, ty = threadIdx.y;
+#ifdef __CUDACC__
+        asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bx));
+        asm volatile("mov.u32 %0, %%ctaid.y;" : "=r"(by));
+        asm volatile("mov.u32 %0, %%ctaid.z;" : "=r"(bz));
+        asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tx));
+        asm volatile("mov.u32 %0, %%tid.y;" : "=r"(ty));
+#endif
+        add_source<Q>(p, f, p.x0 + (int)bz, (int)(by * blockDim.y + ty), (int)(bx * blockDim.x + tx));
+    }
     asm volatile("" : "+l"(a));          // rebuild the Q addresses next to the stores instead of keeping them alive
 #pragma unroll
     for (int i = 0; i < Q; ++i) a[p.pop_off[dir_inv(i)]] = f[i];
@@ -321,17 +326,10 @@ __global__ void __launch_bounds__(MODE == 0 ? 32 * LBM_AA_ODD_WARPS : 128,
     // (MODE 0 and 3 are launched with [x0, x1) already clipped to the interior planes 1..nx-2, see launch_t)
     int x, y, w;
     if constexpr (MODE == 0) {
-        if (EXTRA && p.live_blocks) {                // one block per entry of the live-block list; the faces have their own launches
-            const uint32_t id = __ldg(p.live_blocks + p.live_k0 + blockIdx.x);
-            x = (int)(id >> 20); y = (int)((id >> 8) & 0xfffu);
-            w = (int)(id & 0xffu) * 4 + (int)(threadIdx.x >> 5);
-            if (x == 0 || x == g.nx - 1 || y == 0 || y == g.ny - 1 || w >= wcount) return;
-        } else {
-            w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-            if (w >= wcount) return;
-            y = 1 + blockIdx.y;
-            x = p.x0 + blockIdx.z;
-        }
+        w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        if (w >= wcount) return;
+        y = 1 + blockIdx.y;
+        x = p.x0 + blockIdx.z;
     } else if constexpr (MODE == 2) {
         // face planes of the range: plane 0 if x0 == 0, plane nx-1 if x1 == nx (one plane when nx == 1)
         const long long k = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -700,13 +698,9 @@ cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, cudaStream_t s
             InplaceParams pi = p;          // the interior planes of the range
             pi.x0 = xi0; pi.x1 = xi1;
             if (g.ny > 2) {
-                if (EXTRA && p.live_blocks) {
-                    if (p.n_live > 0) { aa_odd_kernel<Q, MOMENT, EQ64, 0, EXTRA><<<(unsigned)p.n_live, 128, 0, stream>>>(p); ++n; }
-                } else {
-                    dim3 grid((wcount + LBM_AA_ODD_WARPS - 1) / LBM_AA_ODD_WARPS, g.ny - 2, xi1 - xi0);
-                    aa_odd_kernel<Q, MOMENT, EQ64, 0, EXTRA><<<grid, 32 * LBM_AA_ODD_WARPS, 0, stream>>>(pi);
-                    ++n;
-                }
+                dim3 grid((wcount + LBM_AA_ODD_WARPS - 1) / LBM_AA_ODD_WARPS, g.ny - 2, xi1 - xi0);
+                aa_odd_kernel<Q, MOMENT, EQ64, 0, EXTRA><<<grid, 32 * LBM_AA_ODD_WARPS, 0, stream>>>(pi);
+                ++n;
             }
             const long long warps = (long long)(xi1 - xi0) * (g.ny < 2 ? g.ny : 2) * wcount;
             aa_odd_kernel<Q, MOMENT, EQ64, 3, EXTRA><<<(unsigned)((warps + 3) / 4), 128, 0, side>>>(pi);
@@ -733,8 +727,6 @@ cudaError_t launch_t(const InplaceParams& p, cudaStream_t stream, cudaStream_t s
             dim3 grid2((g.nz + 127) / 128, (g.ny + LBM_AA_EVEN_ROWS - 1) / LBM_AA_EVEN_ROWS, p.x1 - p.x0);
             aa_even_rows_kernel<Q, MOMENT, EQ64, EXTRA, LBM_AA_EVEN_ROWS><<<grid2, 128, 0, stream>>>(p);
             ++n;
-        } else if (EXTRA && p.live_blocks) {
-            if (p.n_live > 0) { aa_even_kernel<Q, MOMENT, EQ64, EXTRA><<<(unsigned)p.n_live, 128, 0, stream>>>(p); ++n; }
         } else {
             aa_even_kernel<Q, MOMENT, EQ64, EXTRA><<<grid, block, 0, stream>>>(p);
             ++n;

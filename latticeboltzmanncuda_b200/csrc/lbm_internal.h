@@ -51,9 +51,6 @@ struct lbm_lattice_s {
     uint32_t* special_list = nullptr;   // mask-word indices of the special words
     size_t n_special = 0;
     std::vector<uint32_t> special_start;   // [nx + 1]: first list entry of every interior plane (host side)
-    uint32_t* live_blocks = nullptr;       // single-buffer engine: packed ids of the blocks with a live word (InplaceParams)
-    size_t n_live = 0;
-    std::vector<uint32_t> live_start;      // [nx + 1]: first entry of every plane
     int busy_box[6] = {};                  // bounding box of the words that are not ordinary (whole slab until it is known)
     int dead_box[LBM_DEAD_BOXES][6] = {};               // single-buffer engine: boxes of all-solid words (find_dead_boxes), extent 0 = none
     bool any_solid = false;          // some bit set (geometry or wall ghosts)

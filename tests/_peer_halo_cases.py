@@ -49,8 +49,8 @@ CASES = {
     "inplace_q27_walls_w2": dict(engine=lb.ENGINE_INPLACE, q=27, shape=(6, 4, 33), world=2, bc=(P, W, W), steps=4, wall_u=WALL_U),
     "inplace_q19_thin_slabs_w2": dict(engine=lb.ENGINE_INPLACE, q=19, shape=(4, 6, 64), world=2, bc=(P, P, W), body="edges",
                                       force=True, steps=3),
-    # nz >= 97: with LBM_AA_LIVE_LIST=1 the single-buffer kernels are launched over the list of blocks that hold a live word
-    "inplace_q19_live_block_list_w2": dict(engine=lb.ENGINE_INPLACE, q=19, shape=(6, 5, 170), world=2, bc=(P, W, W), body="slab_of_solid",
+    # long rows with a slab of solid: all-solid words, so every slab finds boxes of them (csrc/lbm_capi.cu find_dead_boxes)
+    "inplace_q19_all_solid_words_w2": dict(engine=lb.ENGINE_INPLACE, q=19, shape=(6, 5, 170), world=2, bc=(P, W, W), body="slab_of_solid",
                                            force=True, steps=5, wall_u=WALL_U),
     "inplace_q19_self_ring_w1": dict(engine=lb.ENGINE_INPLACE, q=19, shape=(5, 4, 36), world=1, bc=(P, W, P), steps=3),
     "pull2_q19_body_w3": dict(engine=lb.ENGINE_PULL2, q=19, shape=(10, 7, 70), world=3, bc=(P, W, P), body="edges", source=True,
