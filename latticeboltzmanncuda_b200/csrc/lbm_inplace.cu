@@ -599,6 +599,28 @@ __device__ __forceinline__ float aa_fetch(const InplaceParams& p, int i, int x, 
     return (e.kind == 0) ? a[e.off] : plus_term(a[(long long)dir_inv(i) * g.np], -e.term);
 }
 
+// The Q populations of a cell for the diagnostics.  Warp-uniform short cuts: in the parked form every population is in the
+// cell's own slots; in the arrived form a word of ordinary cells away from every edge finds population i at the plain push
+// offset.  Everything else (cells next to obstacles or edges) goes through aa_fetch.
+template <int Q>
+__device__ __forceinline__ void aa_fetch_cell(const InplaceParams& p, int x, int y, int z, float (&f)[Q])
+{
+    const Geom& g = p.g;
+    const int w = z >> 5, wcount = (g.nz + 31) >> 5;
+    const float* a = p.f + g.cell(x, y, z);
+    if (p.parity == 0) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) f[i] = a[p.park_off[i]];
+    } else if (x > 0 && x < g.nx - 1 && y > 0 && y < g.ny - 1 && w > 0 && w < wcount - 1 &&
+               (!p.cls || __ldg(p.cls + ((long long)x * wcount + w) * p.cls_pitch + y) == AA_ORDINARY)) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) f[i] = a[p.push_off[i]];
+    } else {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) f[i] = aa_fetch<Q>(p, i, x, y, z);
+    }
+}
+
 template <int Q>
 __global__ void aa_gather_kernel(const __grid_constant__ InplaceParams p, float* __restrict__ dense, int q, int x0, int nxc)
 {
@@ -629,9 +651,11 @@ __global__ void aa_moments_kernel(const __grid_constant__ InplaceParams p, int m
     const int y = blockIdx.y, x = blockIdx.z;
     if (z >= g.nz) return;
     float r = 0.0f, mx = 0.0f, my = 0.0f, mz = 0.0f;
+    float f[Q];
+    aa_fetch_cell<Q>(p, x, y, z, f);
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
-        const float v = aa_fetch<Q>(p, i, x, y, z);
+        const float v = f[i];
         const float s = (moment_mode == 0) ? dir_split(i) : 1.0f;
         r += v;
         mx += v * (float)dir_c(i, 0) * s;
@@ -657,9 +681,11 @@ __global__ void __launch_bounds__(256) aa_mass_kernel(const __grid_constant__ In
     for (long long r = (long long)blockIdx.x * warps_per_block + wib; r < rows; r += (long long)gridDim.x * warps_per_block) {
         const int x = (int)(r / g.ny), y = (int)(r % g.ny);
         for (int z = (int)lane; z < g.nz; z += 32) {
+            float f[Q];
+            aa_fetch_cell<Q>(p, x, y, z, f);
 #pragma unroll
             for (int i = 0; i < Q; ++i) {
-                const double v = (double)aa_fetch<Q>(p, i, x, y, z);
+                const double v = (double)f[i];
                 m += v; px += v * dir_c(i, 0); py += v * dir_c(i, 1); pz += v * dir_c(i, 2);
             }
         }
