@@ -554,8 +554,9 @@ def test_inplace_engine_equals_two_buffer_engine(q, eq, bc, steps):
         assert np.allclose(a, b, rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("bodies", [1, 2])
 @pytest.mark.parametrize("bc", [(1, 1, 1), (1, 2, 2)])
-def test_inplace_engine_with_a_compact_body(bc):
+def test_inplace_engine_with_a_compact_body(bc, bodies):
     """one compact body in a box: the single-buffer kernels skip the all-solid words inside it by a box test on the kernel
     parameters and read no class byte outside the bounding box of the body (csrc/lbm_capi.cu find_dead_boxes, busy_box);
     state and force stay the oracle's after every step"""
@@ -563,6 +564,8 @@ def test_inplace_engine_with_a_compact_body(bc):
     solid = np.zeros((X, Y, Z), np.uint8)
     solid[6:10, 5:9, 60:140] = 1                # words 2 and 3 of these rows are all solid; words 0, 5, 6 of every row are ordinary
     solid[7, 6, 59] = 1; solid[10, 8, 100] = 1  # (not a box)
+    if bodies == 2:
+        solid[12:15, 2:12, 96:192] = 1          # a second body: words 3, 4 and 5 of its rows, a second box of all-solid words
     f = soa_state(q, X, Y, Z, 31, solid)
     lat = make(X, Y, Z, engine=lb.ENGINE_INPLACE, tau=0.7, q=q, bc=bc, moment_mode=lb.MOMENT_STANDARD, eq_precision=lb.EQ_FP32,
                boundary_mode=lb.BOUNDARY_BOUNCE_BACK)
@@ -570,9 +573,11 @@ def test_inplace_engine_with_a_compact_body(bc):
     lat.load_populations(f)
     lat.setReflectionData(lb.ReflectionData())
     st = lat.stats()
-    assert st["words_dead"] == 4 * 4 * 2 and st["words_special"] > 0 and st["words_total"] > 4 * (st["words_dead"] + st["words_special"])
+    assert st["words_dead"] == 4 * 4 * 2 + (bodies - 1) * 3 * 10 * 3 and st["words_special"] > 0
+    assert st["words_total"] > 2 * (st["words_dead"] + st["words_special"])
     force = np.zeros(3, np.float64)
     state = f
+    c = O.DIRECTIONS[:q].astype(np.float64)
     for step in range(1, 7):
         lat.step(1)
         state = O.step_soa(state, X, Y, Z, q, 0.7, bc=bc, solid=solid, moment=O.MOMENT_STANDARD, eq64=False, steps=1, force=force)
@@ -580,6 +585,13 @@ def test_inplace_engine_with_a_compact_body(bc):
         assert rel_err(got, state) <= REL, "step %d" % step
         assert np.all(got[:, solid.astype(bool)] == 0)
         assert np.allclose(lat.force_f64(), force, rtol=1e-4, atol=1e-4), "step %d" % step
+        # the diagnostics read either storage form (odd / even step count), with short cuts for ordinary words
+        s64 = state.astype(np.float64)
+        assert lat.mass() == pytest.approx(float(s64.sum()), rel=1e-6), "step %d" % step
+        rho, ux, uy, uz = lat.moments()
+        assert np.allclose(rho, s64.sum(axis=0), rtol=1e-5, atol=1e-6), "step %d" % step
+        assert np.allclose(ux * rho, (s64 * c[:, 0, None, None, None]).sum(axis=0), rtol=1e-4, atol=1e-5), "step %d" % step
+        assert np.allclose(uz * rho, (s64 * c[:, 2, None, None, None]).sum(axis=0), rtol=1e-4, atol=1e-5), "step %d" % step
     lat.close()
 
 
